@@ -57,9 +57,11 @@ class _Base:
         for n in ("num_ground", "num_nonground"):
             f(n).argtypes = [vp]; f(n).restype = C.c_int64
         for n in ("ground_indices", "nonground_indices", "ground_xyz", "nonground_xyz", "centers", "normals"):
-            f(n).argtypes = [vp, vp]; f(n).restype = None
+            if hasattr(lib, pfx + n):
+                f(n).argtypes = [vp, vp]; f(n).restype = None
         f("num_patches").argtypes = [vp]; f("num_patches").restype = C.c_int
-        f("height").argtypes = [vp]; f("height").restype = C.c_double
+        if hasattr(lib, pfx + "height"):
+            f("height").argtypes = [vp]; f("height").restype = C.c_double
         f("get_state").argtypes = [vp, C.POINTER(PwppState)]; f("get_state").restype = None
         f("history").argtypes = [vp, C.c_int, C.c_int, vp]; f("history").restype = None
         f("destroy").argtypes = [vp]; f("destroy").restype = None
@@ -123,6 +125,7 @@ class Oracle(_Base):
         lib.pwo_num_bins.argtypes = [C.c_void_p]; lib.pwo_num_bins.restype = C.c_int
         lib.pwo_bin_ids.argtypes = [C.c_void_p, C.c_void_p]; lib.pwo_bin_ids.restype = None
         lib.pwo_bin_results.argtypes = [C.c_void_p, C.c_void_p]; lib.pwo_bin_results.restype = None
+        lib.pwo_bin_min_fit_n.argtypes = [C.c_void_p, C.c_void_p]; lib.pwo_bin_min_fit_n.restype = None
         self._lib = lib
         self.params = params if params is not None else default_params()
         self._h = lib.pwo_create(C.byref(self.params), arith)
@@ -133,6 +136,12 @@ class Oracle(_Base):
     def bin_ids(self) -> np.ndarray:
         out = np.empty(self._n, dtype=np.uint16)
         self._lib.pwo_bin_ids(self._h, out.ctypes.data)
+        return out
+
+    def bin_min_fit_n(self) -> np.ndarray:
+        """Per bin: smallest non-empty point set given to estimate_plane (INT32_MAX if never fitted)."""
+        out = np.empty(self.nbins, dtype=np.int32)
+        self._lib.pwo_bin_min_fit_n(self._h, out.ctypes.data)
         return out
 
     def bin_results(self):

@@ -88,6 +88,7 @@ typedef struct pwo {
   /* diagnostics */
   uint16_t* bin_ids; int64_t n_pts;
   pwpp_bin_result* bres;
+  int32_t* min_fit_n; int cur_bin; /* per bin: smallest non-empty point set handed to estimate_plane */
   pt_t* msort_tmp; size_t msort_cap;
 } pwo;
 
@@ -183,6 +184,7 @@ DEFINE_JSVD(double, jsvd3d, sqrt, fabs, DBL_MIN, DBL_EPSILON, NAN)
 static void estimate_plane(pwo* o, const pvec* g) {
   if (g->n == 0) return; /* S:49: members keep the previous plane */
   const size_t n = g->n;
+  if (o->cur_bin >= 0 && (int32_t) n < o->min_fit_n[o->cur_bin]) o->min_fit_n[o->cur_bin] = (int32_t) n;
   if (o->arith == PWO_ARITH_REF32) {
     float mean[3];
     for (int c = 0; c < 3; ++c) { /* colwise().mean(): sequential fp32 sum / float(n) */
@@ -384,12 +386,14 @@ void* pwo_create(const pwpp_params* p, int arith) {
   o->nbins = o->bin_base[4];
   o->czm = (pvec*) calloc((size_t) o->nbins, sizeof(pvec));
   o->bres = (pwpp_bin_result*) calloc((size_t) o->nbins, sizeof(pwpp_bin_result));
+  o->min_fit_n = (int32_t*) calloc((size_t) o->nbins, sizeof(int32_t));
+  o->cur_bin = -1;
   return o;
 }
 void pwo_destroy(void* h) {
   pwo* o = (pwo*) h;
   for (int b = 0; b < o->nbins; ++b) free(o->czm[b].p);
-  free(o->czm); free(o->bres); free(o->bin_ids); free(o->msort_tmp);
+  free(o->czm); free(o->bres); free(o->min_fit_n); free(o->bin_ids); free(o->msort_tmp);
   for (int i = 0; i < 4; ++i) { free(o->upd_flat[i].v); free(o->upd_elev[i].v); }
   free(o->ground_pc.p); free(o->rw_ground.p); free(o->rw_nonground.p); free(o->src_wo.p); free(o->src_tmp.p);
   free(o->cloud_ground.p); free(o->cloud_nonground.p); free(o->centers.p); free(o->normals.p);
@@ -455,6 +459,7 @@ void pwo_estimate(void* h, const float* pts, int64_t n, int cols) {
   candidate_t* cands = NULL; size_t ncand = 0, capcand = 0;
   dvec ringwise_flatness = { 0, 0, 0 };
   memset(o->bres, 0, (size_t) o->nbins * sizeof(pwpp_bin_result));
+  for (int b = 0; b < o->nbins; ++b) o->min_fit_n[b] = INT32_MAX;
 
   for (int zone_idx = 0; zone_idx < P->num_zones; ++zone_idx) {
     for (int ring_idx = 0; ring_idx < P->num_rings_each_zone[zone_idx]; ++ring_idx) {
@@ -469,7 +474,9 @@ void pwo_estimate(void* h, const float* pts, int64_t n, int cols) {
           continue;
         }
         msort(o, bin->p, bin->n); /* S:199 */
+        o->cur_bin = b;
         extract_piecewiseground(o, zone_idx, bin, &o->rw_ground, &o->rw_nonground); /* S:206 */
+        o->cur_bin = -1;
         pt_t cq = { (float) o->mean[0], (float) o->mean[1], (float) o->mean[2], -1 };
         pt_t nq = { (float) o->normal[0], (float) o->normal[1], (float) o->normal[2], -1 };
         pv_push(&o->centers, cq); pv_push(&o->normals, nq); /* S:211-212 */
@@ -560,4 +567,8 @@ void pwo_history(void* h, int ring, int which, double* dst) {
   if (v->n) memcpy(dst, v->v, v->n * sizeof(double));
 }
 void pwo_bin_ids(void* h, uint16_t* dst) { pwo* o = (pwo*) h; memcpy(dst, o->bin_ids, (size_t) o->n_pts * sizeof(uint16_t)); }
+/* Diagnostic: per bin, the smallest non-empty point set that estimate_plane (S:47-75) was given. Fewer than 3
+ * points make the covariance rank deficient: the "normal" is then a null-space vector chosen by rounding noise
+ * (in the reference's fp32 arithmetic as well), so such patches are excluded from cross-arithmetic comparisons. */
+void pwo_bin_min_fit_n(void* h, int32_t* dst) { pwo* o = (pwo*) h; memcpy(dst, o->min_fit_n, (size_t) o->nbins * sizeof(int32_t)); }
 void pwo_bin_results(void* h, pwpp_bin_result* dst) { pwo* o = (pwo*) h; memcpy(dst, o->bres, (size_t) o->nbins * sizeof(pwpp_bin_result)); }

@@ -1,0 +1,67 @@
+"""Builds the product's native code IN-TREE (the .so files travel to the GPU box with the snapshot).
+
+  lib/libpwpp_b200.so    CUDA kernels + C-ABI (csrc/pwpp_capi.cu), sm_100a only
+  lib/pypatchworkpp*.so  pybind11 module mirroring the reference binding (python/pybinding.cpp)
+
+No torch, no JIT cache: plain nvcc / g++ invocations.
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "lib")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_core(force=False, verbose=False):
+    os.makedirs(LIB, exist_ok=True)
+    src = os.path.join(HERE, "csrc", "pwpp_capi.cu")
+    deps = [src, os.path.join(HERE, "csrc", "pwpp_kernels.cuh"), os.path.join(HERE, "csrc", "pwpp_math.cuh"),
+            os.path.join(REPO, "include", "pwpp.h")]
+    out = os.path.join(LIB, "libpwpp_b200.so")
+    if force or _newer(out, deps):
+        cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+               "-I" + os.path.join(REPO, "include"), "-I" + os.path.join(HERE, "csrc"), "-cudart", "static", "-o", out, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return out
+
+
+def build_pybind(force=False):
+    import pybind11
+    os.makedirs(LIB, exist_ok=True)
+    src = os.path.join(HERE, "python", "pybinding.cpp")
+    hdr = os.path.join(REPO, "include", "patchwork", "patchworkpp.h")
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    out = os.path.join(LIB, "pypatchworkpp" + ext)
+    core = build_core()
+    if force or _newer(out, [src, hdr, core]):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+               "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+               "-I" + os.path.join(REPO, "include"), src, "-o", out,
+               "-L" + LIB, "-lpwpp_b200", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+    return out
+
+
+def build_all(force=False):
+    build_core(force)
+    build_pybind(force)
+
+
+if __name__ == "__main__":
+    build_core(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--core-only" not in sys.argv:
+        build_pybind(force="--force" in sys.argv)

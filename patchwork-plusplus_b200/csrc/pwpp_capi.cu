@@ -1,0 +1,577 @@
+// pwpp_capi.cu — implementation of the C-ABI declared in include/pwpp.h (libpwpp_b200.so).
+// Host side only orchestrates: every stage of estimateGround() runs in the kernels of pwpp_kernels.cuh.
+// There is no CPU fallback; without a CUDA device pwpp_create() fails with PWPP_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pwpp.h"
+#include "pwpp_kernels.cuh"
+#include "pwpp_host.hpp"
+
+using namespace pwpp;
+
+static_assert(sizeof(BinFit) == sizeof(pwpp_bin_result), "BinFit must mirror pwpp_bin_result");
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                         \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      return fail(PWPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                                        \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct pwpp_ctx {
+  pwpp_params prm;
+  Geometry g;
+  AlgoParams ap;
+  int device = 0;
+  int num_streams = 0;
+  int nbp = 0;      // padded number of bins incl. pseudo-bins
+  int hcap = 0;     // history row capacity (doubles)
+  bool fast_bin = true;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // persistent per-stream state
+  DevBuf<StreamState> d_states;
+  DevBuf<double> d_hist;
+
+  // per-call work buffers
+  DevBuf<float4> d_in;            // host path only
+  DevBuf<long long> d_pt_off;     // [F+1]
+  DevBuf<int> d_chunk_off;        // [F+1]
+  DevBuf<unsigned short> d_bin_ids;
+  DevBuf<unsigned short> d_chist;
+  DevBuf<unsigned int> d_cbase;
+  DevBuf<int> d_bin_off;          // [F][nbp+1]
+  DevBuf<float4> d_sorted;
+  DevBuf<int> d_part;
+  DevBuf<BinFit> d_fits;          // [F][nbins]
+  DevBuf<BinSeg> d_segs;          // [F][nbins+3]
+  DevBuf<int> d_out_idx;
+  DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
+  DevBuf<float> d_centers, d_normals;  // [F][nbins][3]
+  DevBuf<float> d_xyz;            // gather scratch
+
+  PinBuf<float4> h_in;
+  PinBuf<long long> h_pt_off;
+  PinBuf<int> h_chunk_off;
+  PinBuf<int> h_out_idx;
+  PinBuf<int> h_counts;
+  PinBuf<float> h_centers, h_normals;
+
+  // description of the last call
+  int last_nframes = 0;
+  long long last_total = 0;
+  std::vector<long long> pt_off;  // host copy
+  const float4* last_pts = nullptr;  // device pointer of the input of the last call
+  bool counts_fetched = false, idx_fetched = false, patches_fetched = false;
+  double last_time_us = 0.0;
+  cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int validate_params(const pwpp_params* p) {
+  if (!p) return fail(PWPP_ERR_INVALID_ARG, "params is NULL");
+  if (p->num_zones != PWPP_NUM_ZONES) return fail(PWPP_ERR_UNSUPPORTED, "num_zones must be 4 (the reference hard-wires four zones, patchworkpp.h:127-134)");
+  if (p->num_rings_of_interest < 0 || p->num_rings_of_interest > PWPP_MAX_RINGS_OF_INTEREST)
+    return fail(PWPP_ERR_UNSUPPORTED, "num_rings_of_interest must be in [0,4] (patchworkpp.h:174-175 holds 4 histories)");
+  if (p->num_iter < 1 || p->num_iter > MAX_RVPF) return fail(PWPP_ERR_UNSUPPORTED, "num_iter must be in [1,8]");
+  if (p->num_lpr < 1 || p->num_lpr > MAX_LPR) return fail(PWPP_ERR_UNSUPPORTED, "num_lpr must be in [1,64]");
+  if (!(p->th_seeds > 0) || !(p->th_seeds_v > 0)) return fail(PWPP_ERR_UNSUPPORTED, "th_seeds and th_seeds_v must be > 0");
+  if (!(p->max_range > p->min_range) || !(p->min_range >= 0)) return fail(PWPP_ERR_INVALID_ARG, "need 0 <= min_range < max_range");
+  if (p->max_flatness_storage < 1 || p->max_elevation_storage < 1) return fail(PWPP_ERR_INVALID_ARG, "max_*_storage must be >= 1");
+  long long nb = 0;
+  for (int k = 0; k < 4; ++k) {
+    if (p->num_rings_each_zone[k] < 1 || p->num_sectors_each_zone[k] < 1 || p->num_sectors_each_zone[k] > 1024)
+      return fail(PWPP_ERR_UNSUPPORTED, "rings per zone must be >= 1 and sectors per zone in [1,1024]");
+    nb += (long long) p->num_rings_each_zone[k] * p->num_sectors_each_zone[k];
+  }
+  if (nb + PW_NUM_PSEUDO > 4096) return fail(PWPP_ERR_UNSUPPORTED, "more than 4093 bins are not supported");
+  return PWPP_OK;
+}
+
+int bind_device(pwpp_ctx* ctx) {
+  CU_TRY(cudaSetDevice(ctx->device));
+  return PWPP_OK;
+}
+
+// launches the whole path for nframes frames whose packed float4 points start at d_pts
+int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity, cudaStream_t s) {
+  const long long total = ctx->pt_off[nframes];
+  int max_chunks = 0, total_chunks = 0;
+  CU_TRY(ctx->h_pt_off.reserve(nframes + 1));
+  CU_TRY(ctx->h_chunk_off.reserve(nframes + 1));
+  for (int f = 0; f < nframes; ++f) {
+    const long long n = ctx->pt_off[f + 1] - ctx->pt_off[f];
+    if (n < 0 || n > 0x7fffffffLL - CHUNK_PTS) return fail(PWPP_ERR_INVALID_ARG, "frame size out of range");
+    const int nch = (int) ((n + CHUNK_PTS - 1) / CHUNK_PTS);
+    ctx->h_pt_off.p[f] = ctx->pt_off[f];
+    ctx->h_chunk_off.p[f] = total_chunks;
+    total_chunks += nch;
+    max_chunks = std::max(max_chunks, nch);
+  }
+  ctx->h_pt_off.p[nframes] = total;
+  ctx->h_chunk_off.p[nframes] = total_chunks;
+
+  const int nb = ctx->g.nbins, nbp = ctx->nbp, nb_all = nb + PW_NUM_PSEUDO;
+  CU_TRY(ctx->d_pt_off.reserve(nframes + 1));
+  CU_TRY(ctx->d_chunk_off.reserve(nframes + 1));
+  CU_TRY(ctx->d_bin_ids.reserve((size_t) total));
+  CU_TRY(ctx->d_chist.reserve((size_t) total_chunks * nbp));
+  CU_TRY(ctx->d_cbase.reserve((size_t) total_chunks * nbp));
+  CU_TRY(ctx->d_bin_off.reserve((size_t) nframes * (nbp + 1)));
+  CU_TRY(ctx->d_sorted.reserve((size_t) total));
+  CU_TRY(ctx->d_part.reserve((size_t) total));
+  CU_TRY(ctx->d_fits.reserve((size_t) nframes * nb));
+  CU_TRY(ctx->d_segs.reserve((size_t) nframes * nb_all));
+  CU_TRY(ctx->d_out_idx.reserve((size_t) total));
+  CU_TRY(ctx->d_counts.reserve((size_t) 3 * ctx->num_streams));
+  CU_TRY(ctx->d_centers.reserve((size_t) nframes * nb * 3));
+  CU_TRY(ctx->d_normals.reserve((size_t) nframes * nb * 3));
+
+  CU_TRY(cudaMemcpyAsync(ctx->d_pt_off.p, ctx->h_pt_off.p, (nframes + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(ctx->d_chunk_off.p, ctx->h_chunk_off.p, (nframes + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+
+  FrameTable ft{ctx->d_pt_off.p, ctx->d_chunk_off.p};
+  if (max_chunks > 0) {
+    dim3 grid(max_chunks, nframes);
+    if (ctx->fast_bin)
+      k_bin_hist<true><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, ctx->d_states.p, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
+    else
+      k_bin_hist<false><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, ctx->d_states.p, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
+  }
+  k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, ctx->d_chist.p, ctx->d_cbase.p, ctx->d_bin_off.p);
+  if (max_chunks > 0) {
+    dim3 grid(max_chunks, nframes);
+    k_scatter<<<grid, CHUNK_THREADS, (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int), s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
+  }
+  {
+    const long long items = (long long) nframes * nb_all;
+    const int blocks = (int) ((items + 3) / 4);
+    k_fit<<<blocks, 128, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nframes, nbp, ctx->d_bin_off.p, ctx->d_part.p, ctx->d_fits.p);
+  }
+  int* d_ng = ctx->d_counts.p;
+  int* d_np = ctx->d_counts.p + ctx->num_streams;
+  int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams;
+  k_gle<<<nframes, 32, 0, s>>>(ft, ctx->d_states.p, ctx->d_hist.p, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, d_ng, d_np,
+                               ctx->d_centers.p, ctx->d_normals.p, d_nd);
+  if (max_chunks > 0) {
+    dim3 grid(max_chunks, nframes);
+    k_emit<<<grid, 256, (nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_out_idx.p);
+  }
+  CU_TRY(cudaGetLastError());
+  ctx->last_nframes = nframes;
+  ctx->last_total = total;
+  ctx->last_pts = d_pts;
+  ctx->last_stream = s;
+  ctx->counts_fetched = ctx->idx_fetched = ctx->patches_fetched = false;
+  return PWPP_OK;
+}
+
+int check_frame(pwpp_ctx* ctx, int f) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  if (f < 0 || f >= ctx->last_nframes) return fail(PWPP_ERR_INVALID_ARG, "frame index outside the last estimate call");
+  return PWPP_OK;
+}
+
+int fetch_counts(pwpp_ctx* ctx) {
+  if (ctx->counts_fetched) return PWPP_OK;
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  CU_TRY(ctx->h_counts.reserve((size_t) 3 * ctx->num_streams));
+  CU_TRY(cudaMemcpyAsync(ctx->h_counts.p, ctx->d_counts.p, (size_t) 3 * ctx->num_streams * sizeof(int), cudaMemcpyDeviceToHost, ctx->last_stream));
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  ctx->counts_fetched = true;
+  return PWPP_OK;
+}
+int fetch_indices(pwpp_ctx* ctx) {
+  if (ctx->idx_fetched) return PWPP_OK;
+  int rc = fetch_counts(ctx);
+  if (rc) return rc;
+  CU_TRY(ctx->h_out_idx.reserve((size_t) std::max<long long>(ctx->last_total, 1)));
+  if (ctx->last_total > 0)
+    CU_TRY(cudaMemcpyAsync(ctx->h_out_idx.p, ctx->d_out_idx.p, (size_t) ctx->last_total * sizeof(int), cudaMemcpyDeviceToHost, ctx->last_stream));
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  ctx->idx_fetched = true;
+  return PWPP_OK;
+}
+int fetch_patches(pwpp_ctx* ctx) {
+  if (ctx->patches_fetched) return PWPP_OK;
+  int rc = fetch_counts(ctx);
+  if (rc) return rc;
+  const size_t n = (size_t) ctx->last_nframes * ctx->g.nbins * 3;
+  CU_TRY(ctx->h_centers.reserve(n));
+  CU_TRY(ctx->h_normals.reserve(n));
+  CU_TRY(cudaMemcpyAsync(ctx->h_centers.p, ctx->d_centers.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->last_stream));
+  CU_TRY(cudaMemcpyAsync(ctx->h_normals.p, ctx->d_normals.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->last_stream));
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  ctx->patches_fetched = true;
+  return PWPP_OK;
+}
+
+inline int frame_n(const pwpp_ctx* ctx, int f) { return (int) (ctx->pt_off[f + 1] - ctx->pt_off[f]); }
+
+}  // namespace
+
+extern "C" {
+
+void pwpp_params_default(pwpp_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->verbose = 0; p->enable_RNR = 1; p->enable_RVPF = 1; p->enable_TGR = 1;            // patchworkpp.h:80-83
+  p->num_iter = 3; p->num_lpr = 20; p->num_min_pts = 10; p->num_zones = 4; p->num_rings_of_interest = 4;  // :85-89
+  p->RNR_ver_angle_thr = -15.0; p->RNR_intensity_thr = 0.2;                             // :91-92
+  p->sensor_height = 1.723; p->th_seeds = 0.125; p->th_dist = 0.125; p->th_seeds_v = 0.25; p->th_dist_v = 0.1;  // :94-98
+  p->max_range = 80.0; p->min_range = 2.7; p->uprightness_thr = 0.707; p->adaptive_seed_selection_margin = -1.2;  // :99-102
+  p->intensity_thr = 0.0;
+  const int sectors[4] = {16, 32, 54, 32}, rings[4] = {2, 4, 4, 4};                     // :104-105
+  for (int k = 0; k < 4; ++k) { p->num_sectors_each_zone[k] = sectors[k]; p->num_rings_each_zone[k] = rings[k]; p->elevation_thr[k] = 0; p->flatness_thr[k] = 0; }
+  p->max_flatness_storage = 1000; p->max_elevation_storage = 1000;                      // :107-108
+}
+
+const char* pwpp_last_error(void) { return g_last_error.c_str(); }
+int pwpp_abi_version(void) { return PWPP_ABI_VERSION; }
+int pwpp_num_bins(const pwpp_ctx* ctx) { return ctx ? ctx->g.nbins : 0; }
+
+int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t max_points_per_frame, pwpp_ctx** out) {
+  if (!out) return fail(PWPP_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int rc = validate_params(params);
+  if (rc) return rc;
+  if (num_streams < 1 || num_streams > 65535) return fail(PWPP_ERR_INVALID_ARG, "num_streams must be in [1,65535]");
+  if (max_points_per_frame < 0) return fail(PWPP_ERR_INVALID_ARG, "max_points_per_frame < 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PWPP_ERR_NO_DEVICE, std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                        "); this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(PWPP_ERR_INVALID_ARG, "device index out of range");
+  pwpp_ctx* ctx = new pwpp_ctx();
+  ctx->prm = *params;
+  ctx->device = device;
+  ctx->num_streams = num_streams;
+  build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
+  ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
+  int max_sectors = 0;
+  for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
+  ctx->hcap = std::max(params->max_elevation_storage, params->max_flatness_storage) + 4 * max_sectors + 64;
+#define CU_TRY_CTX(expr)                                                                                  \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);                                 \
+      pwpp_destroy(ctx);                                                                                  \
+      return fail(PWPP_ERR_CUDA, m);                                                                      \
+    }                                                                                                     \
+  } while (0)
+  CU_TRY_CTX(cudaSetDevice(device));
+  CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU_TRY_CTX(cudaEventCreate(&ctx->ev0));
+  CU_TRY_CTX(cudaEventCreate(&ctx->ev1));
+  CU_TRY_CTX(ctx->d_states.reserve(num_streams));
+  CU_TRY_CTX(ctx->d_hist.reserve((size_t) num_streams * 2 * 4 * ctx->hcap));
+  CU_TRY_CTX(ctx->d_counts.reserve((size_t) 3 * num_streams));
+  {
+    const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
+    if (scat > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+  }
+  *out = ctx;
+  rc = pwpp_reset_all(ctx);
+  if (rc) { pwpp_destroy(ctx); *out = nullptr; return rc; }
+  if (max_points_per_frame > 0) {
+    const size_t tot = (size_t) max_points_per_frame * num_streams;
+    CU_TRY_CTX(ctx->d_bin_ids.reserve(tot));
+    CU_TRY_CTX(ctx->d_sorted.reserve(tot));
+    CU_TRY_CTX(ctx->d_part.reserve(tot));
+    CU_TRY_CTX(ctx->d_out_idx.reserve(tot));
+  }
+#undef CU_TRY_CTX
+  return PWPP_OK;
+}
+
+void pwpp_destroy(pwpp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->d_states.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
+  ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
+  ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_out_idx.release(); ctx->d_counts.release();
+  ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();
+  ctx->h_in.release(); ctx->h_pt_off.release(); ctx->h_chunk_off.release(); ctx->h_out_idx.release(); ctx->h_counts.release();
+  ctx->h_centers.release(); ctx->h_normals.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int pwpp_reset_stream(pwpp_ctx* ctx, int f) {
+  if (!ctx || f < 0 || f >= ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "bad stream index");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  StreamState s;
+  init_state(ctx->prm, s);
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaMemcpy(ctx->d_states.p + f, &s, sizeof(s), cudaMemcpyHostToDevice));
+  return PWPP_OK;
+}
+int pwpp_reset_all(pwpp_ctx* ctx) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  std::vector<StreamState> v(ctx->num_streams);
+  for (auto& s : v) init_state(ctx->prm, s);
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaMemcpy(ctx->d_states.p, v.data(), v.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
+  return PWPP_OK;
+}
+
+int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, const int64_t* n, int cols, int64_t row_stride, int64_t col_stride) {
+  if (!ctx || !pts || !n) return fail(PWPP_ERR_INVALID_ARG, "NULL argument");
+  if (nframes < 1 || nframes > ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "nframes must be in [1, num_streams]");
+  if (cols != 3 && cols != 4) return fail(PWPP_ERR_INVALID_ARG, "cols must be 3 or 4 (x,y,z[,intensity])");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+  ctx->pt_off.assign(nframes + 1, 0);
+  for (int f = 0; f < nframes; ++f) {
+    if (n[f] < 0 || (n[f] > 0 && !pts[f])) return fail(PWPP_ERR_INVALID_ARG, "bad frame pointer/size");
+    ctx->pt_off[f + 1] = ctx->pt_off[f] + n[f];
+  }
+  const long long total = ctx->pt_off[nframes];
+  CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1)));
+  CU_TRY(ctx->d_in.reserve((size_t) std::max<long long>(total, 1)));
+  // stage into pinned memory as packed float4 (the private copy the reference makes by value, H:152)
+  for (int f = 0; f < nframes; ++f) {
+    float4* dst = ctx->h_in.p + ctx->pt_off[f];
+    const float* src = pts[f];
+    const int64_t cnt = n[f];
+    if (cols == 4 && col_stride == 1 && row_stride == 4) {
+      std::memcpy(dst, src, (size_t) cnt * sizeof(float4));
+    } else {
+      for (int64_t i = 0; i < cnt; ++i) {
+        const float* r = src + i * row_stride;
+        dst[i] = make_float4(r[0], r[col_stride], r[2 * col_stride], cols == 4 ? r[3 * col_stride] : 0.f);
+      }
+    }
+  }
+  cudaStream_t s = ctx->stream;
+  if (total > 0) CU_TRY(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, (size_t) total * sizeof(float4), cudaMemcpyHostToDevice, s));
+  rc = run_path(ctx, nframes, ctx->d_in.p, cols == 4 ? 1 : 0, s);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(s));
+  ctx->last_time_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  return PWPP_OK;
+}
+
+int pwpp_estimate_device(pwpp_ctx* ctx, int nframes, const void* d_pts, const int64_t* h_offsets, int has_intensity, void* cuda_stream) {
+  if (!ctx || !h_offsets) return fail(PWPP_ERR_INVALID_ARG, "NULL argument");
+  if (nframes < 1 || nframes > ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "nframes must be in [1, num_streams]");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+  ctx->pt_off.assign(nframes + 1, 0);
+  for (int f = 0; f <= nframes; ++f) {
+    ctx->pt_off[f] = h_offsets[f] - h_offsets[0];
+    if (f > 0 && ctx->pt_off[f] < ctx->pt_off[f - 1]) return fail(PWPP_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  }
+  if (ctx->pt_off[nframes] > 0 && !d_pts) return fail(PWPP_ERR_INVALID_ARG, "d_pts is NULL");
+  cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+  // the pinned frame tables of the previous call must have been consumed before they are rewritten
+  if (ctx->last_stream) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  rc = run_path(ctx, nframes, (const float4*) d_pts + h_offsets[0], has_intensity, s);
+  if (rc) return rc;
+  ctx->last_time_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  return PWPP_OK;
+}
+
+int pwpp_synchronize(pwpp_ctx* ctx) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream ? ctx->last_stream : ctx->stream));
+  return PWPP_OK;
+}
+
+int64_t pwpp_num_ground(pwpp_ctx* ctx, int f) {
+  if (check_frame(ctx, f) || fetch_counts(ctx)) return -1;
+  return ctx->h_counts.p[f];
+}
+int64_t pwpp_num_nonground(pwpp_ctx* ctx, int f) {
+  if (check_frame(ctx, f) || fetch_counts(ctx)) return -1;
+  return (int64_t) frame_n(ctx, f) - ctx->h_counts.p[f] - ctx->h_counts.p[2 * ctx->num_streams + f];
+}
+int pwpp_copy_ground_indices(pwpp_ctx* ctx, int f, int32_t* dst) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = fetch_indices(ctx);
+  if (rc) return rc;
+  const int ng = ctx->h_counts.p[f];
+  if (ng > 0) std::memcpy(dst, ctx->h_out_idx.p + ctx->pt_off[f], (size_t) ng * sizeof(int32_t));
+  return PWPP_OK;
+}
+int pwpp_copy_nonground_indices(pwpp_ctx* ctx, int f, int32_t* dst) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = fetch_indices(ctx);
+  if (rc) return rc;
+  const int ng = ctx->h_counts.p[f];
+  const int nn = frame_n(ctx, f) - ng - ctx->h_counts.p[2 * ctx->num_streams + f];
+  if (nn > 0) std::memcpy(dst, ctx->h_out_idx.p + ctx->pt_off[f] + ng, (size_t) nn * sizeof(int32_t));
+  return PWPP_OK;
+}
+
+static int copy_xyz(pwpp_ctx* ctx, int f, float* dst, bool ground) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = fetch_counts(ctx);
+  if (rc) return rc;
+  const int ng = ctx->h_counts.p[f];
+  const int nn = frame_n(ctx, f) - ng - ctx->h_counts.p[2 * ctx->num_streams + f];
+  const int cnt = ground ? ng : nn;
+  if (cnt <= 0) return PWPP_OK;
+  CU_TRY(ctx->d_xyz.reserve((size_t) cnt * 3));
+  const int* idx = ctx->d_out_idx.p + ctx->pt_off[f] + (ground ? 0 : ng);
+  k_gather_xyz<<<(cnt + 255) / 256, 256, 0, ctx->last_stream>>>(ctx->last_pts + ctx->pt_off[f], idx, cnt, ctx->d_xyz.p);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(dst, ctx->d_xyz.p, (size_t) cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->last_stream));
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  return PWPP_OK;
+}
+int pwpp_copy_ground_xyz(pwpp_ctx* ctx, int f, float* dst) { return copy_xyz(ctx, f, dst, true); }
+int pwpp_copy_nonground_xyz(pwpp_ctx* ctx, int f, float* dst) { return copy_xyz(ctx, f, dst, false); }
+
+int pwpp_num_patches(pwpp_ctx* ctx, int f) {
+  if (check_frame(ctx, f) || fetch_counts(ctx)) return -1;
+  return ctx->h_counts.p[ctx->num_streams + f];
+}
+int pwpp_copy_centers(pwpp_ctx* ctx, int f, float* dst) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = fetch_patches(ctx);
+  if (rc) return rc;
+  const int k = ctx->h_counts.p[ctx->num_streams + f];
+  if (k > 0) std::memcpy(dst, ctx->h_centers.p + (size_t) f * ctx->g.nbins * 3, (size_t) k * 3 * sizeof(float));
+  return PWPP_OK;
+}
+int pwpp_copy_normals(pwpp_ctx* ctx, int f, float* dst) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = fetch_patches(ctx);
+  if (rc) return rc;
+  const int k = ctx->h_counts.p[ctx->num_streams + f];
+  if (k > 0) std::memcpy(dst, ctx->h_normals.p + (size_t) f * ctx->g.nbins * 3, (size_t) k * 3 * sizeof(float));
+  return PWPP_OK;
+}
+
+int pwpp_get_state(pwpp_ctx* ctx, int f, pwpp_state* out) {
+  if (!ctx || !out || f < 0 || f >= ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "bad argument");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  if (ctx->last_stream) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  StreamState s;
+  CU_TRY(cudaMemcpy(&s, ctx->d_states.p + f, sizeof(s), cudaMemcpyDeviceToHost));
+  out->sensor_height = s.sensor_height;
+  for (int i = 0; i < 4; ++i) {
+    out->elevation_thr[i] = s.elevation_thr[i]; out->flatness_thr[i] = s.flatness_thr[i];
+    out->n_elevation[i] = s.n_elev[i]; out->n_flatness[i] = s.n_flat[i];
+  }
+  return PWPP_OK;
+}
+double pwpp_height(pwpp_ctx* ctx, int f) {
+  pwpp_state s;
+  if (pwpp_get_state(ctx, f, &s)) return NAN;
+  return s.sensor_height;
+}
+double pwpp_time_us(pwpp_ctx* ctx) { return ctx ? ctx->last_time_us : NAN; }
+
+int pwpp_copy_history(pwpp_ctx* ctx, int f, int ring, int which, double* dst) {
+  if (!ctx || !dst || f < 0 || f >= ctx->num_streams || ring < 0 || ring > 3 || which < 0 || which > 1) return fail(PWPP_ERR_INVALID_ARG, "bad argument");
+  pwpp_state s;
+  int rc = pwpp_get_state(ctx, f, &s);
+  if (rc) return rc;
+  const int n = which ? s.n_flatness[ring] : s.n_elevation[ring];
+  if (n > 0) CU_TRY(cudaMemcpy(dst, ctx->d_hist.p + (((size_t) f * 2 + which) * 4 + ring) * ctx->hcap, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost));
+  return PWPP_OK;
+}
+
+int pwpp_device_results(pwpp_ctx* ctx, const int32_t** d_indices, const int32_t** d_num_ground) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  if (d_indices) *d_indices = ctx->d_out_idx.p;
+  if (d_num_ground) *d_num_ground = ctx->d_counts.p;
+  return PWPP_OK;
+}
+
+int pwpp_copy_bin_results(pwpp_ctx* ctx, int f, pwpp_bin_result* dst) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = bind_device(ctx);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  CU_TRY(cudaMemcpy(dst, ctx->d_fits.p + (size_t) f * ctx->g.nbins, (size_t) ctx->g.nbins * sizeof(BinFit), cudaMemcpyDeviceToHost));
+  return PWPP_OK;
+}
+int pwpp_copy_bin_ids(pwpp_ctx* ctx, int f, uint16_t* dst) {
+  int rc = check_frame(ctx, f);
+  if (rc) return rc;
+  rc = bind_device(ctx);
+  if (rc) return rc;
+  CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  const int n = frame_n(ctx, f);
+  if (n > 0) CU_TRY(cudaMemcpy(dst, ctx->d_bin_ids.p + ctx->pt_off[f], (size_t) n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  return PWPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// pwpp_math.cuh — scalar math of the ground-segmentation path, shared by every kernel.
+//
+// Everything here is __host__ __device__ so that tests/host_math_test.cu can run the exact same
+// code on the CPU (nvcc host pass) against the oracle before it ever runs on a GPU.
+//
+// Arithmetic contract ("CANON64"): the reference's formulas
+// (cpp/patchworkpp/src/patchworkpp.cpp, "S:") evaluated in IEEE double with every operation
+// rounded separately (no FMA contraction: __dmul_rn/__dadd_rn/... on the device, -ffp-contract=off
+// on the host), so that given identical inputs the device and the CPU oracle produce identical bits.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define PW_HD __host__ __device__ __forceinline__
+#else
+#define PW_HD inline
+#endif
+
+namespace pwpp {
+
+// ---- separately rounded double ops ---------------------------------------------------------------
+PW_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+PW_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+PW_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+PW_HD double ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+PW_HD double dsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  return __dsqrt_rn(a);
+#else
+  return sqrt(a);
+#endif
+}
+PW_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+PW_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+PW_HD float fsqrt(float a) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+
+#define PW_PI 3.14159265358979323846 /* M_PI, reference patchworkpp.h:4-6 */
+
+// ---- concentric-zone geometry + thresholds (reference Params, H:42-112, and ctor H:120-134) -------
+struct Geometry {
+  double min_ranges[4];    // H:122-125
+  double ring_sizes[4];    // H:127-130
+  double sector_sizes[4];  // H:131-134
+  double max_range, min_range;
+  int num_rings[4], num_sectors[4];
+  int bin_base[5];         // first bin id of each zone in (zone, ring, sector) order
+  int concentric_base[5];  // first concentric ring index of each zone
+  int nbins;               // 504 with the defaults
+  // float copies for the filtered fast path of bin_of_point()
+  float f_min_ranges[4], f_ring_sizes[4], f_sector_sizes[4], f_max_range;
+};
+
+struct AlgoParams {
+  double RNR_ver_angle_thr, RNR_intensity_thr;
+  double th_seeds, th_seeds_v, th_dist, th_dist_v;
+  double uprightness_thr, adaptive_seed_selection_margin;
+  int num_iter, num_lpr, num_min_pts, num_rings_of_interest;
+  int enable_RNR, enable_RVPF, enable_TGR;
+  int max_flatness_storage, max_elevation_storage;
+};
+
+// Pseudo-bins after the nbins real ones (see include/pwpp.h pwpp_copy_bin_ids)
+#define PW_BIN_RNR(nb) ((nb))        /* reflected noise, S:391-396 -> nonground            */
+#define PW_BIN_OOR(nb) ((nb) + 1)    /* outside (min_range, max_range], S:617-619 -> nonground */
+#define PW_BIN_DROP(nb) ((nb) + 2)   /* input z == FLT_MIN: vanishes from both outputs, S:591  */
+#define PW_NUM_PSEUDO 3
+
+// reflected_noise_removal predicate, S:385-391. r is computed in float like the reference does.
+PW_HD bool rnr_hit(float x, float y, float z, float intensity, double sensor_height, const AlgoParams& ap) {
+  const double zd = (double) z;
+  // cheap conjuncts first (pure predicates, order does not matter): S:391
+  if (!(zd < dsub(-sensor_height, 0.8))) return false;
+  if (!((double) intensity < ap.RNR_intensity_thr)) return false;
+  const float rf = fsqrt(fadd(fmul(x, x), fmul(y, y)));          // S:387 (float ops, std::sqrt(float))
+  const double ang = ddiv(dmul(atan2(zd, (double) rf), 180.0), PW_PI);  // S:389
+  return ang < ap.RNR_ver_angle_thr;
+}
+
+// pc2czm for one point, S:587-619 in double exactly as written. Returns the bin id, or
+// PW_BIN_OOR(nbins) when the point is outside (min_range, max_range] or has a non-finite z
+// (defined behaviour where the reference would sort NaNs, see oracle/pwpp_oracle.c header).
+PW_HD int bin_of_point_exact(float x, float y, float z, const Geometry& g) {
+  const double xd = (double) x, yd = (double) y;
+  const double r = dsqrt(dadd(dmul(xd, xd), dmul(yd, yd)));  // xy2radius S:573-576
+  if (!((r <= g.max_range) && (r > g.min_range)) || !(fabsf(z) <= FLT_MAX)) return PW_BIN_OOR(g.nbins);
+  double theta = atan2(yd, xd);                              // xy2theta S:568-571
+  theta = theta > 0 ? theta : dadd(2 * PW_PI, theta);
+  const int k = (r < g.min_ranges[1]) ? 0 : (r < g.min_ranges[2]) ? 1 : (r < g.min_ranges[3]) ? 2 : 3;
+  int ring = (int) ddiv(dsub(r, g.min_ranges[k]), g.ring_sizes[k]);
+  ring = ring < g.num_rings[k] - 1 ? ring : g.num_rings[k] - 1;
+  int sector = (int) ddiv(theta, g.sector_sizes[k]);
+  sector = sector < g.num_sectors[k] - 1 ? sector : g.num_sectors[k] - 1;
+  return g.bin_base[k] + ring * g.num_sectors[k] + sector;
+}
+
+// Same decision through an fp32 filter: float radius / atan2f decide the bin whenever the float
+// values are farther from every decision boundary than a guard band that is >= 6x the worst-case
+// float error (sqrtf/atan2f <= 3 ulp, CUDA math API accuracy table); only points inside a guard
+// band (~3e-4 of a KITTI scan) pay for the double sqrt/atan2/div of the exact path. The result is
+// identical to bin_of_point_exact by construction.
+PW_HD int bin_of_point(float x, float y, float z, const Geometry& g) {
+  const float GUARD_R = 2e-4f;   // metres; float radius error at 80 m is < 2e-5
+  const float GUARD_U = 2e-4f;   // ring / sector units
+  const float r2 = x * x + y * y;
+  const float rf = sqrtf(r2);
+  if (!(rf < 1e6f) || !(fabsf(z) <= FLT_MAX)) return bin_of_point_exact(x, y, z, g);  // NaN/Inf/huge
+  if (rf > g.f_max_range + GUARD_R || rf < g.f_min_ranges[0] - GUARD_R) return PW_BIN_OOR(g.nbins);
+  bool amb = fabsf(rf - g.f_max_range) <= GUARD_R || fabsf(rf - g.f_min_ranges[0]) <= GUARD_R ||
+             fabsf(rf - g.f_min_ranges[1]) <= GUARD_R || fabsf(rf - g.f_min_ranges[2]) <= GUARD_R ||
+             fabsf(rf - g.f_min_ranges[3]) <= GUARD_R;
+  const int k = (rf < g.f_min_ranges[1]) ? 0 : (rf < g.f_min_ranges[2]) ? 1 : (rf < g.f_min_ranges[3]) ? 2 : 3;
+  const float uf = (rf - g.f_min_ranges[k]) / g.f_ring_sizes[k];
+  const float ur = rintf(uf);
+  amb = amb || fabsf(uf - ur) <= GUARD_U;
+  float tf = atan2f(y, x);
+  amb = amb || fabsf(tf) <= 1e-5f;
+  tf = tf > 0.f ? tf : tf + 6.28318530717958647692f;
+  const float sf = tf / g.f_sector_sizes[k];
+  const float sr = rintf(sf);
+  amb = amb || fabsf(sf - sr) <= GUARD_U;
+  if (amb) return bin_of_point_exact(x, y, z, g);
+  int ring = (int) uf;
+  ring = ring < g.num_rings[k] - 1 ? ring : g.num_rings[k] - 1;
+  int sector = (int) sf;
+  sector = sector < g.num_sectors[k] - 1 ? sector : g.num_sectors[k] - 1;
+  return g.bin_base[k] + ring * g.num_sectors[k] + sector;
+}
+
+// ---- plane of a point set -------------------------------------------------------------------------
+struct Plane {
+  double mean[3];    // pc_mean_           S:59-60
+  double normal[3];  // normal_, z >= 0    S:66-68
+  double sv[3];      // singular_values_, descending  S:63
+  double d;          // d_                 S:74
+};
+
+// rotation in the plane (Eigen/src/Jacobi/Jacobi.h apply_rotation_in_the_plane), restated as in
+// oracle/pwpp_oracle.c DEFINE_JSVD: x_i <- c x_i + s y_i ; y_i <- -s x_i + c y_i
+#define PW_ROT(X, Y, C, S)                                         \
+  {                                                                \
+    const double _xi = (X), _yi = (Y);                             \
+    (X) = dadd(dmul((C), _xi), dmul((S), _yi));                    \
+    (Y) = dadd(-dmul((S), _xi), dmul((C), _yi));                   \
+  }
+
+// 3x3 two-sided Jacobi SVD in double, the algorithm published for Eigen 3.4.0's JacobiSVD that the
+// reference calls at S:62 (there in float), operation for operation the same as jsvd3d() in
+// oracle/pwpp_oracle.c. cov is symmetric and given by its 6 unique entries.
+// Outputs singular values (descending) and U's third column (the least singular vector).
+PW_HD void jacobi_svd3(double cxx, double cxy, double cxz, double cyy, double cyz, double czz, double sv[3], double ucol2[3]) {
+  // W(i,j) and U(i,j) kept in scalars so the whole thing lives in registers on the device
+  double W00 = cxx, W01 = cxy, W02 = cxz, W10 = cxy, W11 = cyy, W12 = cyz, W20 = cxz, W21 = cyz, W22 = czz;
+  double U00 = 1, U01 = 0, U02 = 0, U10 = 0, U11 = 1, U12 = 0, U20 = 0, U21 = 0, U22 = 1;
+  double scale = 0.0;
+  bool finite = true;
+  {
+    const double a[6] = {fabs(cxx), fabs(cxy), fabs(cxz), fabs(cyy), fabs(cyz), fabs(czz)};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (!(a[i] <= DBL_MAX)) finite = false;
+      if (a[i] > scale) scale = a[i];
+    }
+  }
+  if (!finite) {  // S:57 with one point: 0/0. Defined as U = I, singular values NaN (oracle header).
+    sv[0] = sv[1] = sv[2] = NAN;
+    ucol2[0] = 0; ucol2[1] = 0; ucol2[2] = 1;
+    return;
+  }
+  if (scale == 0.0) scale = 1.0;
+  W00 = ddiv(W00, scale); W01 = ddiv(W01, scale); W02 = ddiv(W02, scale);
+  W10 = ddiv(W10, scale); W11 = ddiv(W11, scale); W12 = ddiv(W12, scale);
+  W20 = ddiv(W20, scale); W21 = ddiv(W21, scale); W22 = ddiv(W22, scale);
+  const double precision = 2 * DBL_EPSILON, considerAsZero = DBL_MIN;
+  double maxDiag = fmax(fabs(W00), fmax(fabs(W11), fabs(W22)));
+
+// one (p,q) step; Wpp.. are lvalues naming the entries; R* are the third index r (the row/col not in {p,q})
+#define PW_JSTEP(Wpp, Wpq, Wqp, Wqq, Wpr, Wqr, Wrp, Wrq, Upp_, Upq_, Uqp_, Uqq_, Urp_, Urq_)                     \
+  {                                                                                                               \
+    double thr = dmul(precision, maxDiag);                                                                        \
+    if (considerAsZero > thr) thr = considerAsZero;                                                               \
+    if (fabs(Wpq) > thr || fabs(Wqp) > thr) {                                                                     \
+      finished = false;                                                                                           \
+      double m00 = Wpp, m01 = Wpq, m10 = Wqp, m11 = Wqq;                                                          \
+      double r1c, r1s;                                                                                            \
+      const double t = dadd(m00, m11), dd = dsub(m10, m01);                                                       \
+      if (fabs(dd) < DBL_MIN) { r1s = 0.0; r1c = 1.0; }                                                           \
+      else { const double u = ddiv(t, dd); const double tmp = dsqrt(dadd(1.0, dmul(u, u))); r1s = ddiv(1.0, tmp); r1c = ddiv(u, tmp); } \
+      if (!(r1c == 1.0 && r1s == 0.0)) { PW_ROT(m00, m10, r1c, r1s); PW_ROT(m01, m11, r1c, r1s); }                \
+      double jrc, jrs;                                                                                            \
+      const double deno = dmul(2.0, fabs(m01));                                                                   \
+      if (deno < DBL_MIN) { jrc = 1.0; jrs = 0.0; }                                                               \
+      else {                                                                                                      \
+        const double tau = ddiv(dsub(m00, m11), deno);                                                            \
+        const double w = dsqrt(dadd(dmul(tau, tau), 1.0));                                                        \
+        const double tn = (tau > 0.0) ? ddiv(1.0, dadd(tau, w)) : ddiv(1.0, dsub(tau, w));                        \
+        const double sign_t = tn > 0.0 ? 1.0 : -1.0;                                                              \
+        const double nn = ddiv(1.0, dsqrt(dadd(dmul(tn, tn), 1.0)));                                              \
+        jrs = dmul(dmul(dmul(-sign_t, ddiv(m01, fabs(m01))), fabs(tn)), nn);                                      \
+        jrc = nn;                                                                                                 \
+      }                                                                                                           \
+      const double oc = jrc, os = -jrs;                                                                           \
+      const double jlc = dsub(dmul(r1c, oc), dmul(r1s, os)), jls = dadd(dmul(r1c, os), dmul(r1s, oc));            \
+      if (!(jlc == 1.0 && jls == 0.0)) {                                                                          \
+        /* W.applyOnTheLeft(p,q,j_left): rows p,q, columns in index order */                                      \
+        PW_ROWS_PQ(jlc, jls)                                                                                      \
+        /* U.applyOnTheRight(p,q,j_left^T): columns p,q of U, rows in index order */                              \
+        PW_UCOLS_PQ(jlc, jls)                                                                                     \
+      }                                                                                                           \
+      if (!(jrc == 1.0 && (-jrs) == 0.0)) {                                                                       \
+        /* W.applyOnTheRight(p,q,j_right): columns p,q of W with (c,-s) */                                        \
+        PW_WCOLS_PQ(jrc, -jrs)                                                                                    \
+      }                                                                                                           \
+      const double a1 = fabs(Wpp), a2 = fabs(Wqq);                                                                \
+      const double mx = a1 > a2 ? a1 : a2;                                                                        \
+      if (mx > maxDiag) maxDiag = mx;                                                                             \
+    }                                                                                                             \
+  }
+
+  bool finished = false;
+  while (!finished) {
+    finished = true;
+    // (p,q) = (1,0)
+#define PW_ROWS_PQ(C, S) PW_ROT(W10, W00, C, S) PW_ROT(W11, W01, C, S) PW_ROT(W12, W02, C, S)
+#define PW_UCOLS_PQ(C, S) PW_ROT(U01, U00, C, S) PW_ROT(U11, U10, C, S) PW_ROT(U21, U20, C, S)
+#define PW_WCOLS_PQ(C, S) PW_ROT(W01, W00, C, S) PW_ROT(W11, W10, C, S) PW_ROT(W21, W20, C, S)
+    PW_JSTEP(W11, W10, W01, W00, W12, W02, W21, W20, U11, U10, U01, U00, U21, U20)
+#undef PW_ROWS_PQ
+#undef PW_UCOLS_PQ
+#undef PW_WCOLS_PQ
+    // (p,q) = (2,0)
+#define PW_ROWS_PQ(C, S) PW_ROT(W20, W00, C, S) PW_ROT(W21, W01, C, S) PW_ROT(W22, W02, C, S)
+#define PW_UCOLS_PQ(C, S) PW_ROT(U02, U00, C, S) PW_ROT(U12, U10, C, S) PW_ROT(U22, U20, C, S)
+#define PW_WCOLS_PQ(C, S) PW_ROT(W02, W00, C, S) PW_ROT(W12, W10, C, S) PW_ROT(W22, W20, C, S)
+    PW_JSTEP(W22, W20, W02, W00, W21, W01, W12, W10, U22, U20, U02, U00, U12, U10)
+#undef PW_ROWS_PQ
+#undef PW_UCOLS_PQ
+#undef PW_WCOLS_PQ
+    // (p,q) = (2,1)
+#define PW_ROWS_PQ(C, S) PW_ROT(W20, W10, C, S) PW_ROT(W21, W11, C, S) PW_ROT(W22, W12, C, S)
+#define PW_UCOLS_PQ(C, S) PW_ROT(U02, U01, C, S) PW_ROT(U12, U11, C, S) PW_ROT(U22, U21, C, S)
+#define PW_WCOLS_PQ(C, S) PW_ROT(W02, W01, C, S) PW_ROT(W12, W11, C, S) PW_ROT(W22, W21, C, S)
+    PW_JSTEP(W22, W21, W12, W11, W20, W10, W02, W01, U22, U21, U12, U11, U02, U01)
+#undef PW_ROWS_PQ
+#undef PW_UCOLS_PQ
+#undef PW_WCOLS_PQ
+  }
+#undef PW_JSTEP
+
+  // |diag| * scale, flip U columns of negative diagonal entries
+  double s0 = fabs(W00), s1 = fabs(W11), s2 = fabs(W22);
+  if (W00 < 0.0) { U00 = dmul(U00, -1.0); U10 = dmul(U10, -1.0); U20 = dmul(U20, -1.0); }
+  if (W11 < 0.0) { U01 = dmul(U01, -1.0); U11 = dmul(U11, -1.0); U21 = dmul(U21, -1.0); }
+  if (W22 < 0.0) { U02 = dmul(U02, -1.0); U12 = dmul(U12, -1.0); U22 = dmul(U22, -1.0); }
+  s0 = dmul(s0, scale); s1 = dmul(s1, scale); s2 = dmul(s2, scale);
+  // selection sort descending with U columns swapped (only column 2 is needed at the end, but the
+  // swaps move columns around, so track all three)
+  double c0[3] = {U00, U10, U20}, c1[3] = {U01, U11, U21}, c2[3] = {U02, U12, U22};
+  // i = 0: max over (s0,s1,s2); first maximal position wins (strict >)
+  {
+    int pos = 0; double mx = s0;
+    if (s1 > mx) { mx = s1; pos = 1; }
+    if (s2 > mx) { mx = s2; pos = 2; }
+    if (mx == 0.0) { sv[0] = s0; sv[1] = s1; sv[2] = s2; ucol2[0] = c2[0]; ucol2[1] = c2[1]; ucol2[2] = c2[2]; return; }
+    if (pos == 1) { double t = s0; s0 = s1; s1 = t; for (int k = 0; k < 3; ++k) { double u = c0[k]; c0[k] = c1[k]; c1[k] = u; } }
+    else if (pos == 2) { double t = s0; s0 = s2; s2 = t; for (int k = 0; k < 3; ++k) { double u = c0[k]; c0[k] = c2[k]; c2[k] = u; } }
+  }
+  // i = 1: max over (s1,s2)
+  {
+    int pos = 0; double mx = s1;
+    if (s2 > mx) { mx = s2; pos = 1; }
+    if (mx != 0.0 && pos == 1) { double t = s1; s1 = s2; s2 = t; for (int k = 0; k < 3; ++k) { double u = c1[k]; c1[k] = c2[k]; c2[k] = u; } }
+    // i = 2: single element, nothing to swap (and mx == 0 would only break out)
+  }
+  sv[0] = s0; sv[1] = s1; sv[2] = s2;
+  ucol2[0] = c2[0]; ucol2[1] = c2[1]; ucol2[2] = c2[2];
+}
+
+// Moment sums of a point set taken relative to a reference point c (shifted one-pass covariance):
+//   s1[k] = sum (p_k - c_k),  s2 = sum (p_j - c_j)(p_k - c_k)  in order xx xy xz yy yz zz.
+struct Moments {
+  double s1[3];
+  double s2[6];
+  int n;
+};
+
+// estimate_plane (S:47-75) from the moment sums. n == 0 must be handled by the caller (S:49: keep
+// the previous plane). mean = c + s1/n ; cov = (s2 - s1 s1^T / n) / (n-1).
+PW_HD void plane_from_moments(const Moments& m, const double c[3], Plane& pl) {
+  const double n = (double) m.n;
+  const double m0 = ddiv(m.s1[0], n), m1 = ddiv(m.s1[1], n), m2 = ddiv(m.s1[2], n);
+  pl.mean[0] = dadd(c[0], m0); pl.mean[1] = dadd(c[1], m1); pl.mean[2] = dadd(c[2], m2);
+  const double dn = (double) (m.n - 1);  // n == 1 -> 0/0 = NaN, like S:57
+  const double cxx = ddiv(dsub(m.s2[0], dmul(m.s1[0], m0)), dn);
+  const double cxy = ddiv(dsub(m.s2[1], dmul(m.s1[0], m1)), dn);
+  const double cxz = ddiv(dsub(m.s2[2], dmul(m.s1[0], m2)), dn);
+  const double cyy = ddiv(dsub(m.s2[3], dmul(m.s1[1], m1)), dn);
+  const double cyz = ddiv(dsub(m.s2[4], dmul(m.s1[1], m2)), dn);
+  const double czz = ddiv(dsub(m.s2[5], dmul(m.s1[2], m2)), dn);
+  double u2[3];
+  jacobi_svd3(cxx, cxy, cxz, cyy, cyz, czz, pl.sv, u2);
+  if (u2[2] < 0.0) { u2[0] = dmul(u2[0], -1.0); u2[1] = dmul(u2[1], -1.0); u2[2] = dmul(u2[2], -1.0); }  // S:68
+  pl.normal[0] = u2[0]; pl.normal[1] = u2[1]; pl.normal[2] = u2[2];
+  // d = -(normal . mean), association x0 + (x1 + x2) (S:74 through Eigen's unrolled redux)
+  const double x0 = dmul(u2[0], pl.mean[0]), x1 = dmul(u2[1], pl.mean[1]), x2 = dmul(u2[2], pl.mean[2]);
+  pl.d = -dadd(x0, dadd(x1, x2));
+}
+
+// calc_point_to_plane_d (S:551-554) in double: ((n0*x + n1*y) + n2*z) + d
+PW_HD double point_plane_distance(const Plane& pl, float x, float y, float z) {
+  const double a = dmul(pl.normal[0], (double) x), b = dmul(pl.normal[1], (double) y), c = dmul(pl.normal[2], (double) z);
+  return dadd(dadd(dadd(a, b), c), pl.d);
+}
+
+}  // namespace pwpp
