@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the estimateGround() hot path on synthetic KITTI-64-shaped scans.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                         the reference's own CPU estimateGround on the host cores
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): a batch of 1024 synthetic KITTI-64
+frames (~120k points each) per GPU, each frame on its own FRESH stream state. A "step" is one pass of the whole path
+over that batch. Frames shard across GPUs by global frame index with no data-path collective (weak scaling).
+
+value   : frames/s with the batch resident in HBM when the timed region starts (CUDA events, max over ranks)
+e2e     : the same metric through the C-ABI host entry point with page-locked HOST buffers: host->device copy of the
+          batch and device->host read of all index lists inside the timed region
+roofline: of the slowest kernel of the step; algorithmic bytes = 20 B/point (16 B cloud read + 4 B index write,
+          SURVEY.md §8d) x points per launch / that kernel's mean CUDA-event time in the timed region
+cpu_baseline / --impl reference: the reference's patchworkpp.cpp (compiled against oracle/eigen_shim into
+          oracle/_ref/libpwref.so, unmodified control flow) on all host cores, one instance per frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "patchwork-plusplus_b200")
+for p in (PKG, os.path.join(PKG, "lib")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SEED = 20260922
+METRIC = "frames/sec (120k-pt KITTI cloud)"
+UNIT = "frames/s"
+ALGO_BYTES_PER_POINT = 20  # 16 B/pt compulsory read of the N x 4 f32 cloud + 4 B/pt int32 index write
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=1024)
+    ap.add_argument("--sensor", default="kitti64", choices=["kitti64", "ouster128"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--ref-frames-per-step", type=int, default=0, help="--impl reference: frames per step (0 = 8 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def cpu_reference_throughput(frames, seconds_budget, max_frames=None, threads=None):
+    """The reference's own estimateGround (oracle/_ref/libpwref.so) on `threads` host threads, a fresh instance per
+    frame like config 3. ctypes releases the GIL during the foreign call, so Python threads scale across cores."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle_py as O
+    kind = "reference"
+    try:
+        O.Reference().close()
+        mk = lambda: O.Reference(stable_sort=False)  # noqa: E731
+    except Exception:
+        kind = "port"
+        mk = lambda: O.Oracle(arith=O.ARITH_REF32)  # noqa: E731
+    T = threads or os.cpu_count() or 1
+    T = max(1, min(T, len(frames)))
+    done = [0] * T
+    stop_at = time.perf_counter() + seconds_budget
+    lim = len(frames) if max_frames is None else min(max_frames, len(frames))
+
+    def work(t):
+        i = t
+        while i < lim and time.perf_counter() < stop_at:
+            r = mk()
+            r.estimate(frames[i])
+            r.getGroundIndices(); r.getNongroundIndices()
+            r.close()
+            done[t] += 1
+            i += T
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    dt = time.perf_counter() - t0
+    n = sum(done)
+    return {"value": n / dt if dt > 0 else 0.0, "unit": UNIT, "cores": T, "kind": kind,
+            "sample": f"{n} frames of the same synthetic batch, fresh instance per frame, {dt:.1f} s wall on {T} threads"}, n, dt
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    import synth
+    T = os.cpu_count() or 1
+    per_step = args.ref_frames_per_step or 8 * T
+    per_step = min(per_step, args.frames_per_gpu)
+    dev = "cpu"
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = "cuda"
+    except Exception:
+        pass
+    frames = [synth.make_frame(SEED, f, args.sensor, dev).cpu().numpy() for f in range(per_step)]
+    mean_pts = sum(len(f) for f in frames) / len(frames)
+    for _ in range(args.warmup):
+        cpu_reference_throughput(frames, 1e9)
+    t0 = time.perf_counter()
+    total = 0
+    info = None
+    for _ in range(args.steps):
+        info, n, _dt = cpu_reference_throughput(frames, 1e9)
+        total += n
+    dt = time.perf_counter() - t0
+    val = total / dt
+    info["value"] = val
+    info["sample"] = f"{per_step} frames per step x {args.steps} steps, fresh instance per frame, {T} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"batch of synthetic {args.sensor} frames (~{mean_pts / 1e3:.0f}k pts), fresh state per frame; CPU sample of {per_step} frames/step",
+                   "frames_per_step": per_step, "mean_points": mean_pts},
+        "cpu_baseline": info,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import pwpp_b200
+    import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+
+    F = args.frames_per_gpu
+    dev = torch.device("cuda", local)
+    pts, offs = synth.make_batch(SEED, rank * F, F, args.sensor, dev)  # frames rank*F .. rank*F+F-1 of the global batch
+    offs_np = offs.numpy()
+    total_pts = int(offs_np[-1])
+    mean_pts = total_pts / F
+    eng = pwpp_b200.Engine(device=local, num_streams=F, max_points_per_frame=int(np.diff(offs_np).max()))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.reset()  # every frame on a fresh stream state (config 3); stream-ordered, no host sync
+        eng.estimate_device(pts.data_ptr(), offs_np, True, stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    eng.set_profiling(True)
+    launches0 = eng.launch_count()
+    stage_acc = {}
+    clocks = ClockSampler(local)
+    barrier(); torch.cuda.synchronize()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        for k, v in eng.stage_times_ms().items():  # waits for this step's last event only
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    ev1.record()
+    torch.cuda.synchronize(); barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    eng.set_profiling(False)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * F * args.steps / (ms / 1e3)
+
+    # size-independent sanity of the timed result: every frame's lists partition its points
+    ng = [eng.num_ground(f) + eng.num_nonground(f) for f in range(0, F, max(1, F // 16))]
+    assert all(a == int(offs_np[f + 1] - offs_np[f]) for a, f in zip(ng, range(0, F, max(1, F // 16)))), "partition invariant violated"
+
+    # ---- roofline of the dominant kernel ----
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    top = max(stage_ms, key=stage_ms.get)
+    peak, peak_src = measured_peak_gbs()
+    achieved = ALGO_BYTES_PER_POINT * total_pts / (stage_ms[top] / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if top in tj and tj[top].get("frames") and tj[top].get("dram_bytes"):
+                traffic = tj[top]["dram_bytes"] / tj[top]["frames"] * F
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * total_pts,
+                "stage_ms": stage_ms, "whole_path_frac": (ALGO_BYTES_PER_POINT * total_pts / (ms / args.steps / 1e3) / 1e9) / peak}
+
+    # ---- end to end through the host entry point of the C-ABI (page-locked host buffers) ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((total_pts, 4), dtype=torch.float32, pin_memory=True)
+        host.copy_(pts)
+        torch.cuda.synchronize()
+        base = host.data_ptr()
+        ptrs = [base + int(offs_np[f]) * 16 for f in range(F)]
+        ns = [int(offs_np[f + 1] - offs_np[f]) for f in range(F)]
+        sink = 0
+
+        def e2e_step():
+            nonlocal sink
+            eng.reset()
+            eng.estimate_host_strided(ptrs, ns, 4, 4, 1)      # H2D of the batch + all kernels
+            sink += int(eng.ground_indices(0)[0]) if eng.num_ground(0) else 0  # first getter pulls ALL frames' index lists D2H
+        e2e_step()
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        e2e = {"value": world * F * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": total_pts * 16 + (F + 1) * 12,
+               "d2h_bytes_per_step": total_pts * 4 + 3 * F * 4, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "api": "pwpp_estimate_host + pwpp_copy_*_indices (C-ABI), page-locked host buffers"}
+
+    # ---- CPU baseline on the host cores of this box (rank 0 only) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        T = os.cpu_count() or 1
+        nsample = min(F, max(T * 4, 64))
+        frames = [pts[int(offs_np[f]):int(offs_np[f + 1])].cpu().numpy() for f in range(nsample)]
+        cpu, _, _ = cpu_reference_throughput(frames, args.cpu_seconds)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"batch={F} synthetic {args.sensor} frames (~{mean_pts / 1e3:.0f}k pts each) per GPU, fresh stream state per frame, device-resident input",
+                       "frames_per_gpu": F, "mean_points": mean_pts, "sharding": "frames by global index, no collective",
+                       "l2": f"inputs larger than L2: {total_pts * 16 / 1e9:.2f} GB of points per step vs 126 MB L2"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

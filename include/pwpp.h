@@ -27,6 +27,7 @@
 #ifndef PWPP_H_
 #define PWPP_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -193,12 +194,30 @@ int pwpp_copy_bin_results(pwpp_ctx* ctx, int f, pwpp_bin_result* dst /* [pwpp_nu
  * 0..nbins-1, or nbins (= RNR hit, S:391-396) or nbins+1 (= outside (min_range,max_range], S:617-619). */
 int pwpp_copy_bin_ids(pwpp_ctx* ctx, int f, uint16_t* dst /* [n_f] */);
 
+/* ---- measurement hooks (not part of the reference surface) ---------------------------------- */
+
+/* Page-locked host memory for callers that have no CUDA binding of their own. pwpp_estimate_host copies
+ * straight from a caller buffer that is page-locked (allocated here, by cudaHostAlloc or registered with
+ * cudaHostRegister) and row-major N x 4; any other buffer is first staged through the ctx's pinned buffer. */
+void* pwpp_host_alloc(size_t bytes);
+void pwpp_host_free(void* p);
+
+#define PWPP_NUM_STAGES 6  /* bin_hist, bin_scan, scatter, fit, gle, emit */
+/* With profiling on, CUDA events are recorded around every kernel of the following estimate calls;
+ * pwpp_stage_times_ms() synchronizes and returns the device time of each stage of the LAST call. */
+int pwpp_set_profiling(pwpp_ctx* ctx, int enabled);
+int pwpp_stage_times_ms(pwpp_ctx* ctx, float* ms /* [PWPP_NUM_STAGES] */);
+const char* pwpp_stage_name(int stage);
+/* Number of kernels this ctx has launched since creation. */
+int64_t pwpp_launch_count(const pwpp_ctx* ctx);
+
 /* ---- temporal state (S:338-375) ---------------------------------------------------------- */
 
 int pwpp_get_state(pwpp_ctx* ctx, int f, pwpp_state* out);
 /* Histories: ring r of update_elevation_ / update_flatness_ (H:174-175); dst holds n_* doubles. */
 int pwpp_copy_history(pwpp_ctx* ctx, int f, int ring, int which /*0=elevation,1=flatness*/, double* dst);
-/* Re-initialises stream f to the constructor state (fresh PatchWorkpp instance). */
+/* Re-initialises stream f / all streams to the constructor state (a fresh PatchWorkpp instance).
+ * Stream-ordered: enqueued behind the last estimate call, no host synchronization. */
 int pwpp_reset_stream(pwpp_ctx* ctx, int f);
 int pwpp_reset_all(pwpp_ctx* ctx);
 

@@ -81,9 +81,13 @@ struct pwpp_ctx {
   bool fast_bin = true;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
+  bool profiling = false, stage_valid = false;
+  long long launches = 0;
 
   // persistent per-stream state
   DevBuf<StreamState> d_states;
+  DevBuf<StreamState> d_states_init;  // constructor state of every stream (reset source)
   DevBuf<double> d_hist;
 
   // per-call work buffers
@@ -185,32 +189,50 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   CU_TRY(cudaMemcpyAsync(ctx->d_chunk_off.p, ctx->h_chunk_off.p, (nframes + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
 
   FrameTable ft{ctx->d_pt_off.p, ctx->d_chunk_off.p};
+  const bool prof = ctx->profiling;
+  int stage = 0;
+#define STAGE_MARK() do { if (prof) CU_TRY(cudaEventRecord(ctx->stage_ev[stage], s)); ++stage; } while (0)
+  STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     if (ctx->fast_bin)
       k_bin_hist<true><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, ctx->d_states.p, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
     else
       k_bin_hist<false><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, ctx->d_states.p, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
+    ++ctx->launches;
   }
+  STAGE_MARK();
   k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, ctx->d_chist.p, ctx->d_cbase.p, ctx->d_bin_off.p);
+  ++ctx->launches;
+  STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     k_scatter<<<grid, CHUNK_THREADS, (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int), s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
+    ++ctx->launches;
   }
+  STAGE_MARK();
   {
     const long long items = (long long) nframes * nb_all;
     const int blocks = (int) ((items + 3) / 4);
     k_fit<<<blocks, 128, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nframes, nbp, ctx->d_bin_off.p, ctx->d_part.p, ctx->d_fits.p);
+    ++ctx->launches;
   }
+  STAGE_MARK();
   int* d_ng = ctx->d_counts.p;
   int* d_np = ctx->d_counts.p + ctx->num_streams;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams;
   k_gle<<<nframes, 32, 0, s>>>(ft, ctx->d_states.p, ctx->d_hist.p, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, d_ng, d_np,
                                ctx->d_centers.p, ctx->d_normals.p, d_nd);
+  ++ctx->launches;
+  STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     k_emit<<<grid, 256, (nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_out_idx.p);
+    ++ctx->launches;
   }
+  STAGE_MARK();
+#undef STAGE_MARK
+  ctx->stage_valid = prof;
   CU_TRY(cudaGetLastError());
   ctx->last_nframes = nframes;
   ctx->last_total = total;
@@ -320,7 +342,14 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev0));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev1));
+  for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
   CU_TRY_CTX(ctx->d_states.reserve(num_streams));
+  CU_TRY_CTX(ctx->d_states_init.reserve(num_streams));
+  {
+    std::vector<StreamState> v(num_streams);
+    for (auto& st : v) init_state(*params, st);
+    CU_TRY_CTX(cudaMemcpy(ctx->d_states_init.p, v.data(), v.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
+  }
   CU_TRY_CTX(ctx->d_hist.reserve((size_t) num_streams * 2 * 4 * ctx->hcap));
   CU_TRY_CTX(ctx->d_counts.reserve((size_t) 3 * num_streams));
   {
@@ -345,7 +374,8 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_states.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
+  for (int i = 0; i <= PWPP_NUM_STAGES; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
   ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_out_idx.release(); ctx->d_counts.release();
   ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();
@@ -361,22 +391,46 @@ int pwpp_reset_stream(pwpp_ctx* ctx, int f) {
   if (!ctx || f < 0 || f >= ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "bad stream index");
   int rc = bind_device(ctx);
   if (rc) return rc;
-  StreamState s;
-  init_state(ctx->prm, s);
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  CU_TRY(cudaMemcpy(ctx->d_states.p + f, &s, sizeof(s), cudaMemcpyHostToDevice));
+  cudaStream_t s = ctx->last_stream ? ctx->last_stream : ctx->stream;
+  CU_TRY(cudaMemcpyAsync(ctx->d_states.p + f, ctx->d_states_init.p + f, sizeof(StreamState), cudaMemcpyDeviceToDevice, s));
   return PWPP_OK;
 }
 int pwpp_reset_all(pwpp_ctx* ctx) {
   if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
   int rc = bind_device(ctx);
   if (rc) return rc;
-  std::vector<StreamState> v(ctx->num_streams);
-  for (auto& s : v) init_state(ctx->prm, s);
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  CU_TRY(cudaMemcpy(ctx->d_states.p, v.data(), v.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
+  cudaStream_t s = ctx->last_stream ? ctx->last_stream : ctx->stream;
+  CU_TRY(cudaMemcpyAsync(ctx->d_states.p, ctx->d_states_init.p, (size_t) ctx->num_streams * sizeof(StreamState), cudaMemcpyDeviceToDevice, s));
   return PWPP_OK;
 }
+
+void* pwpp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_last_error = "cudaMallocHost failed"; return nullptr; }
+  return p;
+}
+void pwpp_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int pwpp_set_profiling(pwpp_ctx* ctx, int enabled) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  ctx->profiling = enabled != 0;
+  ctx->stage_valid = false;
+  return PWPP_OK;
+}
+int pwpp_stage_times_ms(pwpp_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return fail(PWPP_ERR_INVALID_ARG, "NULL argument");
+  if (!ctx->stage_valid) return fail(PWPP_ERR_INVALID_ARG, "no profiled estimate call yet (pwpp_set_profiling)");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  CU_TRY(cudaEventSynchronize(ctx->stage_ev[PWPP_NUM_STAGES]));
+  for (int i = 0; i < PWPP_NUM_STAGES; ++i) CU_TRY(cudaEventElapsedTime(&ms[i], ctx->stage_ev[i], ctx->stage_ev[i + 1]));
+  return PWPP_OK;
+}
+const char* pwpp_stage_name(int stage) {
+  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit", "k_gle", "k_emit"};
+  return (stage >= 0 && stage < PWPP_NUM_STAGES) ? names[stage] : "";
+}
+int64_t pwpp_launch_count(const pwpp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, const int64_t* n, int cols, int64_t row_stride, int64_t col_stride) {
   if (!ctx || !pts || !n) return fail(PWPP_ERR_INVALID_ARG, "NULL argument");
@@ -391,14 +445,29 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
     ctx->pt_off[f + 1] = ctx->pt_off[f] + n[f];
   }
   const long long total = ctx->pt_off[nframes];
-  CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1)));
   CU_TRY(ctx->d_in.reserve((size_t) std::max<long long>(total, 1)));
-  // stage into pinned memory as packed float4 (the private copy the reference makes by value, H:152)
+  cudaStream_t s = ctx->stream;
+  // the staging buffers of the previous call must not be in flight any more
+  CU_TRY(cudaStreamSynchronize(s));
+  const bool packed = (cols == 4 && col_stride == 1 && row_stride == 4);
+  bool staged_any = false;
   for (int f = 0; f < nframes; ++f) {
+    const int64_t cnt = n[f];
+    if (cnt == 0) continue;
+    bool pinned = false;
+    if (packed) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, pts[f]) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+      else cudaGetLastError();
+    }
+    if (pinned) {  // page-locked caller buffer: DMA straight from it (the private copy of H:152 is the device buffer)
+      CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], pts[f], (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s));
+      continue;
+    }
+    if (!staged_any) { CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1))); staged_any = true; }
     float4* dst = ctx->h_in.p + ctx->pt_off[f];
     const float* src = pts[f];
-    const int64_t cnt = n[f];
-    if (cols == 4 && col_stride == 1 && row_stride == 4) {
+    if (packed) {
       std::memcpy(dst, src, (size_t) cnt * sizeof(float4));
     } else {
       for (int64_t i = 0; i < cnt; ++i) {
@@ -406,9 +475,8 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
         dst[i] = make_float4(r[0], r[col_stride], r[2 * col_stride], cols == 4 ? r[3 * col_stride] : 0.f);
       }
     }
+    CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], dst, (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s));
   }
-  cudaStream_t s = ctx->stream;
-  if (total > 0) CU_TRY(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, (size_t) total * sizeof(float4), cudaMemcpyHostToDevice, s));
   rc = run_path(ctx, nframes, ctx->d_in.p, cols == 4 ? 1 : 0, s);
   if (rc) return rc;
   CU_TRY(cudaStreamSynchronize(s));

@@ -48,6 +48,12 @@ def load_library():
     lib.pwpp_copy_history.argtypes = [vp, i32, i32, i32, vp]; lib.pwpp_copy_history.restype = i32
     lib.pwpp_reset_stream.argtypes = [vp, i32]; lib.pwpp_reset_stream.restype = i32
     lib.pwpp_reset_all.argtypes = [vp]; lib.pwpp_reset_all.restype = i32
+    lib.pwpp_host_alloc.argtypes = [C.c_size_t]; lib.pwpp_host_alloc.restype = vp
+    lib.pwpp_host_free.argtypes = [vp]; lib.pwpp_host_free.restype = None
+    lib.pwpp_set_profiling.argtypes = [vp, i32]; lib.pwpp_set_profiling.restype = i32
+    lib.pwpp_stage_times_ms.argtypes = [vp, C.POINTER(C.c_float)]; lib.pwpp_stage_times_ms.restype = i32
+    lib.pwpp_stage_name.argtypes = [i32]; lib.pwpp_stage_name.restype = C.c_char_p
+    lib.pwpp_launch_count.argtypes = [vp]; lib.pwpp_launch_count.restype = i64
     _lib = lib
     return lib
 
@@ -174,6 +180,19 @@ class Engine:
         a, b = C.c_void_p(), C.c_void_p()
         _check(self.lib.pwpp_device_results(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    NUM_STAGES = 6
+
+    def set_profiling(self, on: bool):
+        _check(self.lib.pwpp_set_profiling(self._h, 1 if on else 0))
+
+    def stage_times_ms(self):
+        arr = (C.c_float * self.NUM_STAGES)()
+        _check(self.lib.pwpp_stage_times_ms(self._h, arr))
+        return {self.lib.pwpp_stage_name(i).decode(): float(arr[i]) for i in range(self.NUM_STAGES)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.pwpp_launch_count(self._h))
 
     def reset(self, f=None):
         _check(self.lib.pwpp_reset_all(self._h) if f is None else self.lib.pwpp_reset_stream(self._h, f))
