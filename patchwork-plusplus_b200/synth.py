@@ -7,7 +7,8 @@ keeping returns up to 120 m, dropping 5 % at random, with intensity in {0, 0.01,
 low-intensity "reflection" points below the ground (exercise RNR, reference patchworkpp.cpp:377-400).
 
   kitti64   : 64 beams (+2 deg .. -24.33 deg, HDL-64E-like) x 2083 azimuth steps  -> ~110-125k points
-  ouster128 : 128 beams uniform in +-22.5 deg x 8192 azimuth steps                -> ~0.9-1.0M points
+  ouster128 : 128 beams uniform in +-22.5 deg x 8192 azimuth steps                -> ~0.5M returns (upward beams miss)
+  dense1m   : the same beam layout x 16384 azimuth steps                          -> ~1.0M returns
 
 torch is used only as the array engine (CPU here, CUDA on the GPU box where generating a 1024-frame batch
 with numpy would take minutes). Frame f of seed s is fully determined by (s, f, sensor) on a given device.
@@ -19,6 +20,7 @@ import torch
 SENSORS = {
     "kitti64": dict(n_az=2083),
     "ouster128": dict(n_az=8192),
+    "dense1m": dict(n_az=16384),   # Ouster-128 beam layout, 2x azimuth density -> ~1.0M returns (BASELINE config 5)
 }
 
 
@@ -27,7 +29,7 @@ def _elevations(sensor: str, device):
         up = torch.linspace(2.0, -8.33, 32, device=device, dtype=torch.float64)
         lo = torch.linspace(-8.83, -24.33, 32, device=device, dtype=torch.float64)
         el = torch.cat([up, lo])
-    elif sensor == "ouster128":
+    elif sensor in ("ouster128", "dense1m"):
         el = torch.linspace(22.5, -22.5, 128, device=device, dtype=torch.float64)
     else:
         raise ValueError(sensor)

@@ -240,7 +240,8 @@ def test_emission_order_is_bin_major(kitti):
     eng = _engine(); eng.estimate_host([a])
     orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(a)
     ids = orc.bin_ids().astype(np.int64)
-    for ge, go in ((eng.ground_indices(0), orc.getGroundIndices()), (eng.nonground_indices(0), orc.getNongroundIndices())):
+    eng_g = eng.ground_indices(0)
+    for ge, go in ((eng_g, orc.getGroundIndices()), (eng.nonground_indices(0), orc.getNongroundIndices())):
         # same sequence of bins (run-length encoded), same multiset inside each run
         def runs(idx):
             b = ids[idx]
@@ -250,7 +251,10 @@ def test_emission_order_is_bin_major(kitti):
         ro_, bo_ = runs(go)
         assert list(be_) == list(bo_)
         assert all(np.array_equal(x, y) for x, y in zip(re_, ro_))
-        assert all(np.all(np.diff(x) > 0) for x in np.split(ge, np.nonzero(np.diff(ids[ge]))[0] + 1))
+        # inside one bin's run: one ascending piece in the ground list; in the non-ground list at most two
+        # (a rejected patch's ground part, then its non-ground part, patchworkpp.cpp:264/272 then :284)
+        for x in np.split(ge, np.nonzero(np.diff(ids[ge]))[0] + 1):
+            assert int((np.diff(x) <= 0).sum()) <= (0 if ge is eng_g else 1)
 
 
 def test_python_dropin_module(kitti):
@@ -291,15 +295,18 @@ def test_large_batch_properties():
     eng.synchronize()
     host = pts.cpu().numpy()
     offs = offs.numpy()
+    frac = []
     for f in range(nf):
         n = int(offs[f + 1] - offs[f])
         g, ng = eng.ground_indices(f), eng.nonground_indices(f)
         assert len(g) + len(ng) == n
         seen = np.zeros(n, np.int32); seen[g] += 1; seen[ng] += 1
         assert np.all(seen == 1), f"frame {f}: not a partition"
-        assert 0.3 * n < len(g) < 0.98 * n
+        frac.append(len(g) / n)
     ndeg = 0
-    for f in range(0, nf, 8):
+    # oracle on a sample plus the frames with the most unusual ground share
+    sample = sorted(set(range(0, nf, 8)) | {int(np.argmin(frac)), int(np.argmax(frac))})
+    for f in sample:
         a = host[offs[f]:offs[f + 1]]
         orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(a)
         ndeg += compare_frame(eng, f, orc, a, f"large/{f}")
@@ -315,8 +322,8 @@ def test_large_batch_properties():
 def test_dense_ouster_frame():
     """BASELINE config-5 shape: a ~1M-point frame (bins of tens of thousands of points)."""
     import synth
-    a = synth.make_frame(5, 0, "ouster128", "cuda").cpu().numpy()
-    assert a.shape[0] > 700_000
+    a = synth.make_frame(5, 0, "dense1m", "cuda").cpu().numpy()
+    assert a.shape[0] > 800_000
     eng = _engine(); eng.estimate_host([a])
     orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(a)
     compare_frame(eng, 0, orc, a, "ouster128")
