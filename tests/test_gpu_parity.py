@@ -147,10 +147,11 @@ def test_edge_cases():
     rng = np.random.default_rng(11)
     big_bin = np.c_[5 + rng.random(20000) * 0.5, rng.random(20000) * 0.5, -1.7 + rng.normal(0, 0.02, 20000), rng.random(20000)].astype(np.float32)
     nonfinite = np.array([[5, 1, np.nan, .5], [np.nan, 1, -1.7, .5], [5, np.inf, -1.7, .5], [6, 1, -np.inf, .5], [6, 1, np.inf, .01],
-                          [7, 2, -1.7, np.nan]] + [[5 + 0.01 * i, 1, -1.7 + 0.001 * i, .5] for i in range(30)], np.float32)
-    tomb = np.array([[5, 1, np.finfo(np.float32).tiny, .5]] + [[5 + 0.01 * i, 1.2, -1.7, .5] for i in range(15)], np.float32)
+                          [7, 2, -1.7, np.nan]] + [[5 + 0.01 * i, 1 + rng.random() * 0.3, -1.7 + rng.normal(0, 0.01), .5] for i in range(30)], np.float32)
+    # (filler points are scattered, not collinear: a rank-1 covariance has no defined normal, in the reference either)
+    tomb = np.array([[5, 1, np.finfo(np.float32).tiny, .5]] + [[5 + 0.01 * i, 1.2 + rng.random() * 0.3, -1.7 + rng.normal(0, 0.01), .5] for i in range(15)], np.float32)
     rnr = np.array([[4, 0, -3.0, 0.05], [4, 0.1, -3.0, 0.5], [4, 0.2, -2.4, 0.05], [40, 0.2, -3.0, 0.05]] +
-                   [[5 + 0.01 * i, 1, -1.7, .5] for i in range(12)], np.float32)
+                   [[5 + 0.01 * i, 1 + rng.random() * 0.3, -1.7 + rng.normal(0, 0.01), .5] for i in range(12)], np.float32)
     cases = {
         "empty": np.zeros((0, 4), np.float32),
         "one_point": np.array([[5, 0, -1.7, 0.5]], np.float32),
