@@ -25,7 +25,7 @@ __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0,
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   // read-once data: bypass L1 allocation, keep L2 normal
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 

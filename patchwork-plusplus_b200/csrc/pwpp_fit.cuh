@@ -103,46 +103,34 @@ struct GroupOps<256> {
 
 enum FitState { ST_RVPF = 0, ST_SEED = 1, ST_GPF = 2, ST_FINAL = 3, ST_DONE = 4 };
 
-struct PoolSlot {       // one per patch of the CTA: moments in, plane out
-  Moments m;
-  double c[3];
-  Plane pl;
-};
-
-// The resident fit kernel. G lanes cooperate on one patch, K points per lane, NG = FIT_THREADS / G patches per CTA.
-// Point j of a patch lives in lane (j % W) of warp (j / (W*K)) of the group at register slot ((j / W) % K), where
-// W = min(G, 32): consecutive lanes read consecutive float4s and every warp owns a contiguous index range, which
-// makes the final stable partition a warp-local prefix count.
+// The register-resident fit kernel (classes S and M). G lanes cooperate on one patch, K points per lane; a warp
+// holds 32/G patches and is completely independent of the other warps of its CTA (no block barriers): it pulls its
+// own work items from the queue and every lane of a group evaluates the 3x3 eigen-problem of its patch redundantly
+// (the butterfly reductions leave bit-identical moments in all lanes of the group).
+// Point j of a patch lives in lane (j % G) of the group at register slot (j / G).
 template <int G, int K, int CLS>
 __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
-                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
-                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
-  constexpr int NG = FIT_THREADS / G;          // patches per CTA
-  constexpr int W = (G < 32) ? G : 32;         // lanes of a group inside one warp
-  __shared__ PoolSlot s_pool[NG];
-  __shared__ double s_red[16];                 // GroupOps<256> scratch
-  __shared__ int s_base;
-  __shared__ int s_wtot[8][2];                 // per-warp ground / non-ground counts (G = 256 partition)
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int gid = tid / G;                     // patch slot inside the CTA
-  const int gl = tid % G;                      // lane inside the group
-  const int wl = gl % W;                       // lane inside the group's warp segment
-  const int wg = gl / W;                       // warp index inside the group (G = 256 only)
+                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
+                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
+  static_assert(G == 8 || G == 32, "group is a warp or a quarter warp");
+  constexpr int NGW = 32 / G;                  // patches per warp
+  const int lane = threadIdx.x & 31;
+  const int gw = lane / G;                     // group inside the warp
+  const int gl = lane % G;                     // lane inside the group
   typedef GroupOps<G> Ops;
 
   for (;;) {
-    if (tid == 0) s_base = atomicAdd(&wq.head[CLS], NG);
-    __syncthreads();
-    const int base = s_base;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&wq.head[CLS], NGW);
+    base = __shfl_sync(0xffffffffu, base, 0);
     const int count = wq.count[CLS];
     if (base >= count) return;
-    const bool have = (base + gid) < count;
+    const bool have = (base + gw) < count;
     int n = 0, bin = 0, f = 0;
     const float4* P = nullptr;
     int* out = nullptr;
     if (have) {
-      const int item = wq.items[CLS][base + gid];
+      const int item = wq.items[CLS][base + gw];
       f = item >> 12; bin = item & 0xfff;
       const int* bo = bin_off + (size_t) f * (nbp + 1);
       const int off = bo[bin];
@@ -151,33 +139,28 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
       P = sorted + p0 + off;
       out = part + p0 + off;
     }
-    // ---- load the patch into registers ----
+    // ---- load the patches of this warp into registers ----
     float px[K], py[K], pz[K];
     unsigned vmask = 0;                        // bit k: slot k holds a point
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const int j = (wg * K + k) * W + wl;
+      const int j = k * G + gl;
       px[k] = 0.f; py[k] = 0.f; pz[k] = 0.f;
       if (j < n) { const float4 p = P[j]; px[k] = p.x; py[k] = p.y; pz[k] = p.z; vmask |= 1u << k; }
     }
-    // slots in use by ANY patch of this warp (uniform inside the warp): loops over k stop there
-    int kmax = 0;
-    {
-      const int need = (n + W - 1) / W;          // slots this patch uses (G <= 32: one warp segment per patch)
-      kmax = need;
+    // slots in use by ANY patch of this warp (warp-uniform): loops over k stop there
+    int kmax = (n + G - 1) / G;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, kmax, o); kmax = t > kmax ? t : kmax; }
-      if (kmax > K) kmax = K;
-    }
+    for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, kmax, o); kmax = t > kmax ? t : kmax; }
+    if (kmax > K) kmax = K;
     unsigned amask = vmask;                    // alive = not removed by R-VPF (S:495-504)
     const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
     const bool zone0 = (zone == 0);
     const double margin_z = have ? ap.adaptive_seed_selection_margin * states[f].sensor_height : 0.0;  // S:90
-    // first point of the patch: reference point of the shifted moments of the seed fits
-    double c0x = 0.0, c0y = 0.0;
+    double c0x = 0.0, c0y = 0.0;               // first point: reference point of the shifted moments of the seed fits
     if (have) { const float4 p = P[0]; c0x = (double) p.x; c0y = (double) p.y; }
 
-    int state = have ? ((ap.enable_RVPF && zone0) ? ST_RVPF : ST_SEED) : ST_DONE;  // for zone != 0 the R-VPF fit is dead code (see k_fit_stream)
+    int state = have ? ((ap.enable_RVPF && zone0) ? ST_RVPF : ST_SEED) : ST_DONE;  // zone != 0: the R-VPF fit is dead code (see k_fit_stream)
     int rvpf_it = 0, gpf_it = 0, n_ground = 0;
     bool have_plane = false;
     Plane pl;
@@ -186,15 +169,14 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
     for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
     unsigned gmask = 0;
 
-    // ---- rounds ----
-    while (__syncthreads_or(state != ST_DONE)) {
+    // ---- rounds: one pass over the points + one plane fit each ----
+    while (__any_sync(0xffffffffu, state != ST_DONE)) {
       const bool active = state != ST_DONE;
       const bool seed_round = active && (state == ST_RVPF || state == ST_SEED);
       double c[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
       double zthr = 0.0;
-      // (1) LPR selection for seed rounds. All groups of the CTA run the 32 bisection steps together when any
-      //     group needs them (G = 256 uses barriers inside the reductions).
-      if (__syncthreads_or(seed_round)) {
+      // (1) LPR selection for seed rounds: 32-step bisection on order-preserving keys with group-wide counting
+      if (__any_sync(0xffffffffu, seed_round)) {
         unsigned smask = 0;  // candidates: alive and not below the zone-0 margin (S:88-96)
         unsigned keys[K];
 #pragma unroll
@@ -203,7 +185,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
           const bool ok = seed_round && ((amask >> k) & 1u) && !(zone0 && ((double) pz[k] < margin_z));
           smask |= ok ? (1u << k) : 0u;
         }
-        const int nvalid = Ops::sum_i(__popc(smask), s_red);
+        const int nvalid = Ops::sum_i(__popc(smask), nullptr);
         const int target = nvalid < ap.num_lpr ? nvalid : ap.num_lpr;
         unsigned ans = 0;
         for (int bit = 31; bit >= 0; --bit) {
@@ -211,7 +193,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
           int cnt = 0;
 #pragma unroll
           for (int k = 0; k < K; ++k) { if (k >= kmax) break; cnt += (((smask >> k) & 1u) && keys[k] < cand) ? 1 : 0; }
-          cnt = Ops::sum_i(cnt, s_red);
+          cnt = Ops::sum_i(cnt, nullptr);
           if (cnt < target) ans = cand;
         }
         // ans = the target-th smallest key; mean of the target lowest z (S:99-103)
@@ -220,8 +202,8 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
 #pragma unroll
         for (int k = 0; k < K; ++k)
           if (((smask >> k) & 1u) && keys[k] < ans) { part_sum += (double) pz[k]; ++c_lt; }
-        part_sum = Ops::sum_d(part_sum, s_red);
-        c_lt = Ops::sum_i(c_lt, s_red);
+        part_sum = Ops::sum_d(part_sum, nullptr);
+        c_lt = Ops::sum_i(c_lt, nullptr);
         double lpr = 0.0;
         if (target > 0) lpr = (part_sum + (double) (target - c_lt) * (double) key_to_float(ans)) / (double) target;
         if (seed_round) {
@@ -255,20 +237,12 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
         }
       }
 #pragma unroll
-      for (int q = 0; q < 3; ++q) m.s1[q] = Ops::sum_d(m.s1[q], s_red);
+      for (int q = 0; q < 3; ++q) m.s1[q] = Ops::sum_d(m.s1[q], nullptr);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) m.s2[q] = Ops::sum_d(m.s2[q], s_red);
-      m.n = Ops::sum_i(m.n, s_red);
-      // (3) pooled eigen-solve: lane i of warp 0 solves patch i
-      if (gl == 0) {
-        s_pool[gid].m = m;
-        s_pool[gid].m.n = active ? m.n : 0;
-        s_pool[gid].c[0] = c[0]; s_pool[gid].c[1] = c[1]; s_pool[gid].c[2] = c[2];
-      }
-      __syncthreads();
-      if (tid < NG && s_pool[tid].m.n > 0) plane_from_moments(s_pool[tid].m, s_pool[tid].c, s_pool[tid].pl);
-      __syncthreads();
-      if (active && m.n > 0) { pl = s_pool[gid].pl; have_plane = true; }  // S:49: an empty set keeps the previous plane
+      for (int q = 0; q < 6; ++q) m.s2[q] = Ops::sum_d(m.s2[q], nullptr);
+      m.n = Ops::sum_i(m.n, nullptr);
+      // (3) plane of the selected set; an empty set keeps the previous plane (S:49)
+      if (active && m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
       // (4) state transition
       if (state == ST_RVPF) {
         if (have_plane && pl.normal[2] < ap.uprightness_thr) {  // S:489: remove the vertical structure, iterate
@@ -293,34 +267,25 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
 
     // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
     {
-      int g_before = 0, ng_before = 0;  // counts in lower warps of the group (G = 256)
-      if (G == 256) {
-        const int gw = __reduce_add_sync(0xffffffffu, __popc(gmask));
-        const int nw = __reduce_add_sync(0xffffffffu, __popc(vmask & ~gmask));
-        if (lane == 0) { s_wtot[tid >> 5][0] = gw; s_wtot[tid >> 5][1] = nw; }
-        __syncthreads();
-        for (int w = 0; w < (tid >> 5); ++w) { g_before += s_wtot[w][0]; ng_before += s_wtot[w][1]; }
-      }
-      {
-        // every lane runs the ballots (lanes of absent patches hold no valid slot); only valid slots store
-        const unsigned seg_shift = (G == 8) ? (unsigned) ((lane >> 3) << 3) : 0u;
-        const unsigned seg_mask = (G == 8) ? 0xffu : 0xffffffffu;
-        const unsigned lt = ((G == 8) ? ((1u << (lane & 7)) - 1u) : lanemask_lt());
-        int g_run = g_before, ng_run = ng_before;
+      // every lane runs the ballots (lanes of absent patches hold no valid slot); only valid slots store
+      const unsigned seg_shift = (G == 8) ? (unsigned) ((lane >> 3) << 3) : 0u;
+      const unsigned seg_mask = (G == 8) ? 0xffu : 0xffffffffu;
+      const unsigned lt = ((G == 8) ? ((1u << (lane & 7)) - 1u) : lanemask_lt());
+      int g_run = 0, ng_run = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const bool v = (vmask >> k) & 1u, isg = (gmask >> k) & 1u;
-          const unsigned bg = (__ballot_sync(0xffffffffu, v && isg) >> seg_shift) & seg_mask;
-          const unsigned bn = (__ballot_sync(0xffffffffu, v && !isg) >> seg_shift) & seg_mask;
-          if (v) {
-            const int j = (wg * K + k) * W + wl;
-            const int idx = __float_as_int(P[j].w);
-            if (isg) out[g_run + __popc(bg & lt)] = idx;
-            else out[n_ground + ng_run + __popc(bn & lt)] = idx;
-          }
-          g_run += __popc(bg);
-          ng_run += __popc(bn);
+      for (int k = 0; k < K; ++k) {
+        if (k >= kmax) break;
+        const bool v = (vmask >> k) & 1u, isg = (gmask >> k) & 1u;
+        const unsigned bg = (__ballot_sync(0xffffffffu, v && isg) >> seg_shift) & seg_mask;
+        const unsigned bn = (__ballot_sync(0xffffffffu, v && !isg) >> seg_shift) & seg_mask;
+        if (v) {
+          const int j = k * G + gl;
+          const int idx = __float_as_int(P[j].w);
+          if (isg) out[g_run + __popc(bg & lt)] = idx;
+          else out[n_ground + ng_run + __popc(bn & lt)] = idx;
         }
+        g_run += __popc(bg);
+        ng_run += __popc(bn);
       }
       if (have && gl == 0) {
         BinFit& r = fits[(size_t) f * g.nbins + bin];
@@ -331,7 +296,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
         r.d = pl.d;
       }
     }
-    __syncthreads();  // s_base / s_pool / s_wtot are reused by the next batch of patches
+    __syncwarp();
   }
 }
 
@@ -352,14 +317,15 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
   float* sx = s_pts;
   float* sy = sx + CAP;
   float* sz = sy + CAP;
-  __shared__ double s_part[8][9];
+  __shared__ double s_part[2][8][9];   // per-warp partial moments, double-buffered by round parity
+  __shared__ int s_pcnt[2][8];
   __shared__ int s_cnt[8][2];
-  __shared__ Plane s_plane;
   __shared__ unsigned s_min[FIT_THREADS];
   __shared__ unsigned s_cand[CCAP];
   __shared__ double s_lpr;
+  __shared__ double s_fb[8];
   __shared__ unsigned s_T;
-  __shared__ int s_mn, s_ccount, s_item;
+  __shared__ int s_ccount, s_item;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
   for (;;) {
@@ -398,6 +364,7 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
 #pragma unroll
     for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
     unsigned gmask = 0;
+    int round = 0;
 
     while (state != ST_DONE) {   // state is uniform across the CTA
       const bool seed_round = (state == ST_RVPF || state == ST_SEED);
@@ -504,11 +471,11 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
           c_lt = __reduce_add_sync(0xffffffffu, c_lt);
-          if (lane == 0) { s_part[w][0] = ps; s_cnt[w][1] = c_lt; }
+          if (lane == 0) { s_fb[w] = ps; s_cnt[w][1] = c_lt; }
           __syncthreads();
           if (tid == 0) {
             double tps = 0.0; int tlt = 0;
-            for (int q = 0; q < 8; ++q) { tps += s_part[q][0]; tlt += s_cnt[q][1]; }
+            for (int q = 0; q < 8; ++q) { tps += s_fb[q]; tlt += s_cnt[q][1]; }
             s_lpr = target > 0 ? (tps + (double) (target - tlt) * (double) key_to_float(ans)) / (double) target : 0.0;
           }
           __syncthreads();
@@ -544,32 +511,32 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
       }
       mn = __reduce_add_sync(0xffffffffu, mn);
+      const int buf = round & 1;
+      ++round;
       if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) s_part[w][q] = a[q];
-        s_cnt[w][0] = mn;
+        for (int q = 0; q < 9; ++q) s_part[buf][w][q] = a[q];
+        s_pcnt[buf][w] = mn;
       }
       __syncthreads();
-      if (tid == 0) {
-        Moments m;
-        m.n = 0;
+      // every thread combines the 8 partials in the same fixed order (bit-identical everywhere, bit-reproducible
+      // run to run) and solves the 3x3 problem itself: no serial section, no second barrier
+      Moments m;
+      m.n = 0;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
+      for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
-        for (int ww = 0; ww < 8; ++ww) {   // fixed order: bit-reproducible
+      for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) m.s1[q] += s_part[ww][q];
+      for (int ww = 0; ww < 8; ++ww) {
 #pragma unroll
-          for (int q = 0; q < 6; ++q) m.s2[q] += s_part[ww][3 + q];
-          m.n += s_cnt[ww][0];
-        }
-        s_mn = m.n;
-        if (m.n > 0) { Plane t; plane_from_moments(m, c, t); s_plane = t; }
+        for (int q = 0; q < 3; ++q) m.s1[q] += s_part[buf][ww][q];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) m.s2[q] += s_part[buf][ww][3 + q];
+        m.n += s_pcnt[buf][ww];
       }
-      __syncthreads();
-      const int tot_n = s_mn;
-      if (tot_n > 0) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
+      const int tot_n = m.n;
+      if (tot_n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
       // ---- state transition (same machine as k_fit_resident) ----
       if (state == ST_RVPF) {
         if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489
@@ -592,7 +559,6 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         n_ground = tot_n;
         state = ST_DONE;
       }
-      __syncthreads();   // s_part / s_cnt / s_plane are rewritten in the next round
     }
 
     // ---- stable partition: ground indices ascending, then non-ground indices ascending ----

@@ -30,6 +30,8 @@ inline void build_geometry(const pwpp_params& p, Geometry& g, AlgoParams& ap, bo
     g.f_min_ranges[k] = (float) g.min_ranges[k];
     g.f_ring_sizes[k] = (float) g.ring_sizes[k];
     g.f_sector_sizes[k] = (float) g.sector_sizes[k];
+    g.f_inv_ring[k] = (float) (1.0 / g.ring_sizes[k]);
+    g.f_inv_sector[k] = (float) (1.0 / g.sector_sizes[k]);
     // the fp32 filter of bin_of_point() needs decision cells much wider than the float error
     if (!(g.ring_sizes[k] >= 0.5) || g.num_sectors[k] > 128) fast = false;
   }

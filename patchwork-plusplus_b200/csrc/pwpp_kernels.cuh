@@ -503,12 +503,16 @@ __global__ void __launch_bounds__(256) k_emit(FrameTable ft, Geometry g, int nbp
   __syncthreads();
   const BinSeg* seg = segs + (size_t) f * nb_all;
   const BinFit* fit = fits + (size_t) f * g.nbins;
-  for (int i = base + threadIdx.x; i < n && i < base + CHUNK_PTS; i += blockDim.x) {
-    if (i >= s_off[nb_all]) continue;
-    // binary search: largest b with s_off[b] <= i
+  const int total = s_off[nb_all];
+  for (int i0 = base + (threadIdx.x & ~31); i0 < n && i0 < base + CHUNK_PTS; i0 += blockDim.x) {
+    // one binary search per warp (largest b with s_off[b] <= i0), then every lane walks forward to its own bin:
+    // 32 consecutive sorted positions span very few bins
     int lo = 0, hi = nb_all;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
-    const int b = lo;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i0) lo = mid; else hi = mid; }
+    const int i = i0 + (threadIdx.x & 31);
+    if (i >= n || i >= total) continue;
+    int b = lo;
+    while (i >= s_off[b + 1]) ++b;
     const int j = i - s_off[b];
     const BinSeg sg = seg[b];
     if (b < g.nbins && fit[b].fitted) {
