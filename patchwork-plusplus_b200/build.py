@@ -27,8 +27,8 @@ def _newer(target, sources):
 def build_core(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
     src = os.path.join(HERE, "csrc", "pwpp_capi.cu")
-    deps = [src, os.path.join(HERE, "csrc", "pwpp_kernels.cuh"), os.path.join(HERE, "csrc", "pwpp_math.cuh"),
-            os.path.join(REPO, "include", "pwpp.h")]
+    import glob
+    deps = glob.glob(os.path.join(HERE, "csrc", "*")) + [os.path.join(REPO, "include", "pwpp.h")]
     out = os.path.join(LIB, "libpwpp_b200.so")
     if force or _newer(out, deps):
         cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",

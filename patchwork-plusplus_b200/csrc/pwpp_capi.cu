@@ -226,13 +226,13 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
   ++ctx->launches;
   STAGE_MARK();
-  k_fit_resident<32, 16, 1><<<ctx->fit_grid[1], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
   ++ctx->launches;
   STAGE_MARK();
   k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
   ++ctx->launches;
   STAGE_MARK();
-  k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
   ++ctx->launches;
   STAGE_MARK();
   k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
@@ -381,9 +381,10 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     cudaDeviceProp prop;
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
     int per_sm[NUM_CLASSES] = {1, 1, 1, 1, 1};
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_fit_resident<8, 8, 0>, FIT_THREADS, 0));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_resident<32, 16, 1>, FIT_THREADS, 0));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_warp<true>, FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4)));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fit_cta<2048, 2>, FIT_THREADS, 3 * 2048 * sizeof(float)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_fit_cta<8192, 3>, FIT_THREADS, 3 * 8192 * sizeof(float)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_fit_stream, 128, 0));
@@ -468,7 +469,7 @@ int pwpp_stage_times_ms(pwpp_ctx* ctx, float* ms) {
   return PWPP_OK;
 }
 const char* pwpp_stage_name(int stage) {
-  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit_S", "k_fit_M", "k_fit_L1", "k_fit_L2", "k_fit_X", "k_gle", "k_emit"};
+  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit_S", "k_fit_L2", "k_fit_L1", "k_fit_M", "k_fit_X", "k_gle", "k_emit"};
   return (stage >= 0 && stage < PWPP_NUM_STAGES) ? names[stage] : "";
 }
 int64_t pwpp_launch_count(const pwpp_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -47,6 +47,23 @@ __device__ __forceinline__ float key_to_float(unsigned k) {
   return __uint_as_float(u);
 }
 
+// k-th smallest (1-based `target`) of a set of order keys all lying in [kmin, kmax]; count_less(c) must return the
+// number of set members with key < c (uniform across the cooperating lanes). Bits above the highest bit in which
+// kmin and kmax differ are shared by every key, so the bisection starts below them (z values of one patch
+// typically share sign, exponent and a few mantissa bits: ~18 steps instead of 32).
+template <typename F>
+__device__ __forceinline__ unsigned kth_key(unsigned kmin, unsigned kmax, int target, F count_less) {
+  const unsigned diff = kmin ^ kmax;
+  if (diff == 0u) return kmin;
+  const int top = 31 - __clz(diff);
+  unsigned ans = (top == 31) ? 0u : (kmin & ~((2u << top) - 1u));
+  for (int bit = top; bit >= 0; --bit) {
+    const unsigned cand = ans | (1u << bit);
+    if (count_less(cand) < target) ans = cand;
+  }
+  return ans;
+}
+
 // ---- group-wide reductions -------------------------------------------------------------------------
 // G = 8: four independent groups per warp (butterfly inside 8-lane segments); G = 32: one warp;
 // G = 256: one CTA (warp butterfly + shared memory exchange, all threads get the result).
@@ -55,6 +72,14 @@ struct GroupOps;
 
 template <>
 struct GroupOps<8> {
+  __device__ static __forceinline__ unsigned min_u(unsigned v) {
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 4)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 2)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+  }
+  __device__ static __forceinline__ unsigned max_u(unsigned v) {
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 4)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 2)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+  }
   __device__ static __forceinline__ int sum_i(int v, void*) {
     v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
@@ -66,6 +91,8 @@ struct GroupOps<8> {
 };
 template <>
 struct GroupOps<32> {
+  __device__ static __forceinline__ unsigned min_u(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+  __device__ static __forceinline__ unsigned max_u(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
   __device__ static __forceinline__ int sum_i(int v, void*) { return __reduce_add_sync(0xffffffffu, v); }
   __device__ static __forceinline__ double sum_d(double v, void*) {
 #pragma unroll
@@ -119,11 +146,18 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
   const int gl = lane % G;                     // lane inside the group
   typedef GroupOps<G> Ops;
 
+  constexpr int GRAB = 1;                      // batches of NGW patches fetched per queue atomic
+  int grab_base = 0, grab_left = 0;
+  const int count = wq.count[CLS];
   for (;;) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&wq.head[CLS], NGW);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const int count = wq.count[CLS];
+    if (grab_left == 0) {
+      if (lane == 0) grab_base = atomicAdd(&wq.head[CLS], NGW * GRAB);
+      grab_base = __shfl_sync(0xffffffffu, grab_base, 0);
+      grab_left = GRAB;
+    }
+    const int base = grab_base;
+    grab_base += NGW;
+    --grab_left;
     if (base >= count) return;
     const bool have = (base + gw) < count;
     int n = 0, bin = 0, f = 0;
@@ -187,14 +221,25 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
         }
         const int nvalid = Ops::sum_i(__popc(smask), nullptr);
         const int target = nvalid < ap.num_lpr ? nvalid : ap.num_lpr;
-        unsigned ans = 0;
-        for (int bit = 31; bit >= 0; --bit) {
-          const unsigned cand = ans | (1u << bit);
-          int cnt = 0;
+        unsigned kmn = 0xffffffffu, kmx = 0u;
 #pragma unroll
-          for (int k = 0; k < K; ++k) { if (k >= kmax) break; cnt += (((smask >> k) & 1u) && keys[k] < cand) ? 1 : 0; }
-          cnt = Ops::sum_i(cnt, nullptr);
-          if (cnt < target) ans = cand;
+        for (int k = 0; k < K; ++k) if ((smask >> k) & 1u) { kmn = min(kmn, keys[k]); kmx = max(kmx, keys[k]); }
+        kmn = Ops::min_u(kmn); kmx = Ops::max_u(kmx);
+        // the groups of a warp bisect together: use the widest range among them so that the loop is warp-uniform
+        unsigned ans = 0;
+        {
+          unsigned diff = (nvalid > 0) ? (kmn ^ kmx) : 0u;
+          diff = __reduce_or_sync(0xffffffffu, diff);
+          const int top = diff ? (31 - __clz(diff)) : -1;
+          ans = (nvalid > 0) ? ((top >= 31 || top < 0) ? (top < 0 ? kmn : 0u) : (kmn & ~((2u << top) - 1u))) : 0u;
+          for (int bit = top; bit >= 0; --bit) {
+            const unsigned cand = ans | (1u << bit);
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { if (k >= kmax) break; cnt += (((smask >> k) & 1u) && keys[k] < cand) ? 1 : 0; }
+            cnt = Ops::sum_i(cnt, nullptr);
+            if (cnt < target) ans = cand;
+          }
         }
         // ans = the target-th smallest key; mean of the target lowest z (S:99-103)
         double part_sum = 0.0;
@@ -325,7 +370,8 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
   __shared__ double s_lpr;
   __shared__ double s_fb[8];
   __shared__ unsigned s_T;
-  __shared__ int s_ccount, s_item;
+  __shared__ int s_ccount, s_item, s_mn;
+  __shared__ Plane s_plane;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
   for (;;) {
@@ -400,15 +446,17 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
           have = __reduce_add_sync(0xffffffffu, have);
           unsigned ans = 0xffffffffu;   // fewer candidate-holding threads than target: keep everything
           if (target > 0 && have >= target) {
-            ans = 0;
-            for (int bit = 31; bit >= 0; --bit) {
-              const unsigned cand = ans | (1u << bit);
+            unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (mk[q] != 0xffffffffu) { kmn = min(kmn, mk[q]); kmx = max(kmx, mk[q]); }
+            kmn = __reduce_min_sync(0xffffffffu, kmn);
+            kmx = __reduce_max_sync(0xffffffffu, kmx);
+            ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
               int cnt = 0;
 #pragma unroll
               for (int q = 0; q < 8; ++q) cnt += mk[q] < cand;
-              cnt = __reduce_add_sync(0xffffffffu, cnt);
-              if (cnt < target) ans = cand;
-            }
+              return __reduce_add_sync(0xffffffffu, cnt);
+            });
           }
           if (lane == 0) s_T = ans;
         }
@@ -424,17 +472,22 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         if (cc <= CCAP) {
           if (w == 0) {   // exact selection among the gathered candidates
             unsigned ck[CCAP / 32];
+            unsigned kmn = 0xffffffffu, kmx = 0u;
+            const int nq = (cc + 31) >> 5;
 #pragma unroll
-            for (int q = 0; q < CCAP / 32; ++q) { const int i = lane + 32 * q; ck[q] = i < cc ? s_cand[i] : 0xffffffffu; }
-            unsigned ans = 0;
-            for (int bit = 31; bit >= 0; --bit) {
-              const unsigned cand = ans | (1u << bit);
+            for (int q = 0; q < CCAP / 32; ++q) {
+              const int i = lane + 32 * q;
+              ck[q] = i < cc ? s_cand[i] : 0xffffffffu;
+              if (i < cc) { kmn = min(kmn, ck[q]); kmx = max(kmx, ck[q]); }
+            }
+            kmn = __reduce_min_sync(0xffffffffu, kmn);
+            kmx = __reduce_max_sync(0xffffffffu, kmx);
+            const unsigned ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
               int cnt = 0;
 #pragma unroll
-              for (int q = 0; q < CCAP / 32; ++q) cnt += ck[q] < cand;
-              cnt = __reduce_add_sync(0xffffffffu, cnt);
-              if (cnt < target) ans = cand;
-            }
+              for (int q = 0; q < CCAP / 32; ++q) { if (q >= nq) break; cnt += ck[q] < cand; }
+              return __reduce_add_sync(0xffffffffu, cnt);
+            });
             double ps = 0.0;
             int c_lt = 0;
 #pragma unroll
@@ -519,24 +572,34 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         s_pcnt[buf][w] = mn;
       }
       __syncthreads();
-      // every thread combines the 8 partials in the same fixed order (bit-identical everywhere, bit-reproducible
-      // run to run) and solves the 3x3 problem itself: no serial section, no second barrier
-      Moments m;
-      m.n = 0;
+      // warp 0 combines the 8 partials (lane q sums quantity q over the warps in a fixed order: bit-reproducible),
+      // solves the 3x3 problem once and publishes the plane; the other warps wait at the second barrier
+      if (w == 0) {
+        double v = 0.0;
+        int cn = 0;
+        if (lane < 9) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
+          for (int ww = 0; ww < 8; ++ww) v += s_part[buf][ww][lane];
+        } else if (lane == 9) {
 #pragma unroll
-      for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
+          for (int ww = 0; ww < 8; ++ww) cn += s_pcnt[buf][ww];
+        }
+        Moments m;
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) {
+        for (int q = 0; q < 3; ++q) m.s1[q] = __shfl_sync(0xffffffffu, v, q);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) m.s1[q] += s_part[buf][ww][q];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) m.s2[q] += s_part[buf][ww][3 + q];
-        m.n += s_pcnt[buf][ww];
+        for (int q = 0; q < 6; ++q) m.s2[q] = __shfl_sync(0xffffffffu, v, 3 + q);
+        m.n = __shfl_sync(0xffffffffu, cn, 9);
+        if (m.n > 0) {
+          Plane t;
+          plane_from_moments(m, c, t);
+          if (lane == 0) s_plane = t;
+        }
+        if (lane == 0) s_mn = m.n;
       }
-      const int tot_n = m.n;
-      if (tot_n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
+      __syncthreads();
+      const int tot_n = s_mn;
+      if (tot_n > 0) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
       // ---- state transition (same machine as k_fit_resident) ----
       if (state == ST_RVPF) {
         if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489
@@ -730,6 +793,343 @@ __device__ __forceinline__ Moments accumulate(const float4* __restrict__ P, int 
   return m;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// k_fit_warp: one warp per patch, no block-level synchronisation at all.
+//   STAGE = true  (class M, 65..512 points): the patch is copied once into the warp's 8 KB of shared memory and
+//                 every pass reads it from there;
+//   STAGE = false (classes L2 then L1, 513..8192 points): the points are streamed from L2 in every pass, four
+//                 independent 128-bit loads per lane in flight (lane l reads points l, l+32, ...).
+// Per point a pass must remember one bit, kept as the ballot word of its iteration in per-warp shared memory
+// (alive = not removed by R-VPF, S:495-504; member = in the set the current plane was fitted to).
+//
+// Two things keep the per-point cost low:
+//  * the point-to-plane test (S:525/529) is first evaluated in fp32 with a rigorous error bound; only points
+//    whose fp32 distance lies inside the bound of th_dist are re-evaluated in double (identical decisions);
+//  * the moment sums of the R-GPF iterations are INCREMENTAL: all fits of a patch share one reference point, so a
+//    round only adds (+) / removes (-) the points whose membership changed w.r.t. the previous set. A round
+//    without any change has reached the fixpoint of S:516-543 (same set => same plane => same next set) and the
+//    remaining iterations are skipped — exactly, not approximately.
+constexpr int WARP_CAP = CLS_L2_MAX;            // 8192 points -> 256 iterations
+constexpr int FITW_WARPS = 8;
+constexpr int FITW_U = 4;                       // loads in flight per lane
+
+// LPR height for one warp-owned patch (extract_initial_seeds, S:84-103): mean of the (<= num_lpr) lowest z among
+// the points that are alive and, in zone 0, not below the adaptive margin.
+// Two-level selection: the num_lpr-th smallest of the 32 per-lane minima is an upper bound T of the num_lpr-th
+// smallest point, so only the few points with z <= T are gathered (ballot append into the warp's 128-slot buffer)
+// and the exact k-th key is bisected among them. Falls back to the streaming selector when num_lpr > 32 or when
+// more than 128 points tie below the bound.
+__device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool any_removed, const unsigned* __restrict__ alive_w, bool zone0, double margin_z,
+                           int num_lpr, float* sel_buf) {
+  const int lane = lane_id();
+  const unsigned lt = lanemask_lt();
+  unsigned* cbuf = reinterpret_cast<unsigned*>(sel_buf);
+  bool fallback = num_lpr > 32;
+  double lpr = 0.0;
+  if (!fallback) {
+    unsigned kminL = 0xffffffffu;
+    int nv = 0;
+    for (int it = 0; it < nit; ++it) {
+      const int j = it * 32 + lane;
+      bool valid = j < n;
+      const float z = P[j < n ? j : n - 1].z;
+      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
+      if (zone0 && ((double) z < margin_z)) valid = false;
+      if (valid) { kminL = min(kminL, order_key(z)); ++nv; }
+    }
+    const int nvalid = __reduce_add_sync(0xffffffffu, nv);
+    const int target = nvalid < num_lpr ? nvalid : num_lpr;
+    if (target == 0) return 0.0;
+    const int have = __reduce_add_sync(0xffffffffu, kminL != 0xffffffffu ? 1 : 0);
+    unsigned T = 0xffffffffu;   // fewer lanes with candidates than target: keep everything
+    if (have >= target) {
+      const unsigned gmn = __reduce_min_sync(0xffffffffu, kminL);
+      const unsigned gmx = __reduce_max_sync(0xffffffffu, kminL != 0xffffffffu ? kminL : 0u);
+      T = kth_key(gmn, gmx, target, [&](unsigned cand) { return __reduce_add_sync(0xffffffffu, kminL < cand ? 1 : 0); });
+    }
+    int cc = 0;
+    for (int it = 0; it < nit; ++it) {
+      const int j = it * 32 + lane;
+      bool valid = j < n;
+      const float z = P[j < n ? j : n - 1].z;
+      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
+      if (zone0 && ((double) z < margin_z)) valid = false;
+      const unsigned key = order_key(z);
+      const bool c = valid && key <= T;
+      const unsigned bal = __ballot_sync(0xffffffffu, c);
+      if (c) { const int pos = cc + __popc(bal & lt); if (pos < 128) cbuf[pos] = key; }
+      cc += __popc(bal);
+    }
+    __syncwarp();
+    if (cc <= 128) {
+      unsigned ck[4];
+      unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q;
+        ck[q] = i < cc ? cbuf[i] : 0xffffffffu;
+        if (i < cc) { kmn = min(kmn, ck[q]); kmx = max(kmx, ck[q]); }
+      }
+      kmn = __reduce_min_sync(0xffffffffu, kmn);
+      kmx = __reduce_max_sync(0xffffffffu, kmx);
+      const unsigned ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cnt += ck[q] < cand;
+        return __reduce_add_sync(0xffffffffu, cnt);
+      });
+      double ps = 0.0;
+      int c_lt = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (ck[q] < ans) { ps += (double) key_to_float(ck[q]); ++c_lt; }
+      ps = warp_sum(ps);
+      c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+      lpr = (ps + (double) (target - c_lt) * (double) key_to_float(ans)) / (double) target;
+      __syncwarp();
+    } else fallback = true;
+  }
+  if (fallback) {
+    LprSelector sel;
+    sel.init(sel_buf, num_lpr);
+    for (int it = 0; it < nit; ++it) {
+      const int j = it * 32 + lane;
+      bool valid = j < n;
+      const float z = P[j < n ? j : n - 1].z;
+      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
+      if (zone0 && ((double) z < margin_z)) valid = false;
+      sel.push(valid, z);
+    }
+    sel.prune();
+    if (lane == 0) {
+      double sum = 0.0;
+      for (int i = 0; i < sel.m; ++i) sum += (double) sel_buf[i];
+      lpr = sel.m != 0 ? sum / sel.m : 0.0;
+    }
+    __syncwarp();
+    lpr = __shfl_sync(0xffffffffu, lpr, 0);
+  }
+  return lpr;
+}
+
+struct PlaneF { float n0, n1, n2, d; };
+
+// +1: surely below th_dist, 0: surely not, -1: inside the fp32 error bound (decide in double)
+__device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, float y, float z) {
+  const float sf = fmaf(pf.n0, x, fmaf(pf.n1, y, fmaf(pf.n2, z, pf.d)));
+  // |sf - exact| <= 3e-7 * (|x|+|y|+|z|+|d|) (|n_i| <= 1: float coefficients + three fma roundings); 3x margin
+  const float bound = 1e-6f * (fabsf(x) + fabsf(y) + fabsf(z) + fabsf(pf.d) + 1.0f);
+  const float diff = sf - th;
+  return (fabsf(diff) > bound) ? (diff < 0.f ? 1 : 0) : -1;
+}
+
+template <bool STAGE>
+__global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+                                                                             Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
+                                                                             int* __restrict__ part, BinFit* __restrict__ fits) {
+  constexpr int CAP = STAGE ? CLS_M_MAX : WARP_CAP;
+  __shared__ unsigned s_alive[FITW_WARPS][CAP / 32];
+  __shared__ unsigned s_member[FITW_WARPS][CAP / 32];
+  __shared__ float s_sel[FITW_WARPS][128];
+  extern __shared__ float4 s_stage[];           // STAGE: [FITW_WARPS][CLS_M_MAX]
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const unsigned lt = lanemask_lt();
+  unsigned* alive_w = s_alive[warp];
+  unsigned* member_w = s_member[warp];
+  float* sel_buf = s_sel[warp];
+  int cls = STAGE ? 1 : 3;   // queue being drained: M, or L2 then L1 (long patches first)
+  const int cls_last = STAGE ? 1 : 2;
+  const float thf = (float) ap.th_dist;
+
+  for (;;) {
+    int it0 = -1;
+    while (cls >= cls_last) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&wq.head[cls], 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t < wq.count[cls]) { it0 = t; break; }
+      --cls;
+    }
+    if (it0 < 0) return;
+    const int item = wq.items[cls][it0];
+    const int f = item >> 12, bin = item & 0xfff;
+    const int* bo = bin_off + (size_t) f * (nbp + 1);
+    const int off = bo[bin], n = bo[bin + 1] - off;
+    const long long p0 = ft.pt_off[f];
+    const float4* G = sorted + p0 + off;        // the patch in global memory
+    int* out = part + p0 + off;
+    const int nit = (n + 31) >> 5;
+    const float4* P = G;                        // where the passes read the points from
+    if (STAGE) {
+      float4* mine = s_stage + warp * CLS_M_MAX;
+      for (int it = 0; it < nit; it += FITW_U) {
+        float4 q[FITW_U];
+#pragma unroll
+        for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; q[u] = G[j < n ? j : n - 1]; }
+#pragma unroll
+        for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; if (j < n) mine[j] = q[u]; }
+      }
+      __syncwarp();
+      P = mine;
+    }
+    const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
+    const bool zone0 = (zone == 0);
+    const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;  // S:90
+    const float4 first = P[0];
+    double c[3] = {(double) first.x, (double) first.y, 0.0};   // reference point of all moment sums of this patch
+
+    bool have_plane = false, any_removed = false;
+    Plane pl;
+    pl.d = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+
+    // ---- seed rounds: R-VPF iterations (zone 0 only; for other zones the R-VPF fit is dead code, see k_fit_stream)
+    //      followed by the R-GPF seed fit (S:484-514). Each is a selection pass + a full accumulation pass. ----
+    Moments tot;   // running sums of the current member set (valid after the last seed round)
+    int rvpf_left = (ap.enable_RVPF && zone0) ? ap.num_iter : 0;
+    for (;;) {
+      const bool rvpf_round = rvpf_left > 0;
+      // LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103)
+      const double lpr = warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
+      const double zthr = lpr + (rvpf_round ? ap.th_seeds_v : ap.th_seeds);
+      c[2] = lpr;
+      // full accumulation over {alive, z < lpr + th}; the ballots become the member set
+      Moments m;
+      m.n = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
+      for (int it = 0; it < nit; it += FITW_U) {
+        float4 q[FITW_U];
+#pragma unroll
+        for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; q[u] = P[j < n ? j : n - 1]; }
+#pragma unroll
+        for (int u = 0; u < FITW_U; ++u) {
+          const int j = (it + u) * 32 + lane;
+          const float4 p = q[u];
+          bool in = (j < n) && ((double) p.z < zthr);                                     // S:108 / S:145
+          if (any_removed && it + u < nit) in = in && ((alive_w[it + u] >> lane) & 1u);
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          if (lane == 0 && it + u < nit) member_w[it + u] = bal;
+          if (bal) {
+            const double w = in ? 1.0 : 0.0;   // unselected lanes add exact zeros
+            const double dx = ((double) p.x - c[0]) * w, dy = ((double) p.y - c[1]) * w, dz = ((double) p.z - c[2]) * w;
+            m.s1[0] += dx; m.s1[1] += dy; m.s1[2] += dz;
+            m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
+            m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
+            m.n += in ? 1 : 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) m.s1[q] = warp_sum(m.s1[q]);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) m.s2[q] = warp_sum(m.s2[q]);
+      m.n = warp_sum_i(m.n);
+      if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
+      tot = m;
+      if (!rvpf_round) break;
+      if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489: remove the vertical structure, iterate
+        for (int it = 0; it < nit; ++it) {
+          const int j = it * 32 + lane;
+          bool keep = j < n;
+          const float4 p = P[j < n ? j : n - 1];
+          if (any_removed) keep = keep && ((alive_w[it] >> lane) & 1u);
+          keep = keep && !(fabs(point_plane_distance(pl, p.x, p.y, p.z)) < ap.th_dist_v);   // S:499
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (lane == 0) alive_w[it] = bal;
+        }
+        __syncwarp();
+        any_removed = true;
+        --rvpf_left;
+      } else rvpf_left = 0;   // S:506 break
+    }
+    __syncwarp();
+
+    // ---- R-GPF iterations (S:516-543): num_iter distance passes; incremental moments; stop at the fixpoint ----
+    for (int round = 0; round < ap.num_iter && have_plane; ++round) {
+      PlaneF pf;
+      pf.n0 = (float) pl.normal[0]; pf.n1 = (float) pl.normal[1]; pf.n2 = (float) pl.normal[2]; pf.d = (float) pl.d;
+      Moments dm;
+      dm.n = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) dm.s1[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) dm.s2[q] = 0.0;
+      unsigned changed_any = 0;
+      for (int it = 0; it < nit; it += FITW_U) {
+        float4 q[FITW_U];
+#pragma unroll
+        for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; q[u] = P[j < n ? j : n - 1]; }
+#pragma unroll
+        for (int u = 0; u < FITW_U; ++u) {
+          if (it + u >= nit) break;
+          const int j = (it + u) * 32 + lane;
+          const float4 p = q[u];
+          int fl = dist_filter(pf, thf, p.x, p.y, p.z);
+          if (fl < 0) fl = (point_plane_distance(pl, p.x, p.y, p.z) < ap.th_dist) ? 1 : 0;   // S:525 / S:529, exact
+          bool in = (j < n) && (fl != 0);
+          if (any_removed) in = in && ((alive_w[it + u] >> lane) & 1u);
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          const unsigned prev = member_w[it + u];
+          const unsigned chg = bal ^ prev;
+          if (chg) {   // warp-uniform: only iterations with a membership change touch the double-precision sums
+            changed_any |= chg;
+            const bool mine = (chg >> lane) & 1u;
+            const double w = mine ? (in ? 1.0 : -1.0) : 0.0;
+            const double dx = (double) p.x - c[0], dy = (double) p.y - c[1], dz = (double) p.z - c[2];
+            const double wx = dx * w, wy = dy * w, wz = dz * w;
+            dm.s1[0] += wx; dm.s1[1] += wy; dm.s1[2] += wz;
+            dm.s2[0] += wx * dx; dm.s2[1] += wx * dy; dm.s2[2] += wx * dz;
+            dm.s2[3] += wy * dy; dm.s2[4] += wy * dz; dm.s2[5] += wz * dz;
+            dm.n += mine ? (in ? 1 : -1) : 0;
+            __syncwarp();
+            if (lane == 0) member_w[it + u] = bal;
+          }
+        }
+      }
+      if (changed_any == 0) break;   // fixpoint: every later iteration would reproduce this set and this plane
+#pragma unroll
+      for (int q = 0; q < 3; ++q) tot.s1[q] += warp_sum(dm.s1[q]);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) tot.s2[q] += warp_sum(dm.s2[q]);
+      tot.n += warp_sum_i(dm.n);
+      if (tot.n > 0) plane_from_moments(tot, c, pl);   // S:49 otherwise
+      __syncwarp();
+    }
+    const int n_ground = have_plane ? tot.n : 0;
+    __syncwarp();
+    // stable partition: ground indices ascending, then non-ground indices ascending
+    {
+      int g_run = 0, ng_run = 0;
+      for (int it = 0; it < nit; ++it) {
+        const int j = it * 32 + lane;
+        const bool v = j < n;
+        const unsigned bg = have_plane ? member_w[it] : 0u;
+        const unsigned bv = __ballot_sync(0xffffffffu, v);
+        const unsigned bn = bv & ~bg;
+        if (v) {
+          const int idx = __float_as_int(P[j].w);
+          if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idx;
+          else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+        }
+        g_run += __popc(bg);
+        ng_run += __popc(bn);
+      }
+    }
+    if (lane == 0) {
+      BinFit& r = fits[(size_t) f * g.nbins + bin];
+      r.n = n; r.n_ground = n_ground; r.fitted = 1;
+      r.verdict = have_plane ? 0 : PW_FIT_NO_PLANE;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { r.mean[q] = pl.mean[q]; r.normal[q] = pl.normal[q]; r.sv[q] = pl.sv[q]; }
+      r.d = pl.d;
+    }
+    __syncwarp();
+  }
+}
 
 __global__ void __launch_bounds__(128) k_fit_stream(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
                                                     int nbp, const int* __restrict__ bin_off, WorkQueues wq, int* __restrict__ part, BinFit* __restrict__ fits) {

@@ -355,25 +355,34 @@ PW_HD void jacobi_svd3(double cxx, double cxy, double cxz, double cyy, double cy
 PW_HD void cross3(const double a[3], const double b[3], double r[3]) {
   r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
 }
-// unit vector in the null space of (A - lambda I): the largest cross product of two rows
+PW_HD double rsqrt_d(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+// unit vector in the null space of (A - lambda I): the largest cross product of two rows (scalar selects only, so
+// everything stays in registers)
 PW_HD void eigvec_by_rows(double a00, double a01, double a02, double a11, double a12, double a22, double lambda, double v[3]) {
-  const double r0[3] = {a00 - lambda, a01, a02}, r1[3] = {a01, a11 - lambda, a12}, r2[3] = {a02, a12, a22 - lambda};
-  double c01[3], c02[3], c12[3];
-  cross3(r0, r1, c01); cross3(r0, r2, c02); cross3(r1, r2, c12);
-  const double d01 = c01[0] * c01[0] + c01[1] * c01[1] + c01[2] * c01[2];
-  const double d02 = c02[0] * c02[0] + c02[1] * c02[1] + c02[2] * c02[2];
-  const double d12 = c12[0] * c12[0] + c12[1] * c12[1] + c12[2] * c12[2];
-  double dmax = d01;
-  const double* best = c01;
-  if (d02 > dmax) { dmax = d02; best = c02; }
-  if (d12 > dmax) { dmax = d12; best = c12; }
-  if (dmax > 0.0) { const double inv = 1.0 / sqrt(dmax); v[0] = best[0] * inv; v[1] = best[1] * inv; v[2] = best[2] * inv; }
+  const double r00 = a00 - lambda, r11 = a11 - lambda, r22 = a22 - lambda;
+  // rows r0 = (r00, a01, a02), r1 = (a01, r11, a12), r2 = (a02, a12, r22)
+  const double x01 = a01 * a12 - a02 * r11, y01 = a02 * a01 - r00 * a12, z01 = r00 * r11 - a01 * a01;   // r0 x r1
+  const double x02 = a01 * r22 - a02 * a12, y02 = a02 * a02 - r00 * r22, z02 = r00 * a12 - a01 * a02;   // r0 x r2
+  const double x12 = r11 * r22 - a12 * a12, y12 = a12 * a02 - a01 * r22, z12 = a01 * a12 - r11 * a02;   // r1 x r2
+  const double d01 = x01 * x01 + y01 * y01 + z01 * z01;
+  const double d02 = x02 * x02 + y02 * y02 + z02 * z02;
+  const double d12 = x12 * x12 + y12 * y12 + z12 * z12;
+  double bx = x01, by = y01, bz = z01, dmax = d01;
+  if (d02 > dmax) { dmax = d02; bx = x02; by = y02; bz = z02; }
+  if (d12 > dmax) { dmax = d12; bx = x12; by = y12; bz = z12; }
+  if (dmax > 0.0) { const double inv = rsqrt_d(dmax); v[0] = bx * inv; v[1] = by * inv; v[2] = bz * inv; }
   else { v[0] = 0.0; v[1] = 0.0; v[2] = 1.0; }
 }
 // unit vectors u, w with {u, w, v} orthonormal
 PW_HD void orthogonal_complement(const double v[3], double u[3], double w[3]) {
-  if (fabs(v[0]) > fabs(v[1])) { const double inv = 1.0 / sqrt(v[0] * v[0] + v[2] * v[2]); u[0] = -v[2] * inv; u[1] = 0.0; u[2] = v[0] * inv; }
-  else { const double inv = 1.0 / sqrt(v[1] * v[1] + v[2] * v[2]); u[0] = 0.0; u[1] = v[2] * inv; u[2] = -v[1] * inv; }
+  if (fabs(v[0]) > fabs(v[1])) { const double inv = rsqrt_d(v[0] * v[0] + v[2] * v[2]); u[0] = -v[2] * inv; u[1] = 0.0; u[2] = v[0] * inv; }
+  else { const double inv = rsqrt_d(v[1] * v[1] + v[2] * v[2]); u[0] = 0.0; u[1] = v[2] * inv; u[2] = -v[1] * inv; }
   cross3(v, u, w);
 }
 // Same contract as jacobi_svd3(): sv descending, ucol2 = unit eigenvector of the smallest singular value.
@@ -394,9 +403,9 @@ PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, 
   const double inv = 1.0 / amax;
   const double a00 = cxx * inv, a01 = cxy * inv, a02 = cxz * inv, a11 = cyy * inv, a12 = cyz * inv, a22 = czz * inv;
   const double norm = a01 * a01 + a02 * a02 + a12 * a12;
-  const double q = (a00 + a11 + a22) / 3.0;
+  const double q = (a00 + a11 + a22) * (1.0 / 3.0);   // any shift near trace/3 works
   const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
-  const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) / 6.0);
+  const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) * (1.0 / 6.0));
   const double p3 = p * p * p;
   double e0, e1, e2;  // ascending
   double v0[3];
@@ -404,7 +413,7 @@ PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, 
     const double c00 = b11 * b22 - a12 * a12, c01 = a01 * b22 - a12 * a02, c02 = a01 * a12 - b11 * a02;
     double half_det = (b00 * c00 - a01 * c01 + a02 * c02) / p3 * 0.5;
     half_det = half_det < -1.0 ? -1.0 : (half_det > 1.0 ? 1.0 : half_det);
-    const double angle = acos(half_det) / 3.0;
+    const double angle = acos(half_det) * (1.0 / 3.0);
     const bool top = half_det >= 0.0;  // isolate the largest eigenvalue, else the smallest
     const double e_iso = q + p * 2.0 * (top ? cos(angle) : cos(angle + 2.09439510239319549));
     double v[3];
@@ -422,7 +431,7 @@ PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, 
     if (m01 != 0.0) {
       const double tau = (m11 - m00) / (m01 * 2.0);
       const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-      c = 1.0 / sqrt(1.0 + t * t);
+      c = rsqrt_d(1.0 + t * t);
       sn = t * c;
       la = m00 - t * m01;
       lb = m11 + t * m01;
@@ -467,27 +476,27 @@ struct Moments {
 // estimate_plane (S:47-75) from the moment sums. n == 0 must be handled by the caller (S:49: keep
 // the previous plane). mean = c + s1/n ; cov = (s2 - s1 s1^T / n) / (n-1).
 PW_HD void plane_from_moments(const Moments& m, const double c[3], Plane& pl) {
-  const double n = (double) m.n;
-  const double m0 = ddiv(m.s1[0], n), m1 = ddiv(m.s1[1], n), m2 = ddiv(m.s1[2], n);
-  pl.mean[0] = dadd(c[0], m0); pl.mean[1] = dadd(c[1], m1); pl.mean[2] = dadd(c[2], m2);
-  const double dn = (double) (m.n - 1);  // n == 1 -> 0/0 = NaN, like S:57
-  const double cxx = ddiv(dsub(m.s2[0], dmul(m.s1[0], m0)), dn);
-  const double cxy = ddiv(dsub(m.s2[1], dmul(m.s1[0], m1)), dn);
-  const double cxz = ddiv(dsub(m.s2[2], dmul(m.s1[0], m2)), dn);
-  const double cyy = ddiv(dsub(m.s2[3], dmul(m.s1[1], m1)), dn);
-  const double cyz = ddiv(dsub(m.s2[4], dmul(m.s1[1], m2)), dn);
-  const double czz = ddiv(dsub(m.s2[5], dmul(m.s1[2], m2)), dn);
+  const double inv_n = 1.0 / (double) m.n;
+  const double m0 = m.s1[0] * inv_n, m1 = m.s1[1] * inv_n, m2 = m.s1[2] * inv_n;
+  pl.mean[0] = c[0] + m0; pl.mean[1] = c[1] + m1; pl.mean[2] = c[2] + m2;
+  // n == 1: 0 * inf = NaN covariance, like the 0/0 of S:57
+  const double inv_dn = 1.0 / (double) (m.n - 1);
+  const double cxx = (m.s2[0] - m.s1[0] * m0) * inv_dn;
+  const double cxy = (m.s2[1] - m.s1[0] * m1) * inv_dn;
+  const double cxz = (m.s2[2] - m.s1[0] * m2) * inv_dn;
+  const double cyy = (m.s2[3] - m.s1[1] * m1) * inv_dn;
+  const double cyz = (m.s2[4] - m.s1[1] * m2) * inv_dn;
+  const double czz = (m.s2[5] - m.s1[2] * m2) * inv_dn;
   double u2[3];
 #if defined(PWPP_USE_JACOBI)
   jacobi_svd3(cxx, cxy, cxz, cyy, cyz, czz, pl.sv, u2);
 #else
   sym_eig3(cxx, cxy, cxz, cyy, cyz, czz, pl.sv, u2);
 #endif
-  if (u2[2] < 0.0) { u2[0] = dmul(u2[0], -1.0); u2[1] = dmul(u2[1], -1.0); u2[2] = dmul(u2[2], -1.0); }  // S:68
+  if (u2[2] < 0.0) { u2[0] = -u2[0]; u2[1] = -u2[1]; u2[2] = -u2[2]; }  // S:68
   pl.normal[0] = u2[0]; pl.normal[1] = u2[1]; pl.normal[2] = u2[2];
   // d = -(normal . mean), association x0 + (x1 + x2) (S:74 through Eigen's unrolled redux)
-  const double x0 = dmul(u2[0], pl.mean[0]), x1 = dmul(u2[1], pl.mean[1]), x2 = dmul(u2[2], pl.mean[2]);
-  pl.d = -dadd(x0, dadd(x1, x2));
+  pl.d = -(u2[0] * pl.mean[0] + (u2[1] * pl.mean[1] + u2[2] * pl.mean[2]));
 }
 
 // calc_point_to_plane_d (S:551-554) in double: ((n0*x + n1*y) + n2*z) + d
