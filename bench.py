@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=1024)
-    ap.add_argument("--sensor", default="kitti64", choices=["kitti64", "ouster128"])
+    ap.add_argument("--sensor", default="kitti64", choices=["kitti64", "ouster128", "dense1m"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--ref-frames-per-step", type=int, default=0, help="--impl reference: frames per step (0 = 8 x cores)")
@@ -113,7 +113,7 @@ def measured_peak_gbs():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def cpu_reference_throughput(frames, seconds_budget, max_frames=None, threads=None):
+def cpu_reference_throughput(frames, seconds_budget, max_frames=None, threads=None, cycle=False):
     """The reference's own estimateGround (oracle/_ref/libpwref.so) on `threads` host threads, a fresh instance per
     frame like config 3. ctypes releases the GIL during the foreign call, so Python threads scale across cores."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
@@ -133,7 +133,13 @@ def cpu_reference_throughput(frames, seconds_budget, max_frames=None, threads=No
 
     def work(t):
         i = t
-        while i < lim and time.perf_counter() < stop_at:
+        # every thread walks its share of the sample; when a time budget is given the sample is cycled until the
+        # budget is used up (the GPU box has >100 cores: one pass over a few hundred frames lasts < 1 s)
+        while time.perf_counter() < stop_at:
+            if i >= lim:
+                if not cycle:
+                    break
+                i = t
             r = mk()
             r.estimate(frames[i])
             r.getGroundIndices(); r.getNongroundIndices()
@@ -148,7 +154,7 @@ def cpu_reference_throughput(frames, seconds_budget, max_frames=None, threads=No
     dt = time.perf_counter() - t0
     n = sum(done)
     return {"value": n / dt if dt > 0 else 0.0, "unit": UNIT, "cores": T, "kind": kind,
-            "sample": f"{n} frames of the same synthetic batch, fresh instance per frame, {dt:.1f} s wall on {T} threads"}, n, dt
+            "sample": f"{n} estimateGround calls over {min(lim, len(frames))} frames of the same synthetic batch, fresh instance per call, {dt:.1f} s wall on {T} threads"}, n, dt
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -199,24 +205,18 @@ def run_ours(args):
     import pwpp_b200
     import synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import pwpp_dist
+    rank, world, local = pwpp_dist.env_rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier(device_ids=[local])
+    dist = pwpp_dist.Dist(backend="nccl")   # rendezvous + barriers + max-over-ranks only; no data-path collective
+    barrier = dist.barrier
 
     F = args.frames_per_gpu
     dev = torch.device("cuda", local)
-    pts, offs = synth.make_batch(SEED, rank * F, F, args.sensor, dev)  # frames rank*F .. rank*F+F-1 of the global batch
+    shard = pwpp_dist.weak_shard(F, rank, world)   # frames rank*F .. rank*F+F-1 of the global batch
+    pts, offs = synth.make_batch(SEED, shard.start, F, args.sensor, dev)
     offs_np = offs.numpy()
     total_pts = int(offs_np[-1])
     mean_pts = total_pts / F
@@ -248,10 +248,7 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     eng.set_profiling(False)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = dist.max_over_ranks(ms)
     value = world * F * args.steps / (ms / 1e3)
 
     # size-independent sanity of the timed result: every frame's lists partition its points
@@ -299,10 +296,7 @@ def run_ours(args):
             e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        td = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        dt = float(td.item())
+        dt = dist.max_over_ranks(dt)
         e2e = {"value": world * F * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": total_pts * 16 + (F + 1) * 12,
                "d2h_bytes_per_step": total_pts * 4 + 3 * F * 4, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": "pwpp_estimate_host + pwpp_copy_*_indices (C-ABI), page-locked host buffers"}
@@ -313,7 +307,7 @@ def run_ours(args):
         T = os.cpu_count() or 1
         nsample = min(F, max(T * 4, 64))
         frames = [pts[int(offs_np[f]):int(offs_np[f + 1])].cpu().numpy() for f in range(nsample)]
-        cpu, _, _ = cpu_reference_throughput(frames, args.cpu_seconds)
+        cpu, _, _ = cpu_reference_throughput(frames, args.cpu_seconds, cycle=True)
 
     if rank == 0:
         out = {
@@ -326,8 +320,7 @@ def run_ours(args):
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
-    if dist is not None:
-        dist.destroy_process_group()
+    dist.close()
 
 
 if __name__ == "__main__":
