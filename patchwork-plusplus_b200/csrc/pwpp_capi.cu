@@ -249,8 +249,8 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   }
   STAGE_MARK();
   if (max_chunks > 0) {
-    dim3 grid(max_chunks, nframes);
-    k_emit<<<grid, 256, (nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    dim3 grid((max_chunks * CHUNK_PTS + EMIT_PTS - 1) / EMIT_PTS, nframes);
+    k_emit<<<grid, 256, (4 * nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
   STAGE_MARK();

@@ -345,6 +345,17 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
   }
 }
 
+struct PlaneF { float n0, n1, n2, d; };
+
+// +1: surely below th_dist, 0: surely not, -1: inside the fp32 error bound (decide in double)
+__device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, float y, float z) {
+  const float sf = fmaf(pf.n0, x, fmaf(pf.n1, y, fmaf(pf.n2, z, pf.d)));
+  // |sf - exact| <= 3e-7 * (|x|+|y|+|z|+|d|) (|n_i| <= 1: float coefficients + three fma roundings); 3x margin
+  const float bound = 1e-6f * (fabsf(x) + fabsf(y) + fabsf(z) + fabsf(pf.d) + 1.0f);
+  const float diff = sf - th;
+  return (fabsf(diff) > bound) ? (diff < 0.f ? 1 : 0) : -1;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_fit_cta: one CTA per patch, coordinates staged once in shared memory (SoA), CAP points at most.
 // Warp w owns the contiguous index range [w*chunk, (w+1)*chunk); a thread's slot `it` is point
@@ -363,16 +374,17 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
   float* sy = sx + CAP;
   float* sz = sy + CAP;
   __shared__ double s_part[2][8][9];   // per-warp partial moments, double-buffered by round parity
-  __shared__ int s_pcnt[2][8];
+  __shared__ int s_pcnt[2][8], s_pchg[2][8];
   __shared__ int s_cnt[8][2];
   __shared__ unsigned s_min[FIT_THREADS];
   __shared__ unsigned s_cand[CCAP];
   __shared__ double s_lpr;
   __shared__ double s_fb[8];
   __shared__ unsigned s_T;
-  __shared__ int s_ccount, s_item, s_mn;
+  __shared__ int s_ccount, s_item, s_mn, s_fix, s_refit;
   __shared__ Plane s_plane;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float thf = (float) ap.th_dist;
 
   for (;;) {
     if (tid == 0) s_item = atomicAdd(&wq.head[CLS], 1);
@@ -409,8 +421,15 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
     pl.d = 0.0;
 #pragma unroll
     for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
-    unsigned gmask = 0;
+    unsigned gmask = 0, member = 0;
     int round = 0;
+    double c_lpr = 0.0;
+    Moments tot;   // running sums of the R-GPF phase (meaningful in warp 0)
+    tot.n = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) tot.s1[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) tot.s2[q] = 0.0;
 
     while (state != ST_DONE) {   // state is uniform across the CTA
       const bool seed_round = (state == ST_RVPF || state == ST_SEED);
@@ -538,10 +557,19 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         c[0] = c0x; c[1] = c0y; c[2] = lpr;
       }
       // ---- predicate + moments ----
+      // Seed rounds accumulate their whole set. R-GPF rounds are incremental (see k_fit_warp): every fit of the
+      // R-GPF phase shares the reference point c = (first x, first y, lpr), a round adds (+) / removes (-) only
+      // the points whose membership changed, warp 0 keeps the running sums, and a round without any change is the
+      // fixpoint of S:516-543.
+      const bool incr = !seed_round;
+      if (incr) { c[0] = c0x; c[1] = c0y; c[2] = c_lpr; }
+      else if (state == ST_SEED) c_lpr = c[2];
+      PlaneF pf;
+      pf.n0 = (float) pl.normal[0]; pf.n1 = (float) pl.normal[1]; pf.n2 = (float) pl.normal[2]; pf.d = (float) pl.d;
       double a[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
-      int mn = 0;
+      int mn = 0, nchg = 0;
       unsigned sel = 0;
       for (int it = 0; it < nit; ++it) {
         if (!((amask >> it) & 1u)) continue;
@@ -549,31 +577,45 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         const float x = sx[j], y = sy[j], z = sz[j];
         bool in;
         if (seed_round) in = ((double) z < zthr);                                            // S:108 / S:145
-        else in = have_plane && (point_plane_distance(pl, x, y, z) < ap.th_dist);            // S:525 / S:529
-        if (in) {
-          sel |= 1u << it;
-          const double dx = (double) x - c[0], dy = (double) y - c[1], dz = (double) z - c[2];
-          a[0] += dx; a[1] += dy; a[2] += dz;
-          a[3] += dx * dx; a[4] += dx * dy; a[5] += dx * dz; a[6] += dy * dy; a[7] += dy * dz; a[8] += dz * dz;
-          ++mn;
+        else {
+          int fl = have_plane ? dist_filter(pf, thf, x, y, z) : 0;
+          if (fl < 0) fl = (point_plane_distance(pl, x, y, z) < ap.th_dist) ? 1 : 0;         // S:525 / S:529, exact
+          in = fl != 0;
         }
+        if (in) sel |= 1u << it;
+        double wgt = in ? 1.0 : 0.0;
+        if (incr) {
+          const bool was = (member >> it) & 1u;
+          if (was == in) continue;
+          wgt = in ? 1.0 : -1.0;
+          ++nchg;
+        } else if (!in) continue;
+        const double dx = (double) x - c[0], dy = (double) y - c[1], dz = (double) z - c[2];
+        const double wx = dx * wgt, wy = dy * wgt, wz = dz * wgt;
+        a[0] += wx; a[1] += wy; a[2] += wz;
+        a[3] += wx * dx; a[4] += wx * dy; a[5] += wx * dz; a[6] += wy * dy; a[7] += wy * dz; a[8] += wz * dz;
+        mn += in ? 1 : -1;
       }
+      member = sel;
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
       }
       mn = __reduce_add_sync(0xffffffffu, mn);
+      nchg = __reduce_add_sync(0xffffffffu, nchg);
       const int buf = round & 1;
       ++round;
       if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) s_part[buf][w][q] = a[q];
         s_pcnt[buf][w] = mn;
+        s_pchg[buf][w] = nchg;
       }
       __syncthreads();
       // warp 0 combines the 8 partials (lane q sums quantity q over the warps in a fixed order: bit-reproducible),
-      // solves the 3x3 problem once and publishes the plane; the other warps wait at the second barrier
+      // keeps the running sums of the R-GPF phase, solves the 3x3 problem once and publishes the plane; the other
+      // warps wait at the second barrier
       if (w == 0) {
         double v = 0.0;
         int cn = 0;
@@ -583,6 +625,9 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
         } else if (lane == 9) {
 #pragma unroll
           for (int ww = 0; ww < 8; ++ww) cn += s_pcnt[buf][ww];
+        } else if (lane == 10) {
+#pragma unroll
+          for (int ww = 0; ww < 8; ++ww) cn += s_pchg[buf][ww];
         }
         Moments m;
 #pragma unroll
@@ -590,16 +635,29 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
 #pragma unroll
         for (int q = 0; q < 6; ++q) m.s2[q] = __shfl_sync(0xffffffffu, v, 3 + q);
         m.n = __shfl_sync(0xffffffffu, cn, 9);
-        if (m.n > 0) {
+        const int changed = __shfl_sync(0xffffffffu, cn, 10);
+        bool refit = true;
+        if (incr) {
+          if (changed == 0) refit = false;   // fixpoint
+          else {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) tot.s1[q] += m.s1[q];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) tot.s2[q] += m.s2[q];
+            tot.n += m.n;
+          }
+        } else tot = m;
+        if (refit && tot.n > 0) {
           Plane t;
-          plane_from_moments(m, c, t);
+          plane_from_moments(tot, c, t);
           if (lane == 0) s_plane = t;
         }
-        if (lane == 0) s_mn = m.n;
+        if (lane == 0) { s_mn = tot.n; s_fix = (incr && changed == 0) ? 1 : 0; s_refit = (refit && tot.n > 0) ? 1 : 0; }
       }
       __syncthreads();
       const int tot_n = s_mn;
-      if (tot_n > 0) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
+      const bool fixpoint = s_fix != 0;
+      if (s_refit) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
       // ---- state transition (same machine as k_fit_resident) ----
       if (state == ST_RVPF) {
         if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489
@@ -617,11 +675,11 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(
       } else if (state == ST_GPF) {
         ++gpf_it;
         if (gpf_it >= ap.num_iter - 1) state = ST_FINAL;
+        if (fixpoint) state = ST_DONE;
       } else {   // ST_FINAL
-        gmask = sel;
-        n_ground = tot_n;
         state = ST_DONE;
       }
+      if (state == ST_DONE) { gmask = have_plane ? member : 0u; n_ground = have_plane ? tot_n : 0; }
     }
 
     // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
@@ -910,17 +968,6 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
     lpr = __shfl_sync(0xffffffffu, lpr, 0);
   }
   return lpr;
-}
-
-struct PlaneF { float n0, n1, n2, d; };
-
-// +1: surely below th_dist, 0: surely not, -1: inside the fp32 error bound (decide in double)
-__device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, float y, float z) {
-  const float sf = fmaf(pf.n0, x, fmaf(pf.n1, y, fmaf(pf.n2, z, pf.d)));
-  // |sf - exact| <= 3e-7 * (|x|+|y|+|z|+|d|) (|n_i| <= 1: float coefficients + three fma roundings); 3x margin
-  const float bound = 1e-6f * (fabsf(x) + fabsf(y) + fabsf(z) + fabsf(pf.d) + 1.0f);
-  const float diff = sf - th;
-  return (fabsf(diff) > bound) ? (diff < 0.f ? 1 : 0) : -1;
 }
 
 template <bool STAGE>

@@ -29,7 +29,7 @@ namespace pwpp {
 // k_bin_hist: grid (max_chunks_per_frame, F), 256 threads. Each warp owns 512 consecutive points.
 // Writes bin ids (u16) and the chunk's histogram row (u16[nbp]).
 template <bool FAST>
-__global__ void __launch_bounds__(CHUNK_THREADS) k_bin_hist(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states,
+__global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states,
                                                              Geometry g, AlgoParams ap, int has_intensity, int nbp,
                                                              unsigned short* __restrict__ bin_ids, unsigned short* __restrict__ chist) {
   extern __shared__ unsigned int s_hist[];  // [nbp]
@@ -44,22 +44,29 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_bin_hist(const float4* __rest
   const bool rnr_on = ap.enable_RNR && has_intensity;  // S:161, S:379-382
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int base = blockIdx.x * CHUNK_PTS + warp * WARP_PTS;
-#pragma unroll 4
-  for (int it = 0; it < WARP_ITERS; ++it) {
-    const int i = base + it * 32 + lane;
-    int bin = -1;
-    if (i < n) {
-      const float4 p = ld_stream_f4(pts + p0 + i);
-      if (rnr_on && rnr_hit(p.x, p.y, p.z, p.w, sensor_height, ap)) bin = PW_BIN_RNR(g.nbins);
-      else if (p.z == FLT_MIN) bin = PW_BIN_DROP(g.nbins);  // S:591
-      else bin = FAST ? bin_of_point(p.x, p.y, p.z, g) : bin_of_point_exact(p.x, p.y, p.z, g);
-      bin_ids[p0 + i] = (unsigned short) bin;
-    }
-    // warp-aggregated histogram update: one shared atomic per distinct bin in the warp
-    const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
-    if (bin >= 0) {
-      const unsigned peers = __match_any_sync(act, bin);
-      if ((peers & lanemask_lt()) == 0) atomicAdd(&s_hist[bin], __popc(peers));
+  constexpr int HB = 4;   // independent 128-bit loads in flight per lane
+  const int last = n - 1;
+  for (int h = 0; h < WARP_ITERS; h += HB) {
+    float4 q[HB];
+#pragma unroll
+    for (int u = 0; u < HB; ++u) { const int i = base + (h + u) * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
+#pragma unroll
+    for (int u = 0; u < HB; ++u) {
+      const int i = base + (h + u) * 32 + lane;
+      const float4 p = q[u];
+      int bin = -1;
+      if (i < n) {
+        if (rnr_on && rnr_hit(p.x, p.y, p.z, p.w, sensor_height, ap)) bin = PW_BIN_RNR(g.nbins);
+        else if (p.z == FLT_MIN) bin = PW_BIN_DROP(g.nbins);  // S:591
+        else bin = FAST ? bin_of_point(p.x, p.y, p.z, g) : bin_of_point_exact(p.x, p.y, p.z, g);
+        bin_ids[p0 + i] = (unsigned short) bin;
+      }
+      // warp-aggregated histogram update: one shared atomic per distinct bin in the warp
+      const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
+      if (bin >= 0) {
+        const unsigned peers = __match_any_sync(act, bin);
+        if ((peers & lanemask_lt()) == 0) atomicAdd(&s_hist[bin], __popc(peers));
+      }
     }
   }
   __syncthreads();
@@ -158,11 +165,16 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restr
   const int base = blockIdx.x * CHUNK_PTS + warp * WARP_PTS;
   unsigned int* my = s_wcnt + warp * nbp;
   int bins[WARP_ITERS];
+  // all 16 bin ids of the lane are requested before the first one is used (__syncwarp below is a memory barrier the
+  // compiler will not move loads across)
 #pragma unroll
   for (int it = 0; it < WARP_ITERS; ++it) {
     const int i = base + it * 32 + lane;
-    const int bin = (i < n) ? (int) bin_ids[p0 + i] : -1;
-    bins[it] = bin;
+    bins[it] = (i < n) ? (int) bin_ids[p0 + i] : -1;
+  }
+#pragma unroll
+  for (int it = 0; it < WARP_ITERS; ++it) {
+    const int bin = bins[it];
     const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
     if (bin >= 0) {
       const unsigned peers = __match_any_sync(act, bin);
@@ -180,21 +192,29 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restr
   }
   __syncthreads();
   float4* out = sorted + p0;
+  constexpr int SB = 4;   // points in flight per lane
+  const int last = n - 1;
 #pragma unroll
-  for (int it = 0; it < WARP_ITERS; ++it) {
-    const int i = base + it * 32 + lane;
-    const int bin = bins[it];
-    const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
-    if (bin >= 0) {
-      const unsigned peers = __match_any_sync(act, bin);
-      const unsigned int pos = my[bin] + __popc(peers & lanemask_lt());
-      float4 p = ld_stream_f4(pts + p0 + i);
-      p.w = __int_as_float(i);
-      out[pos] = p;
-      __syncwarp(peers);
-      if ((peers & lanemask_lt()) == 0) my[bin] += __popc(peers);
+  for (int h = 0; h < WARP_ITERS; h += SB) {
+    float4 q[SB];
+#pragma unroll
+    for (int u = 0; u < SB; ++u) { const int i = base + (h + u) * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int i = base + (h + u) * 32 + lane;
+      const int bin = bins[h + u];
+      const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
+      if (bin >= 0) {
+        const unsigned peers = __match_any_sync(act, bin);
+        const unsigned int pos = my[bin] + __popc(peers & lanemask_lt());
+        float4 p = q[u];
+        p.w = __int_as_float(i);
+        out[pos] = p;
+        __syncwarp(peers);
+        if ((peers & lanemask_lt()) == 0) my[bin] += __popc(peers);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -488,40 +508,52 @@ __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restri
 // place in the final index lists (addCloud S:28-31 + toIndices S:18-26). Fitted patches were partitioned by the fit
 // kernels (part[]: ground ascending, then non-ground ascending); patches that were not fitted (below num_min_pts,
 // RNR hits, out-of-range points) are emitted straight from the sorted array in ascending point index.
+constexpr int EMIT_PTS = 16384;   // sorted positions per CTA (amortises the per-CTA copy of the bin tables)
+
 __global__ void __launch_bounds__(256) k_emit(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
                                               const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
                                               int* __restrict__ out_idx) {
-  extern __shared__ int s_off[];  // [nb_all + 1]
+  extern __shared__ int s_emit[];  // s_off[nb_all + 1], then per bin: ground count (-1: not fitted), g_dst, ng_dst
   const int f = blockIdx.y;
   const long long p0 = ft.pt_off[f];
   const int n = (int) (ft.pt_off[f + 1] - p0);
-  const int base = blockIdx.x * CHUNK_PTS;
+  const int base = blockIdx.x * EMIT_PTS;
   if (base >= n) return;
   const int nb_all = g.nbins + PW_NUM_PSEUDO;
+  int* s_off = s_emit;
+  int* s_ng = s_off + nb_all + 1;
+  int* s_gd = s_ng + nb_all;
+  int* s_nd = s_gd + nb_all;
   const int* bo = bin_off + (size_t) f * (nbp + 1);
-  for (int b = threadIdx.x; b <= nb_all; b += blockDim.x) s_off[b] = bo[b];
-  __syncthreads();
   const BinSeg* seg = segs + (size_t) f * nb_all;
   const BinFit* fit = fits + (size_t) f * g.nbins;
+  for (int b = threadIdx.x; b <= nb_all; b += blockDim.x) s_off[b] = bo[b];
+  for (int b = threadIdx.x; b < nb_all; b += blockDim.x) {
+    const BinSeg sg = seg[b];
+    s_gd[b] = sg.g_dst; s_nd[b] = sg.ng_dst;
+    s_ng[b] = (b < g.nbins && fit[b].fitted) ? fit[b].n_ground : -1;
+  }
+  __syncthreads();
   const int total = s_off[nb_all];
-  for (int i0 = base + (threadIdx.x & ~31); i0 < n && i0 < base + CHUNK_PTS; i0 += blockDim.x) {
+  const int end = min(min(n, total), base + EMIT_PTS);
+  for (int i0 = base + (threadIdx.x & ~31); i0 < end; i0 += blockDim.x) {
     // one binary search per warp (largest b with s_off[b] <= i0), then every lane walks forward to its own bin:
     // 32 consecutive sorted positions span very few bins
     int lo = 0, hi = nb_all;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i0) lo = mid; else hi = mid; }
     const int i = i0 + (threadIdx.x & 31);
-    if (i >= n || i >= total) continue;
+    if (i >= end) continue;
     int b = lo;
     while (i >= s_off[b + 1]) ++b;
     const int j = i - s_off[b];
-    const BinSeg sg = seg[b];
-    if (b < g.nbins && fit[b].fitted) {
-      const int ng = fit[b].n_ground;
-      const int dst = (j < ng) ? (sg.g_dst + j) : (sg.ng_dst + (j - ng));
+    const int ng = s_ng[b];
+    if (ng >= 0) {
+      const int dst = (j < ng) ? (s_gd[b] + j) : (s_nd[b] + (j - ng));
       out_idx[p0 + dst] = part[p0 + i];
     } else {
-      if (sg.ng_dst < 0) continue;  // dropped points (S:591)
-      out_idx[p0 + sg.ng_dst + j] = __float_as_int(sorted[p0 + i].w);
+      const int nd = s_nd[b];
+      if (nd < 0) continue;  // dropped points (S:591)
+      out_idx[p0 + nd + j] = __float_as_int(sorted[p0 + i].w);
     }
   }
 }
