@@ -319,7 +319,11 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {total_pts * 16 / 1e9:.2f} GB of points per step vs 126 MB L2"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    # orderly teardown: release the engine (CUDA buffers, streams) while the CUDA context is still alive
+    eng.close()
+    del pts
+    torch.cuda.synchronize()
     dist.close()
 
 

@@ -79,7 +79,7 @@ struct pwpp_ctx {
   int nbp = 0;      // padded number of bins incl. pseudo-bins
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
   bool profiling = false, stage_valid = false;
@@ -156,24 +156,21 @@ int bind_device(pwpp_ctx* ctx) {
   return PWPP_OK;
 }
 
-// launches the whole path for nframes frames whose packed float4 points start at d_pts
-int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity, cudaStream_t s) {
+// Sizes the work buffers for a call over nframes frames (ctx->pt_off filled) and uploads the frame tables.
+int prepare_call(pwpp_ctx* ctx, int nframes, cudaStream_t s) {
   const long long total = ctx->pt_off[nframes];
-  int max_chunks = 0, total_chunks = 0;
+  int total_chunks = 0;
   CU_TRY(ctx->h_pt_off.reserve(nframes + 1));
   CU_TRY(ctx->h_chunk_off.reserve(nframes + 1));
   for (int f = 0; f < nframes; ++f) {
     const long long n = ctx->pt_off[f + 1] - ctx->pt_off[f];
     if (n < 0 || n > 0x7fffffffLL - CHUNK_PTS) return fail(PWPP_ERR_INVALID_ARG, "frame size out of range");
-    const int nch = (int) ((n + CHUNK_PTS - 1) / CHUNK_PTS);
     ctx->h_pt_off.p[f] = ctx->pt_off[f];
     ctx->h_chunk_off.p[f] = total_chunks;
-    total_chunks += nch;
-    max_chunks = std::max(max_chunks, nch);
+    total_chunks += (int) ((n + CHUNK_PTS - 1) / CHUNK_PTS);
   }
   ctx->h_pt_off.p[nframes] = total;
   ctx->h_chunk_off.p[nframes] = total_chunks;
-
   const int nb = ctx->g.nbins, nbp = ctx->nbp, nb_all = nb + PW_NUM_PSEUDO;
   CU_TRY(ctx->d_pt_off.reserve(nframes + 1));
   CU_TRY(ctx->d_chunk_off.reserve(nframes + 1));
@@ -186,26 +183,45 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   CU_TRY(ctx->d_fits.reserve((size_t) nframes * nb));
   CU_TRY(ctx->d_segs.reserve((size_t) nframes * nb_all));
   for (int c = 0; c < NUM_CLASSES; ++c) CU_TRY(ctx->d_wq_items[c].reserve((size_t) nframes * nb));
-  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, 2 * NUM_CLASSES * sizeof(int), s));
   CU_TRY(ctx->d_out_idx.reserve((size_t) total));
   CU_TRY(ctx->d_counts.reserve((size_t) 3 * ctx->num_streams));
   CU_TRY(ctx->d_centers.reserve((size_t) nframes * nb * 3));
   CU_TRY(ctx->d_normals.reserve((size_t) nframes * nb * 3));
-
   CU_TRY(cudaMemcpyAsync(ctx->d_pt_off.p, ctx->h_pt_off.p, (nframes + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
   CU_TRY(cudaMemcpyAsync(ctx->d_chunk_off.p, ctx->h_chunk_off.p, (nframes + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  ctx->last_nframes = nframes;
+  ctx->last_total = total;
+  ctx->counts_fetched = ctx->idx_fetched = ctx->patches_fetched = false;
+  ctx->stage_valid = false;
+  return PWPP_OK;
+}
 
-  FrameTable ft{ctx->d_pt_off.p, ctx->d_chunk_off.p};
-  const bool prof = ctx->profiling;
+// Launches the whole path for frames [f0, f0 + nf) of the prepared call on stream s. A frame range is the same
+// launch sequence over per-frame arrays offset by f0 (frame tables hold absolute point / chunk positions), which is
+// what lets pwpp_estimate_host pipeline chunks of frames against their H2D / D2H copies.
+int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_intensity, cudaStream_t s, bool prof) {
+  int max_chunks = 0;
+  for (int f = f0; f < f0 + nf; ++f) max_chunks = std::max(max_chunks, ctx->h_chunk_off.p[f + 1] - ctx->h_chunk_off.p[f]);
+  const int nb = ctx->g.nbins, nbp = ctx->nbp, nb_all = nb + PW_NUM_PSEUDO;
+  const int nframes = nf;
+  FrameTable ft{ctx->d_pt_off.p + f0, ctx->d_chunk_off.p + f0};
+  StreamState* states = ctx->d_states.p + f0;
+  double* hist = ctx->d_hist.p + (size_t) f0 * 2 * 4 * ctx->hcap;
+  int* bin_off = ctx->d_bin_off.p + (size_t) f0 * (nbp + 1);
+  BinFit* fits = ctx->d_fits.p + (size_t) f0 * nb;
+  BinSeg* segs = ctx->d_segs.p + (size_t) f0 * nb_all;
+  float* centers = ctx->d_centers.p + (size_t) f0 * nb * 3;
+  float* normals = ctx->d_normals.p + (size_t) f0 * nb * 3;
+  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, 2 * NUM_CLASSES * sizeof(int), s));
   int stage = 0;
 #define STAGE_MARK() do { if (prof) CU_TRY(cudaEventRecord(ctx->stage_ev[stage], s)); ++stage; } while (0)
   STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     if (ctx->fast_bin)
-      k_bin_hist<true><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, ctx->d_states.p, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
+      k_bin_hist<true><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
     else
-      k_bin_hist<false><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, ctx->d_states.p, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
+      k_bin_hist<false><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -213,7 +229,7 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = ctx->d_wq_items[c].p;
   wq.count = ctx->d_wq_ctr.p;
   wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
-  k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, ctx->d_bin_off.p, wq, ctx->d_fits.p);
+  k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
   ++ctx->launches;
   STAGE_MARK();
   if (max_chunks > 0) {
@@ -223,46 +239,48 @@ int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity,
   }
   STAGE_MARK();
   // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan)
-  k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
   ++ctx->launches;
   STAGE_MARK();
-  k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
   ++ctx->launches;
   STAGE_MARK();
-  k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
   ++ctx->launches;
   STAGE_MARK();
-  k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
   ++ctx->launches;
   STAGE_MARK();
-  k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, ctx->d_states.p, ctx->g, ctx->ap, nbp, ctx->d_bin_off.p, wq, ctx->d_part.p, ctx->d_fits.p);
+  k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
   ++ctx->launches;
   STAGE_MARK();
-  int* d_ng = ctx->d_counts.p;
-  int* d_np = ctx->d_counts.p + ctx->num_streams;
-  int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams;
+  int* d_ng = ctx->d_counts.p + f0;
+  int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
+  int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
   {
     const size_t gle_smem = (size_t) 6 * ctx->max_sectors * sizeof(double) + (size_t) 2 * ctx->max_sectors * sizeof(int);
-    k_gle<<<nframes, 32, gle_smem, s>>>(ft, ctx->d_states.p, ctx->d_hist.p, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->max_sectors, ctx->d_bin_off.p, ctx->d_fits.p,
-                                        ctx->d_segs.p, d_ng, d_np, ctx->d_centers.p, ctx->d_normals.p, d_nd);
+    k_gle<<<nframes, 32, gle_smem, s>>>(ft, states, hist, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->max_sectors, bin_off, fits, segs, d_ng, d_np, centers, normals, d_nd);
     ++ctx->launches;
   }
   STAGE_MARK();
   if (max_chunks > 0) {
-    dim3 grid((max_chunks * CHUNK_PTS + EMIT_PTS - 1) / EMIT_PTS, nframes);
-    k_emit<<<grid, 256, (4 * nb_all + 1) * sizeof(int), s>>>(ft, ctx->g, nbp, ctx->d_bin_off.p, ctx->d_fits.p, ctx->d_segs.p, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
+    k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
   STAGE_MARK();
 #undef STAGE_MARK
-  ctx->stage_valid = prof;
+  if (prof) ctx->stage_valid = true;
   CU_TRY(cudaGetLastError());
-  ctx->last_nframes = nframes;
-  ctx->last_total = total;
   ctx->last_pts = d_pts;
   ctx->last_stream = s;
-  ctx->counts_fetched = ctx->idx_fetched = ctx->patches_fetched = false;
   return PWPP_OK;
+}
+
+int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity, cudaStream_t s) {
+  int rc = prepare_call(ctx, nframes, s);
+  if (rc) return rc;
+  return launch_range(ctx, 0, nframes, d_pts, has_intensity, s, ctx->profiling);
 }
 
 int check_frame(pwpp_ctx* ctx, int f) {
@@ -364,6 +382,8 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   } while (0)
   CU_TRY_CTX(cudaSetDevice(device));
   CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking));
+  CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev0));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev1));
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
@@ -426,6 +446,8 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
+  if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
   delete ctx;
 }
 
@@ -488,40 +510,69 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
   }
   const long long total = ctx->pt_off[nframes];
   CU_TRY(ctx->d_in.reserve((size_t) std::max<long long>(total, 1)));
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->stream, s_in = ctx->stream_h2d, s_out = ctx->stream_d2h;
   // the staging buffers of the previous call must not be in flight any more
   CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaStreamSynchronize(s_in));
+  CU_TRY(cudaStreamSynchronize(s_out));
+  rc = prepare_call(ctx, nframes, s);
+  if (rc) return rc;
+  CU_TRY(ctx->h_out_idx.reserve((size_t) std::max<long long>(total, 1)));
+  CU_TRY(ctx->h_counts.reserve((size_t) 3 * ctx->num_streams));
   const bool packed = (cols == 4 && col_stride == 1 && row_stride == 4);
   bool staged_any = false;
-  for (int f = 0; f < nframes; ++f) {
-    const int64_t cnt = n[f];
-    if (cnt == 0) continue;
-    bool pinned = false;
-    if (packed) {
-      cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, pts[f]) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
-      else cudaGetLastError();
-    }
-    if (pinned) {  // page-locked caller buffer: DMA straight from it (the private copy of H:152 is the device buffer)
-      CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], pts[f], (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s));
-      continue;
-    }
-    if (!staged_any) { CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1))); staged_any = true; }
-    float4* dst = ctx->h_in.p + ctx->pt_off[f];
-    const float* src = pts[f];
-    if (packed) {
-      std::memcpy(dst, src, (size_t) cnt * sizeof(float4));
-    } else {
-      for (int64_t i = 0; i < cnt; ++i) {
-        const float* r = src + i * row_stride;
-        dst[i] = make_float4(r[0], r[col_stride], r[2 * col_stride], cols == 4 ? r[3 * col_stride] : 0.f);
-      }
-    }
-    CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], dst, (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s));
+  // Chunks of frames flow through three streams: H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1.
+  // ~64 MB of points per chunk keeps every stage busy without delaying the first kernels.
+  int chunk_frames = nframes;
+  if (nframes > 1 && total > 0) {
+    const long long per_frame = std::max<long long>(1, total / nframes);
+    chunk_frames = (int) std::min<long long>(nframes, std::max<long long>(1, (4LL << 20) / per_frame));
   }
-  rc = run_path(ctx, nframes, ctx->d_in.p, cols == 4 ? 1 : 0, s);
-  if (rc) return rc;
+  const int nchunks = (nframes + chunk_frames - 1) / chunk_frames;
+  for (int k = 0; k < nchunks; ++k) {
+    const int f0 = k * chunk_frames, f1 = std::min(nframes, f0 + chunk_frames);
+    for (int f = f0; f < f1; ++f) {
+      const int64_t cnt = n[f];
+      if (cnt == 0) continue;
+      bool pinned = false;
+      if (packed) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, pts[f]) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+      }
+      if (pinned) {  // page-locked caller buffer: DMA straight from it (the private copy of H:152 is the device buffer)
+        CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], pts[f], (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s_in));
+        continue;
+      }
+      if (!staged_any) { CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1))); staged_any = true; }
+      float4* dst = ctx->h_in.p + ctx->pt_off[f];
+      const float* src = pts[f];
+      if (packed) {
+        std::memcpy(dst, src, (size_t) cnt * sizeof(float4));
+      } else {
+        for (int64_t i = 0; i < cnt; ++i) {
+          const float* r = src + i * row_stride;
+          dst[i] = make_float4(r[0], r[col_stride], r[2 * col_stride], cols == 4 ? r[3 * col_stride] : 0.f);
+        }
+      }
+      CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], dst, (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s_in));
+    }
+    CU_TRY(cudaEventRecord(ctx->ev0, s_in));
+    CU_TRY(cudaStreamWaitEvent(s, ctx->ev0, 0));
+    rc = launch_range(ctx, f0, f1 - f0, ctx->d_in.p, cols == 4 ? 1 : 0, s, ctx->profiling && nchunks == 1);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ctx->ev1, s));
+    CU_TRY(cudaStreamWaitEvent(s_out, ctx->ev1, 0));
+    const long long o0 = ctx->pt_off[f0], o1 = ctx->pt_off[f1];
+    if (o1 > o0) CU_TRY(cudaMemcpyAsync(ctx->h_out_idx.p + o0, ctx->d_out_idx.p + o0, (size_t) (o1 - o0) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+    for (int q = 0; q < 3; ++q)
+      CU_TRY(cudaMemcpyAsync(ctx->h_counts.p + (size_t) q * ctx->num_streams + f0, ctx->d_counts.p + (size_t) q * ctx->num_streams + f0,
+                             (size_t) (f1 - f0) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+  }
+  CU_TRY(cudaStreamSynchronize(s_out));
   CU_TRY(cudaStreamSynchronize(s));
+  ctx->counts_fetched = true;
+  ctx->idx_fetched = true;
   ctx->last_time_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
   return PWPP_OK;
 }

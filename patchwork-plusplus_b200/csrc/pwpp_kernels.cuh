@@ -508,53 +508,43 @@ __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restri
 // place in the final index lists (addCloud S:28-31 + toIndices S:18-26). Fitted patches were partitioned by the fit
 // kernels (part[]: ground ascending, then non-ground ascending); patches that were not fitted (below num_min_pts,
 // RNR hits, out-of-range points) are emitted straight from the sorted array in ascending point index.
-constexpr int EMIT_PTS = 16384;   // sorted positions per CTA (amortises the per-CTA copy of the bin tables)
+constexpr int EMIT_WARPS = 8;     // bins per CTA: every warp copies the two parts of one bin, big bins are split
 
-__global__ void __launch_bounds__(256) k_emit(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
-                                              const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
-                                              int* __restrict__ out_idx) {
-  extern __shared__ int s_emit[];  // s_off[nb_all + 1], then per bin: ground count (-1: not fitted), g_dst, ng_dst
+// One warp per (frame, bin): the ground part and the non-ground part of a bin are contiguous both in `part` /
+// `sorted` and in the output lists, so the copy is two coalesced streams (typical bins: a few to a few thousand
+// points; a pathological bin holding a whole frame is copied by one warp, which is slow but correct).
+__global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
+                                                          const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
+                                                          int* __restrict__ out_idx) {
   const int f = blockIdx.y;
-  const long long p0 = ft.pt_off[f];
-  const int n = (int) (ft.pt_off[f + 1] - p0);
-  const int base = blockIdx.x * EMIT_PTS;
-  if (base >= n) return;
   const int nb_all = g.nbins + PW_NUM_PSEUDO;
-  int* s_off = s_emit;
-  int* s_ng = s_off + nb_all + 1;
-  int* s_gd = s_ng + nb_all;
-  int* s_nd = s_gd + nb_all;
+  const int b = blockIdx.x * EMIT_WARPS + (threadIdx.x >> 5);
+  if (b >= nb_all) return;
+  const int lane = lane_id();
+  const long long p0 = ft.pt_off[f];
   const int* bo = bin_off + (size_t) f * (nbp + 1);
-  const BinSeg* seg = segs + (size_t) f * nb_all;
-  const BinFit* fit = fits + (size_t) f * g.nbins;
-  for (int b = threadIdx.x; b <= nb_all; b += blockDim.x) s_off[b] = bo[b];
-  for (int b = threadIdx.x; b < nb_all; b += blockDim.x) {
-    const BinSeg sg = seg[b];
-    s_gd[b] = sg.g_dst; s_nd[b] = sg.ng_dst;
-    s_ng[b] = (b < g.nbins && fit[b].fitted) ? fit[b].n_ground : -1;
-  }
-  __syncthreads();
-  const int total = s_off[nb_all];
-  const int end = min(min(n, total), base + EMIT_PTS);
-  for (int i0 = base + (threadIdx.x & ~31); i0 < end; i0 += blockDim.x) {
-    // one binary search per warp (largest b with s_off[b] <= i0), then every lane walks forward to its own bin:
-    // 32 consecutive sorted positions span very few bins
-    int lo = 0, hi = nb_all;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i0) lo = mid; else hi = mid; }
-    const int i = i0 + (threadIdx.x & 31);
-    if (i >= end) continue;
-    int b = lo;
-    while (i >= s_off[b + 1]) ++b;
-    const int j = i - s_off[b];
-    const int ng = s_ng[b];
-    if (ng >= 0) {
-      const int dst = (j < ng) ? (s_gd[b] + j) : (s_nd[b] + (j - ng));
-      out_idx[p0 + dst] = part[p0 + i];
-    } else {
-      const int nd = s_nd[b];
-      if (nd < 0) continue;  // dropped points (S:591)
-      out_idx[p0 + nd + j] = __float_as_int(sorted[p0 + i].w);
+  const int off = bo[b], nbin = bo[b + 1] - off;
+  if (nbin == 0) return;
+  const BinSeg sg = segs[(size_t) f * nb_all + b];
+  int ng = -1;
+  if (b < g.nbins) { const BinFit& r = fits[(size_t) f * g.nbins + b]; if (r.fitted) ng = r.n_ground; }
+  const int j0 = 0, j1 = nbin;
+  if (ng >= 0) {
+    const int* src = part + p0 + off;
+    for (int j = j0 + lane; j < j1; j += 128) {   // four independent loads in flight per lane
+      int v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int jj = j + 32 * u; v[u] = src[jj < j1 ? jj : j1 - 1]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + 32 * u;
+        if (jj < j1) out_idx[p0 + ((jj < ng) ? (sg.g_dst + jj) : (sg.ng_dst + (jj - ng)))] = v[u];
+      }
     }
+  } else {
+    if (sg.ng_dst < 0) return;  // dropped points (S:591)
+    const float4* src = sorted + p0 + off;
+    for (int j = j0 + lane; j < j1; j += 32) out_idx[p0 + sg.ng_dst + j] = __float_as_int(src[j].w);
   }
 }
 

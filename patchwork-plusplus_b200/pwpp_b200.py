@@ -86,8 +86,12 @@ class Engine:
             self._h = None
 
     def __del__(self):
+        # at interpreter shutdown the CUDA runtime may already be torn down: only release explicitly-open handles
+        # while the library is still importable
         try:
-            self.close()
+            import sys
+            if sys is not None and not sys.is_finalizing():
+                self.close()
         except Exception:
             pass
 
