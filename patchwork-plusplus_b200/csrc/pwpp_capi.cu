@@ -82,6 +82,8 @@ struct pwpp_ctx {
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
+  cudaStream_t side[4] = {};              // side streams of the concurrent fit kernels
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
   bool profiling = false, stage_valid = false;
   long long launches = 0;
 
@@ -238,22 +240,33 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     ++ctx->launches;
   }
   STAGE_MARK();
-  // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan)
-  k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-  ++ctx->launches;
-  STAGE_MARK();
-  k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-  ++ctx->launches;
-  STAGE_MARK();
-  k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-  ++ctx->launches;
-  STAGE_MARK();
-  k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-  ++ctx->launches;
-  STAGE_MARK();
-  k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-  ++ctx->launches;
-  STAGE_MARK();
+  // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan). The classes are independent:
+  // unless per-stage timing is requested they run on side streams so that the tail of one class (few long patches
+  // left) overlaps the start of the next.
+  if (prof) {
+    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    STAGE_MARK();
+    k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    STAGE_MARK();
+    k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    STAGE_MARK();
+    k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    STAGE_MARK();
+    k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    STAGE_MARK();
+  } else {
+    CU_TRY(cudaEventRecord(ctx->ev_fork, s));
+    for (int q = 0; q < 4; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
+    // longest class first on the main stream
+    k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), ctx->side[0]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), ctx->side[1]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, ctx->side[2]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_stream<<<ctx->fit_grid[4], 128, 0, ctx->side[3]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    for (int q = 0; q < 4; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
+    stage += 5;
+  }
+  ctx->launches += 5;
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
@@ -387,6 +400,11 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   CU_TRY_CTX(cudaEventCreate(&ctx->ev0));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev1));
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
+  CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  for (int q = 0; q < 4; ++q) {
+    CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking));
+    CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_join[q], cudaEventDisableTiming));
+  }
   CU_TRY_CTX(ctx->d_states.reserve(num_streams));
   CU_TRY_CTX(ctx->d_states_init.reserve(num_streams));
   {
@@ -435,6 +453,8 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int q = 0; q < 4; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
   ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release();
@@ -541,7 +561,12 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
         else cudaGetLastError();
       }
       if (pinned) {  // page-locked caller buffer: DMA straight from it (the private copy of H:152 is the device buffer)
-        CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], pts[f], (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s_in));
+        // frames that follow each other in the caller's buffer travel as one copy
+        int f_last = f;
+        int64_t run = cnt;
+        while (f_last + 1 < f1 && n[f_last + 1] > 0 && pts[f_last + 1] == pts[f_last] + n[f_last] * 4) { ++f_last; run += n[f_last]; }
+        CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], pts[f], (size_t) run * sizeof(float4), cudaMemcpyHostToDevice, s_in));
+        f = f_last;
         continue;
       }
       if (!staged_any) { CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1))); staged_any = true; }

@@ -201,12 +201,14 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
     pl.d = 0.0;
 #pragma unroll
     for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
-    unsigned gmask = 0;
+    unsigned gmask = 0, prev_sel = 0;
+    bool have_prev = false;   // prev_sel is the set the current plane was fitted to (a SEED / GPF round, not R-VPF)
 
     // ---- rounds: one pass over the points + one plane fit each ----
     while (__any_sync(0xffffffffu, state != ST_DONE)) {
       const bool active = state != ST_DONE;
       const bool seed_round = active && (state == ST_RVPF || state == ST_SEED);
+      const bool seed_round_was_rvpf = (state == ST_RVPF);
       double c[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
       double zthr = 0.0;
       // (1) LPR selection for seed rounds: 32-step bisection on order-preserving keys with group-wide counting
@@ -286,6 +288,8 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
 #pragma unroll
       for (int q = 0; q < 6; ++q) m.s2[q] = Ops::sum_d(m.s2[q], nullptr);
       m.n = Ops::sum_i(m.n, nullptr);
+      // every lane of the warp takes part in this reduction (the groups of a warp are in different states)
+      const bool set_unchanged = Ops::sum_i((active && sel != prev_sel) ? 1 : 0, nullptr) == 0;
       // (3) plane of the selected set; an empty set keeps the previous plane (S:49)
       if (active && m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
       // (4) state transition
@@ -303,11 +307,15 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
       } else if (state == ST_GPF) {
         ++gpf_it;
         if (gpf_it >= ap.num_iter - 1) state = ST_FINAL;
+        // fixpoint of S:516-543: the set selected by the current plane equals the set that plane was fitted to,
+        // so every later iteration selects it again and refits the same plane
+        if (set_unchanged && have_prev) { gmask = sel; n_ground = m.n; state = ST_DONE; }
       } else if (state == ST_FINAL) {
         gmask = sel;
         n_ground = m.n;
         state = ST_DONE;
       }
+      if (active) { have_prev = !seed_round_was_rvpf; prev_sel = sel; }
     }
 
     // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
