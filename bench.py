@@ -253,6 +253,7 @@ def run_ours(args):
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     torch.cuda.synchronize()
     eng.set_profiling(False)
+    ms_ranks = dist.gather_floats(ms) if hasattr(dist, 'gather_floats') else [ms]
     ms = dist.max_over_ranks(ms)
     value = world * F * args.steps / (ms / 1e3)
 
@@ -317,7 +318,7 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / args.steps, "ms_per_step_ranks": [m / args.steps for m in ms_ranks], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"batch={F} synthetic {args.sensor} frames (~{mean_pts / 1e3:.0f}k pts each) per GPU, fresh stream state per frame, device-resident input",
                        "frames_per_gpu": F, "mean_points": mean_pts, "sharding": "frames by global index, no collective",

@@ -114,8 +114,11 @@ struct pwpp_ctx {
   DevBuf<float> d_xyz;            // gather scratch
 
   PinBuf<float4> h_in;
-  PinBuf<long long> h_pt_off;
-  PinBuf<int> h_chunk_off;
+  PinBuf<long long> h_pt_off_buf[2];      // double-buffered: a call never waits for the previous call's upload
+  PinBuf<int> h_chunk_off_buf[2];
+  cudaEvent_t tab_ev[2] = {nullptr, nullptr};
+  int tab_cur = 0;
+  std::vector<int> chunk_off;             // host copy of the current call's chunk table
   PinBuf<int> h_out_idx;
   PinBuf<int> h_counts;
   PinBuf<float> h_centers, h_normals;
@@ -162,17 +165,25 @@ int bind_device(pwpp_ctx* ctx) {
 int prepare_call(pwpp_ctx* ctx, int nframes, cudaStream_t s) {
   const long long total = ctx->pt_off[nframes];
   int total_chunks = 0;
-  CU_TRY(ctx->h_pt_off.reserve(nframes + 1));
-  CU_TRY(ctx->h_chunk_off.reserve(nframes + 1));
+  ctx->tab_cur ^= 1;
+  const int tb = ctx->tab_cur;
+  PinBuf<long long>& h_pt_off = ctx->h_pt_off_buf[tb];
+  PinBuf<int>& h_chunk_off = ctx->h_chunk_off_buf[tb];
+  CU_TRY(cudaEventSynchronize(ctx->tab_ev[tb]));   // upload issued two calls ago: long finished
+  CU_TRY(h_pt_off.reserve(nframes + 1));
+  CU_TRY(h_chunk_off.reserve(nframes + 1));
+  ctx->chunk_off.assign(nframes + 1, 0);
   for (int f = 0; f < nframes; ++f) {
     const long long n = ctx->pt_off[f + 1] - ctx->pt_off[f];
     if (n < 0 || n > 0x7fffffffLL - CHUNK_PTS) return fail(PWPP_ERR_INVALID_ARG, "frame size out of range");
-    ctx->h_pt_off.p[f] = ctx->pt_off[f];
-    ctx->h_chunk_off.p[f] = total_chunks;
+    h_pt_off.p[f] = ctx->pt_off[f];
+    h_chunk_off.p[f] = total_chunks;
+    ctx->chunk_off[f] = total_chunks;
     total_chunks += (int) ((n + CHUNK_PTS - 1) / CHUNK_PTS);
   }
-  ctx->h_pt_off.p[nframes] = total;
-  ctx->h_chunk_off.p[nframes] = total_chunks;
+  h_pt_off.p[nframes] = total;
+  h_chunk_off.p[nframes] = total_chunks;
+  ctx->chunk_off[nframes] = total_chunks;
   const int nb = ctx->g.nbins, nbp = ctx->nbp, nb_all = nb + PW_NUM_PSEUDO;
   CU_TRY(ctx->d_pt_off.reserve(nframes + 1));
   CU_TRY(ctx->d_chunk_off.reserve(nframes + 1));
@@ -189,8 +200,9 @@ int prepare_call(pwpp_ctx* ctx, int nframes, cudaStream_t s) {
   CU_TRY(ctx->d_counts.reserve((size_t) 3 * ctx->num_streams));
   CU_TRY(ctx->d_centers.reserve((size_t) nframes * nb * 3));
   CU_TRY(ctx->d_normals.reserve((size_t) nframes * nb * 3));
-  CU_TRY(cudaMemcpyAsync(ctx->d_pt_off.p, ctx->h_pt_off.p, (nframes + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
-  CU_TRY(cudaMemcpyAsync(ctx->d_chunk_off.p, ctx->h_chunk_off.p, (nframes + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(ctx->d_pt_off.p, h_pt_off.p, (nframes + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(ctx->d_chunk_off.p, h_chunk_off.p, (nframes + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaEventRecord(ctx->tab_ev[tb], s));
   ctx->last_nframes = nframes;
   ctx->last_total = total;
   ctx->counts_fetched = ctx->idx_fetched = ctx->patches_fetched = false;
@@ -203,7 +215,7 @@ int prepare_call(pwpp_ctx* ctx, int nframes, cudaStream_t s) {
 // what lets pwpp_estimate_host pipeline chunks of frames against their H2D / D2H copies.
 int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_intensity, cudaStream_t s, bool prof) {
   int max_chunks = 0;
-  for (int f = f0; f < f0 + nf; ++f) max_chunks = std::max(max_chunks, ctx->h_chunk_off.p[f + 1] - ctx->h_chunk_off.p[f]);
+  for (int f = f0; f < f0 + nf; ++f) max_chunks = std::max(max_chunks, ctx->chunk_off[f + 1] - ctx->chunk_off[f]);
   const int nb = ctx->g.nbins, nbp = ctx->nbp, nb_all = nb + PW_NUM_PSEUDO;
   const int nframes = nf;
   FrameTable ft{ctx->d_pt_off.p + f0, ctx->d_chunk_off.p + f0};
@@ -400,6 +412,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   CU_TRY_CTX(cudaEventCreate(&ctx->ev0));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev1));
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
+  for (int i = 0; i < 2; ++i) CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
   CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   for (int q = 0; q < 4; ++q) {
     CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking));
@@ -454,6 +467,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 2; ++i) if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);
   for (int q = 0; q < 4; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
@@ -461,7 +475,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int c = 0; c < NUM_CLASSES; ++c) ctx->d_wq_items[c].release();
   ctx->d_out_idx.release(); ctx->d_counts.release();
   ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();
-  ctx->h_in.release(); ctx->h_pt_off.release(); ctx->h_chunk_off.release(); ctx->h_out_idx.release(); ctx->h_counts.release();
+  ctx->h_in.release(); for (int i = 0; i < 2; ++i) { ctx->h_pt_off_buf[i].release(); ctx->h_chunk_off_buf[i].release(); } ctx->h_out_idx.release(); ctx->h_counts.release();
   ctx->h_centers.release(); ctx->h_normals.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -615,8 +629,8 @@ int pwpp_estimate_device(pwpp_ctx* ctx, int nframes, const void* d_pts, const in
   }
   if (ctx->pt_off[nframes] > 0 && !d_pts) return fail(PWPP_ERR_INVALID_ARG, "d_pts is NULL");
   cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
-  // the pinned frame tables of the previous call must have been consumed before they are rewritten
-  if (ctx->last_stream) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  // work buffers are reused stream-ordered: a call on a different stream than the previous one waits for it
+  if (ctx->last_stream && ctx->last_stream != s) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
   rc = run_path(ctx, nframes, (const float4*) d_pts + h_offsets[0], has_intensity, s);
   if (rc) return rc;
   ctx->last_time_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();

@@ -74,6 +74,15 @@ class Dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_floats(self, value: float):
+        """Every rank's value, in rank order."""
+        if not self.pg:
+            return [float(value)]
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, float(value))
+        return out
+
     def gather_ints(self, values):
         """All ranks' integer lists concatenated in rank order (rank 0's view; used by tests for result checks)."""
         if not self.pg:
