@@ -221,7 +221,13 @@ def run_ours(args):
     total_pts = int(offs_np[-1])
     mean_pts = total_pts / F
     eng = pwpp_b200.Engine(device=local, num_streams=F, max_points_per_frame=int(np.diff(offs_np).max()))
-    stream = torch.cuda.current_stream().cuda_stream
+    # All timing uses CUDA events ON THE STREAM THE KERNELS RUN ON: an explicit torch stream whose handle is passed to
+    # pwpp_estimate_device (the legacy default stream has handle 0, which the C-ABI reads as "use the ctx's own
+    # stream" - torch events would then not see the kernels at all).
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         eng.reset()  # every frame on a fresh stream state (config 3); stream-ordered, no host sync

@@ -202,7 +202,7 @@ int pwpp_copy_bin_ids(pwpp_ctx* ctx, int f, uint16_t* dst /* [n_f] */);
 void* pwpp_host_alloc(size_t bytes);
 void pwpp_host_free(void* p);
 
-#define PWPP_NUM_STAGES 10  /* bin_hist, bin_scan, scatter, fit_S, fit_L2, fit_L1, fit_M, fit_X, gle, emit */
+#define PWPP_NUM_STAGES 11  /* bin_hist, bin_scan, scatter, fit_S, fit_L3, fit_L2, fit_L1, fit_M, fit_X, gle, emit */
 /* With profiling on, CUDA events are recorded around every kernel of the following estimate calls;
  * pwpp_stage_times_ms() synchronizes and returns the device time of each stage of the LAST call. */
 int pwpp_set_profiling(pwpp_ctx* ctx, int enabled);

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -82,8 +83,8 @@ struct pwpp_ctx {
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
-  cudaStream_t side[4] = {};              // side streams of the concurrent fit kernels
-  cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
+  cudaStream_t side[5] = {};              // side streams of the concurrent fit kernels
+  cudaEvent_t ev_fork = nullptr, ev_join[5] = {};
   bool profiling = false, stage_valid = false;
   long long launches = 0;
 
@@ -106,7 +107,8 @@ struct pwpp_ctx {
   DevBuf<BinSeg> d_segs;          // [F][nbins+3]
   DevBuf<int> d_wq_items[NUM_CLASSES];  // fit work queues
   DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES]: counts, heads
-  int fit_grid[NUM_CLASSES] = {0, 0, 0, 0, 0};  // persistent grid sizes
+  int fit_grid[NUM_CLASSES] = {0, 0, 0, 0, 0, 0};  // persistent grid sizes
+  int fit_grid_l1w = 0;
   int max_sectors = 0;
   DevBuf<int> d_out_idx;
   DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
@@ -255,30 +257,43 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan). The classes are independent:
   // unless per-stage timing is requested they run on side streams so that the tail of one class (few long patches
   // left) overlaps the start of the next.
-  if (prof) {
-    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+#define FIT_ARGS ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits
+  static const bool serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;   // diagnostic switch
+  // 513..2048-point patches: the barrier-free streaming warp kernel beats the CTA kernel at this size (measured on
+  // B200: 0.88 vs 1.23 ms per 1024 frames); PWPP_L1_CTA=1 switches back for comparison
+  static const bool l1_warp = std::getenv("PWPP_L1_CTA") == nullptr;
+  const size_t sm_l1 = 3 * 2048 * sizeof(float), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
+  const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4);
+  if (prof || serial_fit) {
+    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(FIT_ARGS);
     STAGE_MARK();
-    k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_cta<8192, 4><<<ctx->fit_grid[4], FIT_THREADS, sm_l3, s>>>(FIT_ARGS);
     STAGE_MARK();
-    k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_cta<4096, 3><<<ctx->fit_grid[3], FIT_THREADS, sm_l2, s>>>(FIT_ARGS);
     STAGE_MARK();
-    k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    if (l1_warp) k_fit_warp<false, 2, 2><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, s>>>(FIT_ARGS);
+    else k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, sm_l1, s>>>(FIT_ARGS);
     STAGE_MARK();
-    k_fit_stream<<<ctx->fit_grid[4], 128, 0, s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
+    k_fit_warp<true, 1, 1><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, s>>>(FIT_ARGS);
+    STAGE_MARK();
+    k_fit_stream<<<ctx->fit_grid[5], 128, 0, s>>>(FIT_ARGS);
     STAGE_MARK();
   } else {
     CU_TRY(cudaEventRecord(ctx->ev_fork, s));
-    for (int q = 0; q < 4; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
-    // longest class first on the main stream
-    k_fit_cta<8192, 3><<<ctx->fit_grid[3], FIT_THREADS, 3 * 8192 * sizeof(float), s>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-    k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, 3 * 2048 * sizeof(float), ctx->side[0]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-    k_fit_warp<true><<<ctx->fit_grid[1], FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4), ctx->side[1]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, ctx->side[2]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-    k_fit_stream<<<ctx->fit_grid[4], 128, 0, ctx->side[3]>>>(ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits);
-    for (int q = 0; q < 4; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
-    stage += 5;
+    for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
+    // longest classes first
+    k_fit_cta<8192, 4><<<ctx->fit_grid[4], FIT_THREADS, sm_l3, s>>>(FIT_ARGS);
+    k_fit_cta<4096, 3><<<ctx->fit_grid[3], FIT_THREADS, sm_l2, ctx->side[0]>>>(FIT_ARGS);
+    if (l1_warp) k_fit_warp<false, 2, 2><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, ctx->side[1]>>>(FIT_ARGS);
+    else k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, sm_l1, ctx->side[1]>>>(FIT_ARGS);
+    k_fit_warp<true, 1, 1><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, ctx->side[2]>>>(FIT_ARGS);
+    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, ctx->side[3]>>>(FIT_ARGS);
+    k_fit_stream<<<ctx->fit_grid[5], 128, 0, ctx->side[4]>>>(FIT_ARGS);
+    for (int q = 0; q < 5; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
+    stage += 6;
   }
-  ctx->launches += 5;
+#undef FIT_ARGS
+  ctx->launches += 6;
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
@@ -302,10 +317,32 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   return PWPP_OK;
 }
 
+// Frames per launch sequence. The five persistent fit kernels of one sequence overlap on side streams; with a very
+// large batch each of them saturates the SMs' register file in turn and the overlap is lost, so a big call is
+// processed as consecutive sub-batches (measured on B200: 256-frame sub-batches of ~120k-point frames run at
+// 0.81 ms each, a single 1024-frame sequence takes 4.9 ms). Sized by points so that dense frames get fewer frames.
+long long subbatch_points() {
+  static long long v = [] {
+    const char* e = std::getenv("PWPP_SUBBATCH_POINTS");
+    return e ? std::atoll(e) : (1LL << 62);   // default: one sequence per call (sub-batching measured slower on B200)
+  }();
+  return v;
+}
+
 int run_path(pwpp_ctx* ctx, int nframes, const float4* d_pts, int has_intensity, cudaStream_t s) {
   int rc = prepare_call(ctx, nframes, s);
   if (rc) return rc;
-  return launch_range(ctx, 0, nframes, d_pts, has_intensity, s, ctx->profiling);
+  if (ctx->profiling) return launch_range(ctx, 0, nframes, d_pts, has_intensity, s, true);
+  const long long cap = subbatch_points();
+  int f0 = 0;
+  while (f0 < nframes) {
+    int f1 = f0 + 1;
+    while (f1 < nframes && ctx->pt_off[f1 + 1] - ctx->pt_off[f0] <= cap) ++f1;
+    rc = launch_range(ctx, f0, f1 - f0, d_pts, has_intensity, s, false);
+    if (rc) return rc;
+    f0 = f1;
+  }
+  return PWPP_OK;
 }
 
 int check_frame(pwpp_ctx* ctx, int f) {
@@ -414,7 +451,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
   for (int i = 0; i < 2; ++i) CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
   CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 5; ++q) {
     CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking));
     CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_join[q], cudaEventDisableTiming));
   }
@@ -431,14 +468,21 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   {
     cudaDeviceProp prop;
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
-    int per_sm[NUM_CLASSES] = {1, 1, 1, 1, 1};
+    int per_sm[NUM_CLASSES] = {1, 1, 1, 1, 1, 1};
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<4096, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 4096 * sizeof(float))));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_fit_resident<8, 8, 0>, FIT_THREADS, 0));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_warp<true>, FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4)));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_warp<true, 1, 1>, FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fit_cta<2048, 2>, FIT_THREADS, 3 * 2048 * sizeof(float)));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_fit_cta<8192, 3>, FIT_THREADS, 3 * 8192 * sizeof(float)));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_fit_stream, 128, 0));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_fit_cta<4096, 3>, FIT_THREADS, 3 * 4096 * sizeof(float)));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_fit_cta<8192, 4>, FIT_THREADS, 3 * 8192 * sizeof(float)));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[5], k_fit_stream, 128, 0));
+    {
+      int l1w = 1;
+      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&l1w, k_fit_warp<false, 2, 2>, FITW_WARPS * 32, 0));
+      ctx->fit_grid_l1w = std::max(1, l1w) * prop.multiProcessorCount;
+    }
     for (int c = 0; c < NUM_CLASSES; ++c) ctx->fit_grid[c] = std::max(1, per_sm[c]) * prop.multiProcessorCount;
     const size_t gle_smem = (size_t) 6 * max_sectors * sizeof(double) + (size_t) 2 * max_sectors * sizeof(int);
     if (gle_smem > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_gle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gle_smem));
@@ -468,7 +512,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int i = 0; i < 2; ++i) if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);
-  for (int q = 0; q < 4; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
+  for (int q = 0; q < 5; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
   ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release();
@@ -525,7 +569,7 @@ int pwpp_stage_times_ms(pwpp_ctx* ctx, float* ms) {
   return PWPP_OK;
 }
 const char* pwpp_stage_name(int stage) {
-  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit_S", "k_fit_L2", "k_fit_L1", "k_fit_M", "k_fit_X", "k_gle", "k_emit"};
+  static const char* names[PWPP_NUM_STAGES] = {"k_bin_hist", "k_bin_scan", "k_scatter", "k_fit_S", "k_fit_L3", "k_fit_L2", "k_fit_L1", "k_fit_M", "k_fit_X", "k_gle", "k_emit"};
   return (stage >= 0 && stage < PWPP_NUM_STAGES) ? names[stage] : "";
 }
 int64_t pwpp_launch_count(const pwpp_ctx* ctx) { return ctx ? ctx->launches : 0; }

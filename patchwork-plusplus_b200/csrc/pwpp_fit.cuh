@@ -8,8 +8,9 @@
 // items from device-side queues built by k_bin_scan:
 //     class S   n <= 64     8 lanes x 8 points in registers,  32 patches per CTA   (k_fit_resident)
 //     class M   n <= 512    1 warp  x 16 points in registers,  8 patches per CTA   (k_fit_resident)
-//     class L1  n <= 2048   1 CTA, points staged in 24 KB of shared memory         (k_fit_cta)
-//     class L2  n <= 8192   1 CTA, points staged in 96 KB of shared memory         (k_fit_cta)
+//     class L1  n <= 2048   1 warp per patch, points streamed from L2, 4 loads in flight (k_fit_warp<false>)
+//     class L2  n <= 4096   1 CTA, points staged in 48 KB of shared memory         (k_fit_cta)
+//     class L3  n <= 8192   1 CTA, points staged in 96 KB of shared memory         (k_fit_cta)
 //     class X   n >  8192   streaming fallback (k_fit_stream, points re-read from L2 each pass)
 // All patches of a CTA advance in lock-step "rounds"; a round is one pass over the points (seed selection or
 // distance filter + moment accumulation in double) followed by ONE pooled eigen-solve in which lane i of warp 0
@@ -28,8 +29,8 @@
 namespace pwpp {
 
 constexpr int FIT_THREADS = 256;
-constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 8192;
-constexpr int NUM_CLASSES = 5;  // S, M, L1, L2, X
+constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 4096, CLS_L3_MAX = 8192;
+constexpr int NUM_CLASSES = 6;  // S, M, L1, L2, L3, X
 
 // device-side work queues, filled by k_bin_scan
 struct WorkQueues {
@@ -372,7 +373,7 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
 // selected exactly by one warp.
 template <int CAP, int CLS>
-__global__ void __launch_bounds__(FIT_THREADS, (CAP <= 2048 ? 3 : 2)) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+__global__ void __launch_bounds__(FIT_THREADS, (CAP <= 4096 ? 3 : 2)) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
   constexpr int ITERS = CAP / FIT_THREADS;   // 8 or 32 slots per thread
@@ -876,7 +877,7 @@ __device__ __forceinline__ Moments accumulate(const float4* __restrict__ P, int 
 //    round only adds (+) / removes (-) the points whose membership changed w.r.t. the previous set. A round
 //    without any change has reached the fixpoint of S:516-543 (same set => same plane => same next set) and the
 //    remaining iterations are skipped — exactly, not approximately.
-constexpr int WARP_CAP = CLS_L2_MAX;            // 8192 points -> 256 iterations
+constexpr int WARP_CAP = CLS_L3_MAX;            // 8192 points -> 256 iterations
 constexpr int FITW_WARPS = 8;
 constexpr int FITW_U = 4;                       // loads in flight per lane
 
@@ -978,11 +979,11 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-template <bool STAGE>
+template <bool STAGE, int CLS_HI, int CLS_LO>
 __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
-  constexpr int CAP = STAGE ? CLS_M_MAX : WARP_CAP;
+  constexpr int CAP = STAGE ? CLS_M_MAX : (CLS_HI == 2 ? CLS_L1_MAX : WARP_CAP);
   __shared__ unsigned s_alive[FITW_WARPS][CAP / 32];
   __shared__ unsigned s_member[FITW_WARPS][CAP / 32];
   __shared__ float s_sel[FITW_WARPS][128];
@@ -992,8 +993,8 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
   unsigned* alive_w = s_alive[warp];
   unsigned* member_w = s_member[warp];
   float* sel_buf = s_sel[warp];
-  int cls = STAGE ? 1 : 3;   // queue being drained: M, or L2 then L1 (long patches first)
-  const int cls_last = STAGE ? 1 : 2;
+  int cls = CLS_HI;          // queues being drained, longest patches first
+  const int cls_last = CLS_LO;
   const float thf = (float) ap.th_dist;
 
   for (;;) {

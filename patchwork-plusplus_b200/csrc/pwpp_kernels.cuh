@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __r
   const int base = blockIdx.x * CHUNK_PTS + warp * WARP_PTS;
   constexpr int HB = 4;   // independent 128-bit loads in flight per lane
   const int last = n - 1;
+#pragma unroll 1
   for (int h = 0; h < WARP_ITERS; h += HB) {
     float4 q[HB];
 #pragma unroll
@@ -119,7 +120,7 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
     }
   }
   // work queues
-  auto cls_of = [](int n) { return n <= CLS_S_MAX ? 0 : n <= CLS_M_MAX ? 1 : n <= CLS_L1_MAX ? 2 : n <= CLS_L2_MAX ? 3 : 4; };
+  auto cls_of = [](int n) { return n <= CLS_S_MAX ? 0 : n <= CLS_M_MAX ? 1 : n <= CLS_L1_MAX ? 2 : n <= CLS_L2_MAX ? 3 : n <= CLS_L3_MAX ? 4 : 5; };
   for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
     const int n = s_scan[b + 1] - s_scan[b];
     if (n >= num_min_pts && n > 0) atomicAdd(&s_cls_cnt[cls_of(n)], 1);

@@ -80,6 +80,14 @@ PW_HD float fsqrt(float a) {
 
 #define PW_PI 3.14159265358979323846 /* M_PI, reference patchworkpp.h:4-6 */
 
+// double atan2 of the exact (rare) paths: kept out of line on the device so that the unrolled hot loops of the
+// binning kernel do not carry eight inlined copies of it (instruction-cache footprint)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__ inline double atan2_exact(double y, double x) { return atan2(y, x); }
+#else
+inline double atan2_exact(double y, double x) { return atan2(y, x); }
+#endif
+
 // ---- concentric-zone geometry + thresholds (reference Params, H:42-112, and ctor H:120-134) -------
 struct Geometry {
   double min_ranges[4];    // H:122-125
@@ -118,7 +126,7 @@ PW_HD bool rnr_hit(float x, float y, float z, float intensity, double sensor_hei
   if (!(zd < dsub(-sensor_height, 0.8))) return false;
   if (!((double) intensity < ap.RNR_intensity_thr)) return false;
   const float rf = fsqrt(fadd(fmul(x, x), fmul(y, y)));          // S:387 (float ops, std::sqrt(float))
-  const double ang = ddiv(dmul(atan2(zd, (double) rf), 180.0), PW_PI);  // S:389
+  const double ang = ddiv(dmul(atan2_exact(zd, (double) rf), 180.0), PW_PI);  // S:389
   return ang < ap.RNR_ver_angle_thr;
 }
 
@@ -129,7 +137,7 @@ PW_HD int bin_of_point_exact(float x, float y, float z, const Geometry& g) {
   const double xd = (double) x, yd = (double) y;
   const double r = dsqrt(dadd(dmul(xd, xd), dmul(yd, yd)));  // xy2radius S:573-576
   if (!((r <= g.max_range) && (r > g.min_range)) || !(fabsf(z) <= FLT_MAX)) return PW_BIN_OOR(g.nbins);
-  double theta = atan2(yd, xd);                              // xy2theta S:568-571
+  double theta = atan2_exact(yd, xd);                        // xy2theta S:568-571
   theta = theta > 0 ? theta : dadd(2 * PW_PI, theta);
   const int k = (r < g.min_ranges[1]) ? 0 : (r < g.min_ranges[2]) ? 1 : (r < g.min_ranges[3]) ? 2 : 3;
   int ring = (int) ddiv(dsub(r, g.min_ranges[k]), g.ring_sizes[k]);

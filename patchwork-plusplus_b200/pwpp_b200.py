@@ -185,7 +185,7 @@ class Engine:
         _check(self.lib.pwpp_device_results(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    NUM_STAGES = 10
+    NUM_STAGES = 11
 
     def set_profiling(self, on: bool):
         _check(self.lib.pwpp_set_profiling(self._h, 1 if on else 0))

@@ -11,7 +11,7 @@ pts, offs = synth.make_batch(777, 0, F, "kitti64", "cuda")
 pts2, offs2 = synth.make_batch(778, 0, F, "kitti64", "cuda")
 offs_np, offs2_np = offs.numpy(), offs2.numpy()
 eng = pwpp_b200.Engine(device=0, num_streams=F)
-st = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream; assert st != 0
 # A, B, A back to back without any host synchronisation in between
 for (p, o) in ((pts, offs_np), (pts2, offs2_np), (pts, offs_np)):
     eng.reset(); eng.estimate_device(p.data_ptr(), o, True, st)
