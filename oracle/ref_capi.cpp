@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <vector>
@@ -80,7 +81,10 @@ patchwork::Params to_params(const pwpp_params* p) {
 extern "C" {
 
 void* pwref_create(const pwpp_params* p) {
-  // the reference constructor prints an unconditional banner (patchworkpp.h:149); silence it
+  // the reference constructor prints an unconditional banner (patchworkpp.h:149); silence it. bench.py creates
+  // instances from many threads: redirecting std::cout is not thread-safe, so construction is serialised.
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   std::streambuf* old = std::cout.rdbuf();
   std::ostringstream sink;
   std::cout.rdbuf(sink.rdbuf());
