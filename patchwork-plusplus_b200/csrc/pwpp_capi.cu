@@ -23,6 +23,14 @@ namespace {
 
 thread_local std::string g_last_error;
 
+// integer experiment switch from the environment, clamped to [lo, hi]
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = std::getenv(name);
+  if (!e || !*e) return dflt;
+  const long v = std::strtol(e, nullptr, 10);
+  return (int) (v < lo ? lo : (v > hi ? hi : v));
+}
+
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
@@ -80,6 +88,9 @@ struct pwpp_ctx {
   int nbp = 0;      // padded number of bins incl. pseudo-bins
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
+  // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
+  int sw_hist_pipe = 1, sw_scatter_pipe = 1, sw_warp_top = 2, sw_m_u = 4;
+  bool sw_l1_warp = true, sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
@@ -105,7 +116,7 @@ struct pwpp_ctx {
   DevBuf<int> d_part;
   DevBuf<BinFit> d_fits;          // [F][nbins]
   DevBuf<BinSeg> d_segs;          // [F][nbins+3]
-  DevBuf<int> d_wq_items[NUM_CLASSES];  // fit work queues
+  DevBuf<int4> d_wq_items[NUM_CLASSES];  // fit work queues
   DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES]: counts, heads
   int fit_grid[NUM_CLASSES] = {0, 0, 0, 0, 0, 0};  // persistent grid sizes
   int fit_grid_l1w = 0;
@@ -234,10 +245,14 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
-    if (ctx->fast_bin)
-      k_bin_hist<true><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
-    else
-      k_bin_hist<false><<<grid, CHUNK_THREADS, nbp * sizeof(unsigned int), s>>>(d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p);
+    const int hist_pipe = ctx->sw_hist_pipe;
+#define HIST_ARGS d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p
+    const size_t sm_h = nbp * sizeof(unsigned int);
+    if (!ctx->fast_bin) k_bin_hist<false, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
+    else if (hist_pipe == 0) k_bin_hist<true, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
+    else if (hist_pipe == 1) k_bin_hist<true, 1><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
+    else k_bin_hist<true, 2><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
+#undef HIST_ARGS
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -250,7 +265,10 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
-    k_scatter<<<grid, CHUNK_THREADS, (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int), s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
+    const bool scatter_pipe = ctx->sw_scatter_pipe != 0;
+    const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
+    if (scatter_pipe) k_scatter<true><<<grid, CHUNK_THREADS, sm_sc, s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
+    else k_scatter<false><<<grid, CHUNK_THREADS, sm_sc, s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -258,23 +276,40 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   // unless per-stage timing is requested they run on side streams so that the tail of one class (few long patches
   // left) overlaps the start of the next.
 #define FIT_ARGS ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits
-  static const bool serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;   // diagnostic switch
-  // 513..2048-point patches: the barrier-free streaming warp kernel beats the CTA kernel at this size (measured on
-  // B200: 0.88 vs 1.23 ms per 1024 frames); PWPP_L1_CTA=1 switches back for comparison
-  static const bool l1_warp = std::getenv("PWPP_L1_CTA") == nullptr;
+  const bool serial_fit = ctx->sw_serial_fit;   // PWPP_SERIAL_FIT: diagnostic switch
+  // Experiment switches (defaults = the measured best):
+  //   PWPP_WARP_TOP=2|3|4  largest class drained by the barrier-free streaming warp kernel (2: 513..2048-point patches,
+  //                        measured 0.88 vs 1.23 ms per 1024 frames against the CTA kernel; 3/4 also take the 4096 / 8192 classes)
+  //   PWPP_L1_CTA=1        class 2 back on the CTA kernel
+  //   PWPP_M_U=1|2|4       pass unrolling of the staged warp kernel (65..512-point patches)
+  const int warp_top = ctx->sw_warp_top;
+  const bool l1_warp = ctx->sw_l1_warp;
+  const int m_u = ctx->sw_m_u;
   const size_t sm_l1 = 3 * 2048 * sizeof(float), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4);
+  auto launch_l3 = [&](cudaStream_t st) { if (warp_top < 4 || !l1_warp) k_fit_cta<8192, 4><<<ctx->fit_grid[4], FIT_THREADS, sm_l3, st>>>(FIT_ARGS); };
+  auto launch_l2 = [&](cudaStream_t st) { if (warp_top < 3 || !l1_warp) k_fit_cta<4096, 3><<<ctx->fit_grid[3], FIT_THREADS, sm_l2, st>>>(FIT_ARGS); };
+  auto launch_l1 = [&](cudaStream_t st) {
+    if (!l1_warp) k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, sm_l1, st>>>(FIT_ARGS);
+    else if (warp_top == 4) k_fit_warp<false, 4, 2, FITW_U><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, st>>>(FIT_ARGS);
+    else if (warp_top == 3) k_fit_warp<false, 3, 2, FITW_U><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, st>>>(FIT_ARGS);
+    else k_fit_warp<false, 2, 2, FITW_U><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, st>>>(FIT_ARGS);
+  };
+  auto launch_m = [&](cudaStream_t st) {
+    if (m_u == 1) k_fit_warp<true, 1, 1, 1><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, st>>>(FIT_ARGS);
+    else if (m_u == 2) k_fit_warp<true, 1, 1, 2><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, st>>>(FIT_ARGS);
+    else k_fit_warp<true, 1, 1, 4><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, st>>>(FIT_ARGS);
+  };
   if (prof || serial_fit) {
     k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(FIT_ARGS);
     STAGE_MARK();
-    k_fit_cta<8192, 4><<<ctx->fit_grid[4], FIT_THREADS, sm_l3, s>>>(FIT_ARGS);
+    launch_l3(s);
     STAGE_MARK();
-    k_fit_cta<4096, 3><<<ctx->fit_grid[3], FIT_THREADS, sm_l2, s>>>(FIT_ARGS);
+    launch_l2(s);
     STAGE_MARK();
-    if (l1_warp) k_fit_warp<false, 2, 2><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, s>>>(FIT_ARGS);
-    else k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, sm_l1, s>>>(FIT_ARGS);
+    launch_l1(s);
     STAGE_MARK();
-    k_fit_warp<true, 1, 1><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, s>>>(FIT_ARGS);
+    launch_m(s);
     STAGE_MARK();
     k_fit_stream<<<ctx->fit_grid[5], 128, 0, s>>>(FIT_ARGS);
     STAGE_MARK();
@@ -282,11 +317,10 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     CU_TRY(cudaEventRecord(ctx->ev_fork, s));
     for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
     // longest classes first
-    k_fit_cta<8192, 4><<<ctx->fit_grid[4], FIT_THREADS, sm_l3, s>>>(FIT_ARGS);
-    k_fit_cta<4096, 3><<<ctx->fit_grid[3], FIT_THREADS, sm_l2, ctx->side[0]>>>(FIT_ARGS);
-    if (l1_warp) k_fit_warp<false, 2, 2><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, ctx->side[1]>>>(FIT_ARGS);
-    else k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, sm_l1, ctx->side[1]>>>(FIT_ARGS);
-    k_fit_warp<true, 1, 1><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, ctx->side[2]>>>(FIT_ARGS);
+    launch_l3(s);
+    launch_l2(ctx->side[0]);
+    launch_l1(ctx->side[1]);
+    launch_m(ctx->side[2]);
     k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, ctx->side[3]>>>(FIT_ARGS);
     k_fit_stream<<<ctx->fit_grid[5], 128, 0, ctx->side[4]>>>(FIT_ARGS);
     for (int q = 0; q < 5; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
@@ -317,10 +351,9 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   return PWPP_OK;
 }
 
-// Frames per launch sequence. The five persistent fit kernels of one sequence overlap on side streams; with a very
-// large batch each of them saturates the SMs' register file in turn and the overlap is lost, so a big call is
-// processed as consecutive sub-batches (measured on B200: 256-frame sub-batches of ~120k-point frames run at
-// 0.81 ms each, a single 1024-frame sequence takes 4.9 ms). Sized by points so that dense frames get fewer frames.
+// Optional sub-batching of a big call (PWPP_SUBBATCH_POINTS=n: consecutive launch sequences of at most n points).
+// Measured on B200 with correctly placed CUDA events: slower than one sequence per call at every size tried (each
+// persistent fit kernel already fills the GPU; splitting only adds tails), so the default is one sequence.
 long long subbatch_points() {
   static long long v = [] {
     const char* e = std::getenv("PWPP_SUBBATCH_POINTS");
@@ -428,6 +461,12 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->device = device;
   ctx->num_streams = num_streams;
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
+  ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", 1, 0, 2);
+  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_PIPE", 1, 0, 1);
+  ctx->sw_warp_top = env_int("PWPP_WARP_TOP", 2, 2, 4);
+  ctx->sw_m_u = env_int("PWPP_M_U", 4, 1, 4);
+  ctx->sw_l1_warp = std::getenv("PWPP_L1_CTA") == nullptr;
+  ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -471,16 +510,18 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     int per_sm[NUM_CLASSES] = {1, 1, 1, 1, 1, 1};
     CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
     CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<4096, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 4096 * sizeof(float))));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
+    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_fit_resident<8, 8, 0>, FIT_THREADS, 0));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_warp<true, 1, 1>, FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4)));
+    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_warp<true, 1, 1, 4>, FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fit_cta<2048, 2>, FIT_THREADS, 3 * 2048 * sizeof(float)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_fit_cta<4096, 3>, FIT_THREADS, 3 * 4096 * sizeof(float)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_fit_cta<8192, 4>, FIT_THREADS, 3 * 8192 * sizeof(float)));
     CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[5], k_fit_stream, 128, 0));
     {
       int l1w = 1;
-      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&l1w, k_fit_warp<false, 2, 2>, FITW_WARPS * 32, 0));
+      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&l1w, k_fit_warp<false, 4, 2, FITW_U>, FITW_WARPS * 32, 0));
       ctx->fit_grid_l1w = std::max(1, l1w) * prop.multiProcessorCount;
     }
     for (int c = 0; c < NUM_CLASSES; ++c) ctx->fit_grid[c] = std::max(1, per_sm[c]) * prop.multiProcessorCount;
@@ -489,7 +530,10 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   }
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
-    if (scat > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+    if (scat > 48 * 1024) {
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+    }
   }
   *out = ctx;
   rc = pwpp_reset_all(ctx);

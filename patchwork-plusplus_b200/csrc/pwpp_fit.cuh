@@ -32,12 +32,24 @@ constexpr int FIT_THREADS = 256;
 constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 4096, CLS_L3_MAX = 8192;
 constexpr int NUM_CLASSES = 6;  // S, M, L1, L2, L3, X
 
-// device-side work queues, filled by k_bin_scan
+// device-side work queues, filled by k_bin_scan. An item describes one patch completely, so that a fit kernel needs
+// a single load between claiming a queue position and touching the patch's points:
+//   x = (frame << 12) | bin,  y = number of points,  (z, w) = low / high word of the patch's offset into the
+//   bin-sorted point array (frame offset + bin offset)
 struct WorkQueues {
-  int* items[NUM_CLASSES];   // item = (frame << 12) | bin
+  int4* items[NUM_CLASSES];
   int* count;                // [NUM_CLASSES]  number of items
   int* head;                 // [NUM_CLASSES]  next item to hand out (persistent kernels)
 };
+__device__ __forceinline__ int4 make_work_item(int frame, int bin, int n, long long start) {
+  return make_int4((frame << 12) | bin, n, (int) (unsigned) (start & 0xffffffffll), (int) (start >> 32));
+}
+__device__ __forceinline__ long long work_item_start(const int4& w) { return ((long long) w.w << 32) | (long long) (unsigned) w.z; }
+// Pull the lines of a patch that will be processed next towards L2 (fire and forget): lanes stride over 128-byte lines.
+__device__ __forceinline__ void prefetch_patch_l2(const float4* P, int n, int lane, int nlanes) {
+  const int lines = (n + 7) >> 3;
+  for (int l = lane; l < lines; l += nlanes) asm volatile("prefetch.global.L2 [%0];" ::"l"(P + (size_t) l * 8));
+}
 
 __device__ __forceinline__ unsigned order_key(float z) {
   const unsigned u = __float_as_uint(z);
@@ -147,32 +159,26 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
   const int gl = lane % G;                     // lane inside the group
   typedef GroupOps<G> Ops;
 
-  constexpr int GRAB = 1;                      // batches of NGW patches fetched per queue atomic
-  int grab_base = 0, grab_left = 0;
   const int count = wq.count[CLS];
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&wq.head[CLS], NGW);
+  base = __shfl_sync(0xffffffffu, base, 0);
   for (;;) {
-    if (grab_left == 0) {
-      if (lane == 0) grab_base = atomicAdd(&wq.head[CLS], NGW * GRAB);
-      grab_base = __shfl_sync(0xffffffffu, grab_base, 0);
-      grab_left = GRAB;
-    }
-    const int base = grab_base;
-    grab_base += NGW;
-    --grab_left;
     if (base >= count) return;
+    // claim the next NGW patches now: the atomic's round trip overlaps the processing of the current ones
+    int next_raw = 0;
+    if (lane == 0) next_raw = atomicAdd(&wq.head[CLS], NGW);
     const bool have = (base + gw) < count;
     int n = 0, bin = 0, f = 0;
     const float4* P = nullptr;
     int* out = nullptr;
     if (have) {
-      const int item = wq.items[CLS][base + gw];
-      f = item >> 12; bin = item & 0xfff;
-      const int* bo = bin_off + (size_t) f * (nbp + 1);
-      const int off = bo[bin];
-      n = bo[bin + 1] - off;
-      const long long p0 = ft.pt_off[f];
-      P = sorted + p0 + off;
-      out = part + p0 + off;
+      const int4 wi = wq.items[CLS][base + gw];
+      f = wi.x >> 12; bin = wi.x & 0xfff;
+      n = wi.y;
+      const long long start = work_item_start(wi);
+      P = sorted + start;
+      out = part + start;
     }
     // ---- load the patches of this warp into registers ----
     float px[K], py[K], pz[K];
@@ -351,6 +357,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* _
       }
     }
     __syncwarp();
+    base = __shfl_sync(0xffffffffu, next_raw, 0);
   }
 }
 
@@ -390,23 +397,32 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 4096 ? 3 : 2)) k_fit_cta(
   __shared__ double s_lpr;
   __shared__ double s_fb[8];
   __shared__ unsigned s_T;
-  __shared__ int s_ccount, s_item, s_mn, s_fix, s_refit;
+  __shared__ int s_ccount, s_mn, s_fix, s_refit;
+  __shared__ int4 s_item;
   __shared__ Plane s_plane;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float thf = (float) ap.th_dist;
+  const int count = wq.count[CLS];
+  const int4 no_item = make_int4(-1, 0, 0, 0);
 
+  // Queue protocol: the last warp claims one patch AHEAD — the atomic at the top of a patch, the descriptor load after
+  // the staging loads, an L2 prefetch of that patch's points while warp 0 solves the first plane (when the other
+  // warps idle anyway) — and publishes the descriptor through s_item at the end of the patch; x < 0 = queue drained.
+  constexpr int LOOK_W = FIT_THREADS / 32 - 1, LOOK_TID = LOOK_W * 32;
+  if (tid == 0) {
+    const int t = atomicAdd(&wq.head[CLS], 1);
+    s_item = t < count ? wq.items[CLS][t] : no_item;
+  }
+  __syncthreads();
   for (;;) {
-    if (tid == 0) s_item = atomicAdd(&wq.head[CLS], 1);
-    __syncthreads();
-    const int it0 = s_item;
-    if (it0 >= wq.count[CLS]) return;
-    const int item = wq.items[CLS][it0];
-    const int f = item >> 12, bin = item & 0xfff;
-    const int* bo = bin_off + (size_t) f * (nbp + 1);
-    const int off = bo[bin], n = bo[bin + 1] - off;
-    const long long p0 = ft.pt_off[f];
-    const float4* P = sorted + p0 + off;
-    int* out = part + p0 + off;
+    const int4 cur = s_item;
+    if (cur.x < 0) return;
+    int next_raw = 0;
+    if (tid == LOOK_TID) next_raw = atomicAdd(&wq.head[CLS], 1);
+    const int f = cur.x >> 12, bin = cur.x & 0xfff, n = cur.y;
+    const long long start = work_item_start(cur);
+    const float4* P = sorted + start;
+    int* out = part + start;
     const int chunk = (((n + 7) >> 3) + 31) & ~31;   // points per warp, multiple of 32
     const int nit = chunk >> 5;                      // slots per thread actually used (<= ITERS)
     const int jbase = w * chunk + lane;
@@ -415,6 +431,11 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 4096 ? 3 : 2)) k_fit_cta(
     for (int it = 0; it < nit; ++it) {
       const int j = jbase + it * 32;
       if (j < n) { const float4 p = P[j]; sx[j] = p.x; sy[j] = p.y; sz[j] = p.z; vmask |= 1u << it; }
+    }
+    int4 nxt = no_item;   // next patch (meaningful in the look-ahead warp)
+    if (w == LOOK_W) {
+      const int t = __shfl_sync(0xffffffffu, next_raw, 0);
+      if (t < count) nxt = wq.items[CLS][t];
     }
     unsigned amask = vmask;
     const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
@@ -662,6 +683,8 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 4096 ? 3 : 2)) k_fit_cta(
           if (lane == 0) s_plane = t;
         }
         if (lane == 0) { s_mn = tot.n; s_fix = (incr && changed == 0) ? 1 : 0; s_refit = (refit && tot.n > 0) ? 1 : 0; }
+      } else if (w == LOOK_W && state == ST_SEED) {   // the R-GPF seed round: exactly once per patch
+        if (nxt.x >= 0) prefetch_patch_l2(sorted + work_item_start(nxt), nxt.y, lane, 32);
       }
       __syncthreads();
       const int tot_n = s_mn;
@@ -720,6 +743,7 @@ __global__ void __launch_bounds__(FIT_THREADS, (CAP <= 4096 ? 3 : 2)) k_fit_cta(
         for (int q = 0; q < 3; ++q) { r.mean[q] = pl.mean[q]; r.normal[q] = pl.normal[q]; r.sv[q] = pl.sv[q]; }
         r.d = pl.d;
       }
+      if (tid == LOOK_TID) s_item = nxt;   // every thread read the current descriptor before the barrier above
     }
     __syncthreads();
   }
@@ -881,6 +905,32 @@ constexpr int WARP_CAP = CLS_L3_MAX;            // 8192 points -> 256 iterations
 constexpr int FITW_WARPS = 8;
 constexpr int FITW_U = 4;                       // loads in flight per lane
 
+// Rare path of warp_lpr (num_lpr > 32, or more than 128 points tie below the bound): streaming selector with a
+// bitonic sort of the candidate buffer. Kept out of line so that its ~2000 instructions stay out of the hot code.
+__device__ __noinline__ double warp_lpr_fallback(const float4* __restrict__ P, int n, int nit, bool any_removed, const unsigned* __restrict__ alive_w, bool zone0,
+                                                 double margin_z, int num_lpr, float* sel_buf) {
+  const int lane = lane_id();
+  double lpr = 0.0;
+  LprSelector sel;
+  sel.init(sel_buf, num_lpr);
+  for (int it = 0; it < nit; ++it) {
+    const int j = it * 32 + lane;
+    bool valid = j < n;
+    const float z = P[j < n ? j : n - 1].z;
+    if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
+    if (zone0 && ((double) z < margin_z)) valid = false;
+    sel.push(valid, z);
+  }
+  sel.prune();
+  if (lane == 0) {
+    double sum = 0.0;
+    for (int i = 0; i < sel.m; ++i) sum += (double) sel_buf[i];
+    lpr = sel.m != 0 ? sum / sel.m : 0.0;
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, lpr, 0);
+}
+
 // LPR height for one warp-owned patch (extract_initial_seeds, S:84-103): mean of the (<= num_lpr) lowest z among
 // the points that are alive and, in zone 0, not below the adaptive margin.
 // Two-level selection: the num_lpr-th smallest of the 32 per-lane minima is an upper bound T of the num_lpr-th
@@ -956,30 +1006,11 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
       __syncwarp();
     } else fallback = true;
   }
-  if (fallback) {
-    LprSelector sel;
-    sel.init(sel_buf, num_lpr);
-    for (int it = 0; it < nit; ++it) {
-      const int j = it * 32 + lane;
-      bool valid = j < n;
-      const float z = P[j < n ? j : n - 1].z;
-      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
-      if (zone0 && ((double) z < margin_z)) valid = false;
-      sel.push(valid, z);
-    }
-    sel.prune();
-    if (lane == 0) {
-      double sum = 0.0;
-      for (int i = 0; i < sel.m; ++i) sum += (double) sel_buf[i];
-      lpr = sel.m != 0 ? sum / sel.m : 0.0;
-    }
-    __syncwarp();
-    lpr = __shfl_sync(0xffffffffu, lpr, 0);
-  }
+  if (fallback) lpr = warp_lpr_fallback(P, n, nit, any_removed, alive_w, zone0, margin_z, num_lpr, sel_buf);
   return lpr;
 }
 
-template <bool STAGE, int CLS_HI, int CLS_LO>
+template <bool STAGE, int CLS_HI, int CLS_LO, int U>
 __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -996,29 +1027,40 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
   int cls = CLS_HI;          // queues being drained, longest patches first
   const int cls_last = CLS_LO;
   const float thf = (float) ap.th_dist;
-
-  for (;;) {
-    int it0 = -1;
+  int cnt = wq.count[cls];
+  const int4 no_item = make_int4(-1, 0, 0, 0);
+  int4 cur = no_item;
+  // synchronous claim: at the start and when a class runs dry. Inside the loop the warp claims one patch AHEAD (atomic at
+  // the top of a patch, descriptor load after the first pass, L2 prefetch of its points before the R-GPF rounds), so
+  // the queue round trips and most of the DRAM latency of the next patch overlap the current one.
+  auto claim_sync = [&]() {
+    cur = no_item;
     while (cls >= cls_last) {
       int t = 0;
       if (lane == 0) t = atomicAdd(&wq.head[cls], 1);
       t = __shfl_sync(0xffffffffu, t, 0);
-      if (t < wq.count[cls]) { it0 = t; break; }
+      if (t < cnt) { cur = wq.items[cls][t]; return; }
       --cls;
+      if (cls >= cls_last) cnt = wq.count[cls];
     }
-    if (it0 < 0) return;
-    const int item = wq.items[cls][it0];
-    const int f = item >> 12, bin = item & 0xfff;
-    const int* bo = bin_off + (size_t) f * (nbp + 1);
-    const int off = bo[bin], n = bo[bin + 1] - off;
-    const long long p0 = ft.pt_off[f];
-    const float4* G = sorted + p0 + off;        // the patch in global memory
-    int* out = part + p0 + off;
+  };
+  claim_sync();
+
+  for (;;) {
+    if (cur.x < 0) return;
+    int next_raw = 0;
+    if (lane == 0) next_raw = atomicAdd(&wq.head[cls], 1);
+    int4 nxt = no_item;
+    bool looked_ahead = false;
+    const int f = cur.x >> 12, bin = cur.x & 0xfff, n = cur.y;
+    const long long start = work_item_start(cur);
+    const float4* G = sorted + start;           // the patch in global memory
+    int* out = part + start;
     const int nit = (n + 31) >> 5;
     const float4* P = G;                        // where the passes read the points from
     if (STAGE) {
       float4* mine = s_stage + warp * CLS_M_MAX;
-      for (int it = 0; it < nit; it += FITW_U) {
+      for (int it = 0; it < nit; it += FITW_U) {   // global loads: always FITW_U in flight
         float4 q[FITW_U];
 #pragma unroll
         for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; q[u] = G[j < n ? j : n - 1]; }
@@ -1050,6 +1092,11 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
       const double lpr = warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
       const double zthr = lpr + (rvpf_round ? ap.th_seeds_v : ap.th_seeds);
       c[2] = lpr;
+      if (!looked_ahead) {   // the claim issued at the top has returned by now: fetch the next patch's descriptor
+        const int t_next = __shfl_sync(0xffffffffu, next_raw, 0);
+        if (t_next < cnt) nxt = wq.items[cls][t_next];
+        looked_ahead = true;
+      }
       // full accumulation over {alive, z < lpr + th}; the ballots become the member set
       Moments m;
       m.n = 0;
@@ -1057,12 +1104,12 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
       for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
 #pragma unroll
       for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
-      for (int it = 0; it < nit; it += FITW_U) {
-        float4 q[FITW_U];
+      for (int it = 0; it < nit; it += U) {
+        float4 q[U];
 #pragma unroll
-        for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; q[u] = P[j < n ? j : n - 1]; }
+        for (int u = 0; u < U; ++u) { const int j = (it + u) * 32 + lane; q[u] = P[j < n ? j : n - 1]; }
 #pragma unroll
-        for (int u = 0; u < FITW_U; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int j = (it + u) * 32 + lane;
           const float4 p = q[u];
           bool in = (j < n) && ((double) p.z < zthr);                                     // S:108 / S:145
@@ -1104,6 +1151,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
     }
     __syncwarp();
 
+    if (nxt.x >= 0) prefetch_patch_l2(sorted + work_item_start(nxt), nxt.y, lane, 32);
     // ---- R-GPF iterations (S:516-543): num_iter distance passes; incremental moments; stop at the fixpoint ----
     for (int round = 0; round < ap.num_iter && have_plane; ++round) {
       PlaneF pf;
@@ -1115,12 +1163,12 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
 #pragma unroll
       for (int q = 0; q < 6; ++q) dm.s2[q] = 0.0;
       unsigned changed_any = 0;
-      for (int it = 0; it < nit; it += FITW_U) {
-        float4 q[FITW_U];
+      for (int it = 0; it < nit; it += U) {
+        float4 q[U];
 #pragma unroll
-        for (int u = 0; u < FITW_U; ++u) { const int j = (it + u) * 32 + lane; q[u] = P[j < n ? j : n - 1]; }
+        for (int u = 0; u < U; ++u) { const int j = (it + u) * 32 + lane; q[u] = P[j < n ? j : n - 1]; }
 #pragma unroll
-        for (int u = 0; u < FITW_U; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (it + u >= nit) break;
           const int j = (it + u) * 32 + lane;
           const float4 p = q[u];
@@ -1184,6 +1232,12 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* _
       r.d = pl.d;
     }
     __syncwarp();
+    if (nxt.x >= 0) cur = nxt;
+    else {   // this class is drained (the look-ahead claim ran past its end): continue with the next one
+      --cls;
+      if (cls >= cls_last) cnt = wq.count[cls];
+      claim_sync();
+    }
   }
 }
 
@@ -1197,13 +1251,11 @@ __global__ void __launch_bounds__(128) k_fit_stream(const float4* __restrict__ s
     if (lane == 0) it0 = atomicAdd(&wq.head[NUM_CLASSES - 1], 1);
     it0 = __shfl_sync(0xffffffffu, it0, 0);
     if (it0 >= wq.count[NUM_CLASSES - 1]) return;
-    const int item = wq.items[NUM_CLASSES - 1][it0];
-    const int f = item >> 12, bin = item & 0xfff;
-    const int* bo = bin_off + (size_t) f * (nbp + 1);
-    const int off = bo[bin], n = bo[bin + 1] - off;
-    const long long p0 = ft.pt_off[f];
-    const float4* P = sorted + p0 + off;
-    int* out = part + p0 + off;
+    const int4 wi = wq.items[NUM_CLASSES - 1][it0];
+    const int f = wi.x >> 12, bin = wi.x & 0xfff, n = wi.y;
+    const long long start = work_item_start(wi);
+    const float4* P = sorted + start;
+    int* out = part + start;
     const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
     const bool zone0 = (zone == 0);
     const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;  // S:90

@@ -28,7 +28,9 @@ namespace pwpp {
 // ---------------------------------------------------------------------------------------------------
 // k_bin_hist: grid (max_chunks_per_frame, F), 256 threads. Each warp owns 512 consecutive points.
 // Writes bin ids (u16) and the chunk's histogram row (u16[nbp]).
-template <bool FAST>
+// PIPE: 0 = load a group of 4 points per lane, bin them, repeat; 1 / 2 = groups of 4 / 2 with the next group's loads in
+// flight while the current one is binned (PWPP_HIST_PIPE, A/B switch)
+template <bool FAST, int PIPE>
 __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states,
                                                              Geometry g, AlgoParams ap, int has_intensity, int nbp,
                                                              unsigned short* __restrict__ bin_ids, unsigned short* __restrict__ chist) {
@@ -44,13 +46,17 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __r
   const bool rnr_on = ap.enable_RNR && has_intensity;  // S:161, S:379-382
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int base = blockIdx.x * CHUNK_PTS + warp * WARP_PTS;
-  constexpr int HB = 4;   // independent 128-bit loads in flight per lane
+  constexpr int HB = PIPE == 2 ? 2 : 4;   // points per load group and lane
   const int last = n - 1;
+  float4 q[HB], qn[HB];
+#pragma unroll
+  for (int u = 0; u < HB; ++u) { const int i = base + u * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
 #pragma unroll 1
   for (int h = 0; h < WARP_ITERS; h += HB) {
-    float4 q[HB];
+    if (PIPE != 0 && h + HB < WARP_ITERS) {
 #pragma unroll
-    for (int u = 0; u < HB; ++u) { const int i = base + (h + u) * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
+      for (int u = 0; u < HB; ++u) { const int i = base + (h + HB + u) * 32 + lane; qn[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
+    }
 #pragma unroll
     for (int u = 0; u < HB; ++u) {
       const int i = base + (h + u) * 32 + lane;
@@ -68,6 +74,13 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __r
         const unsigned peers = __match_any_sync(act, bin);
         if ((peers & lanemask_lt()) == 0) atomicAdd(&s_hist[bin], __popc(peers));
       }
+    }
+    if (PIPE != 0) {
+#pragma unroll
+      for (int u = 0; u < HB; ++u) q[u] = qn[u];
+    } else if (h + HB < WARP_ITERS) {
+#pragma unroll
+      for (int u = 0; u < HB; ++u) { const int i = base + (h + HB + u) * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
     }
   }
   __syncthreads();
@@ -140,7 +153,7 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
     const int n = s_scan[b + 1] - s_scan[b];
     if (n >= num_min_pts && n > 0) {
       const int c = cls_of(n);
-      wq.items[c][s_cls_base[c] + atomicAdd(&s_cls_pos[c], 1)] = (f << 12) | b;
+      wq.items[c][s_cls_base[c] + atomicAdd(&s_cls_pos[c], 1)] = make_work_item(f, b, n, ft.pt_off[f] + (long long) s_scan[b]);
     }
   }
 }
@@ -150,9 +163,14 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
 // among the frame's points of that bin in ascending point index.
 //   rank = cbase[chunk][bin] + (#points of bin in lower warps of the chunk)
 //        + (#points of bin in earlier iterations of this warp) + (#lower lanes with the same bin)
-__global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restrict__ pts, FrameTable ft, int nbp,
-                                                            const unsigned short* __restrict__ bin_ids, const unsigned int* __restrict__ cbase,
-                                                            float4* __restrict__ sorted) {
+// PIPE = true: the point loads are software-pipelined in two groups of SB and the first two groups are issued before
+// the histogram / prefix phases, so that 4..8 loads per lane are in flight from the first instruction to the last
+// (the kernel is latency-bound: 23 % active warps, 52 % long-scoreboard stalls in the r01 capture). PIPE = false is the
+// previous schedule (kept for A/B runs: PWPP_SCATTER_PIPE=0).
+template <bool PIPE>
+__global__ void __launch_bounds__(CHUNK_THREADS, 2) k_scatter(const float4* __restrict__ pts, FrameTable ft, int nbp,
+                                                               const unsigned short* __restrict__ bin_ids, const unsigned int* __restrict__ cbase,
+                                                               float4* __restrict__ sorted) {
   extern __shared__ unsigned int s_wcnt[];  // [8][nbp]: per-warp histograms, then per-warp running positions
   const int f = blockIdx.y;
   const long long p0 = ft.pt_off[f];
@@ -160,10 +178,18 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restr
   const int nchunks = (n + CHUNK_PTS - 1) / CHUNK_PTS;
   if ((int) blockIdx.x >= nchunks) return;
   const int nwarps = CHUNK_THREADS / 32;
-  for (int b = threadIdx.x; b < nwarps * nbp; b += CHUNK_THREADS) s_wcnt[b] = 0;
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int base = blockIdx.x * CHUNK_PTS + warp * WARP_PTS;
+  const int last = n - 1;
+  constexpr int SB = 4;   // points per load group and lane
+  float4 qa[SB], qb[SB];
+  auto load_group = [&](float4 (&q)[SB], int h) {
+#pragma unroll
+    for (int u = 0; u < SB; ++u) { const int i = base + (h + u) * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
+  };
+  if (PIPE) { load_group(qa, 0); load_group(qb, SB); }
+  for (int b = threadIdx.x; b < nwarps * nbp; b += CHUNK_THREADS) s_wcnt[b] = 0;
+  __syncthreads();
   unsigned int* my = s_wcnt + warp * nbp;
   int bins[WARP_ITERS];
   // all 16 bin ids of the lane are requested before the first one is used (__syncwarp below is a memory barrier the
@@ -193,13 +219,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restr
   }
   __syncthreads();
   float4* out = sorted + p0;
-  constexpr int SB = 4;   // points in flight per lane
-  const int last = n - 1;
-#pragma unroll
-  for (int h = 0; h < WARP_ITERS; h += SB) {
-    float4 q[SB];
-#pragma unroll
-    for (int u = 0; u < SB; ++u) { const int i = base + (h + u) * 32 + lane; q[u] = ld_stream_f4(pts + p0 + (i < n ? i : last)); }
+  auto place_group = [&](const float4 (&q)[SB], int h) {
 #pragma unroll
     for (int u = 0; u < SB; ++u) {
       const int i = base + (h + u) * 32 + lane;
@@ -215,6 +235,22 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const float4* __restr
         if ((peers & lanemask_lt()) == 0) my[bin] += __popc(peers);
       }
       __syncwarp();
+    }
+  };
+  static_assert(WARP_ITERS % (2 * SB) == 0, "two load groups per pipeline step");
+  if (PIPE) {
+#pragma unroll
+    for (int h = 0; h < WARP_ITERS; h += 2 * SB) {
+      place_group(qa, h);
+      if (h + 2 * SB < WARP_ITERS) load_group(qa, h + 2 * SB);
+      place_group(qb, h + SB);
+      if (h + 3 * SB < WARP_ITERS) load_group(qb, h + 3 * SB);
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < WARP_ITERS; h += SB) {
+      load_group(qa, h);
+      place_group(qa, h);
     }
   }
 }

@@ -11,6 +11,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define PW_HD __host__ __device__ __forceinline__
@@ -363,11 +364,37 @@ PW_HD void jacobi_svd3(double cxx, double cxy, double cxz, double cyy, double cy
 PW_HD void cross3(const double a[3], const double b[3], double r[3]) {
   r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
 }
+// Reciprocal and reciprocal square root for the plane solve: the hardware seed (MUFU.RCP64H / RSQ64H, ~2^-19) plus two
+// Newton steps, ~1 ulp, no slow-path subroutine. Operands here are sums of squares / counts in the normal range;
+// 0 -> inf seed -> NaN after the Newton step, which every caller treats like the reference's 0/0 (degenerate patch).
+PW_HD double rcp_d(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
 PW_HD double rsqrt_d(double x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = fma(fma(-hx * y, y, 0.5), y, y);
+  y = fma(fma(-hx * y, y, 0.5), y, y);
+  return y;
 #else
   return 1.0 / sqrt(x);
+#endif
+}
+PW_HD float rcp_f(float x) {   // ~1e-7 relative; only steers a Newton iteration
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
 #endif
 }
 // unit vector in the null space of (A - lambda I): the largest cross product of two rows (scalar selects only, so
@@ -387,43 +414,83 @@ PW_HD void eigvec_by_rows(double a00, double a01, double a02, double a11, double
   if (dmax > 0.0) { const double inv = rsqrt_d(dmax); v[0] = bx * inv; v[1] = by * inv; v[2] = bz * inv; }
   else { v[0] = 0.0; v[1] = 0.0; v[2] = 1.0; }
 }
-// unit vectors u, w with {u, w, v} orthonormal
+// unit vectors u, w with {u, w, v} orthonormal (branch-free: one reciprocal square root)
 PW_HD void orthogonal_complement(const double v[3], double u[3], double w[3]) {
-  if (fabs(v[0]) > fabs(v[1])) { const double inv = rsqrt_d(v[0] * v[0] + v[2] * v[2]); u[0] = -v[2] * inv; u[1] = 0.0; u[2] = v[0] * inv; }
-  else { const double inv = rsqrt_d(v[1] * v[1] + v[2] * v[2]); u[0] = 0.0; u[1] = v[2] * inv; u[2] = -v[1] * inv; }
+  const bool x_big = fabs(v[0]) > fabs(v[1]);
+  const double a = x_big ? v[0] : v[1];
+  const double inv = rsqrt_d(a * a + v[2] * v[2]);
+  const double s = v[2] * inv, t = a * inv;
+  u[0] = x_big ? -s : 0.0; u[1] = x_big ? 0.0 : s; u[2] = x_big ? t : -t;
   cross3(v, u, w);
 }
+PW_HD double pow2_biased(int biased_exponent) {   // 2^(biased_exponent - 1023), 1 <= biased_exponent <= 2046
+  const long long bits = (long long) biased_exponent << 52;
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(bits);
+#else
+  double d; memcpy(&d, &bits, sizeof d); return d;
+#endif
+}
+PW_HD int biased_exponent_of(double x) {
+#if defined(__CUDA_ARCH__)
+  return (int) ((__double_as_longlong(x) >> 52) & 0x7ff);
+#else
+  long long bits; memcpy(&bits, &x, sizeof bits); return (int) ((bits >> 52) & 0x7ff);
+#endif
+}
+// Largest root of  l^3 - 3 l - x = 0  for x in [0, 2]  (= 2 cos(acos(x/2)/3), in [sqrt 3, 2]).
+// The root is simple with f' = 3 l^2 - 3 in [6, 9], so Newton's iteration is quadratically convergent from the
+// degree-4 fit below (|error| <= 1.9e-5 over the interval): 2e-5 -> 3e-10 -> 1e-17 -> done; the slope's reciprocal only
+// needs single precision for that. ~30 instructions instead of the double-precision acos + cos (~600 with their
+// slow paths), and the same arithmetic on host and device.
+PW_HD double cubic_top_root(double x) {
+  const float t = (float) x - 1.0f;
+  const float l0 = fmaf(fmaf(fmaf(fmaf(-5.08044654e-04f, t, 2.34362113e-03f), t, -1.28488787e-02f), t, 1.31615076e-01f), t, 1.87938457f);
+  double l = (double) l0;
+  for (int k = 0; k < 3; ++k) {
+    const double f = fma(fma(l, l, -3.0), l, -x);
+    const double fp = fma(3.0 * l, l, -3.0);
+    const double r = (double) rcp_f((float) fp);
+    l = fma(-f, r, l);
+  }
+  return l;
+}
 // Same contract as jacobi_svd3(): sv descending, ucol2 = unit eigenvector of the smallest singular value.
-// Steps: (1) scale by the largest |entry|; (2) trigonometric root of the characteristic cubic for the extreme
-// eigenvalue that is better isolated (the largest if det(B) >= 0, else the smallest) — that root is insensitive to
-// the rounding of acos, unlike the clustered pair; (3) its eigenvector from the rows of (A - lambda I);
-// (4) the other two eigenpairs EXACTLY from the 2x2 problem in the orthogonal complement (one Jacobi rotation).
+// Steps: (1) scale by the power of two that brings the largest |entry| into [1, 2) (exact); (2) the extreme eigenvalue
+// that is better isolated (the largest if det(B) >= 0, else the smallest) as the simple root of the characteristic
+// cubic in its trigonometric normal form (cubic_top_root) — that root is well conditioned, unlike the clustered pair;
+// (3) its eigenvector from the rows of (A - lambda I); (4) the other two eigenpairs EXACTLY from the 2x2 problem in
+// the orthogonal complement (one Jacobi rotation).
 // Measured accuracy of the returned vector: <= 8 eps * lambda_max / (lambda_mid - lambda_min) over 2e5 random
-// matrices including clustered spectra, i.e. the conditioning limit of the problem itself.
+// matrices including clustered spectra, i.e. the conditioning limit of the problem itself (tests/test_host_twin.py).
 PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, double czz, double sv[3], double ucol2[3]) {
   const double amax = fmax(fmax(fabs(cxx), fabs(cxy)), fmax(fmax(fabs(cxz), fabs(cyy)), fmax(fabs(cyz), fabs(czz))));
-  if (!(amax <= DBL_MAX)) {  // S:57 with one point: 0/0. Defined as U = I, singular values NaN (oracle header).
+  const double chk = (cxx + cxy) + (cxz + cyy) + (cyz + czz);   // fmax() skips NaN operands; the sum does not
+  if (!(amax <= DBL_MAX) || chk != chk) {  // S:57 with one point: 0/0. Defined as U = I, singular values NaN (oracle header).
     sv[0] = sv[1] = sv[2] = NAN;
     ucol2[0] = 0; ucol2[1] = 0; ucol2[2] = 1;
     return;
   }
   if (amax == 0.0) { sv[0] = sv[1] = sv[2] = 0.0; ucol2[0] = 0; ucol2[1] = 0; ucol2[2] = 1; return; }
-  const double inv = 1.0 / amax;
+  int be = biased_exponent_of(amax);
+  be = be < 1 ? 1 : (be > 2045 ? 2045 : be);
+  const double inv = pow2_biased(2046 - be), unscale = pow2_biased(be);
   const double a00 = cxx * inv, a01 = cxy * inv, a02 = cxz * inv, a11 = cyy * inv, a12 = cyz * inv, a22 = czz * inv;
   const double norm = a01 * a01 + a02 * a02 + a12 * a12;
   const double q = (a00 + a11 + a22) * (1.0 / 3.0);   // any shift near trace/3 works
   const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
-  const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) * (1.0 / 6.0));
-  const double p3 = p * p * p;
+  const double p2 = (b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) * (1.0 / 6.0);
+  const double rp = rsqrt_d(p2), rp3 = rp * rp * rp;   // p2 == 0 -> inf, rejected below
   double e0, e1, e2;  // ascending
   double v0[3];
-  if (norm > 0.0 && p3 > 0.0) {
+  if (norm > 0.0 && rp3 <= DBL_MAX) {
     const double c00 = b11 * b22 - a12 * a12, c01 = a01 * b22 - a12 * a02, c02 = a01 * a12 - b11 * a02;
-    double half_det = (b00 * c00 - a01 * c01 + a02 * c02) / p3 * 0.5;
-    half_det = half_det < -1.0 ? -1.0 : (half_det > 1.0 ? 1.0 : half_det);
-    const double angle = acos(half_det) * (1.0 / 3.0);
-    const bool top = half_det >= 0.0;  // isolate the largest eigenvalue, else the smallest
-    const double e_iso = q + p * 2.0 * (top ? cos(angle) : cos(angle + 2.09439510239319549));
+    const double det = b00 * c00 - a01 * c01 + a02 * c02;   // det(B); det(B / p) = 2 cos(3 theta) in [-2, 2]
+    double x = fabs(det) * rp3;
+    x = x > 2.0 ? 2.0 : x;
+    const bool top = det >= 0.0;  // isolate the largest eigenvalue, else the smallest
+    const double pl = p2 * rp * cubic_top_root(x);
+    const double e_iso = top ? q + pl : q - pl;
     double v[3];
     eigvec_by_rows(a00, a01, a02, a11, a12, a22, e_iso, v);
     const double av[3] = {a00 * v[0] + a01 * v[1] + a02 * v[2], a01 * v[0] + a11 * v[1] + a12 * v[2], a02 * v[0] + a12 * v[1] + a22 * v[2]};
@@ -435,10 +502,12 @@ PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, 
     const double m00 = u[0] * au[0] + u[1] * au[1] + u[2] * au[2];
     const double m01 = u[0] * aw[0] + u[1] * aw[1] + u[2] * aw[2];
     const double m11 = w[0] * aw[0] + w[1] * aw[1] + w[2] * aw[2];
+    // Jacobi rotation of [[m00, m01], [m01, m11]]: t = tan(phi) = sign(d) m01 / (|d| + hypot(d, m01)), d = (m11 - m00)/2
     double c = 1.0, sn = 0.0, la = m00, lb = m11;
-    if (m01 != 0.0) {
-      const double tau = (m11 - m00) / (m01 * 2.0);
-      const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+    const double dl = (m11 - m00) * 0.5;
+    const double h2 = dl * dl + m01 * m01;
+    if (m01 != 0.0 && h2 > 0.0) {
+      const double t = (dl >= 0.0 ? m01 : -m01) * rcp_d(fabs(dl) + h2 * rsqrt_d(h2));
       c = rsqrt_d(1.0 + t * t);
       sn = t * c;
       la = m00 - t * m01;
@@ -465,7 +534,7 @@ PW_HD void sym_eig3(double cxx, double cxy, double cxz, double cyy, double cyz, 
     if (e1 > e2) { const double t = e1; e1 = e2; e2 = t; }
     if (e0 > e1) { const double t = e0; e0 = e1; e1 = t; }
   }
-  double s0 = fabs(e2) * amax, s1 = fabs(e1) * amax, s2 = fabs(e0) * amax;
+  double s0 = fabs(e2) * unscale, s1 = fabs(e1) * unscale, s2 = fabs(e0) * unscale;
   if (s1 > s0) { const double t = s0; s0 = s1; s1 = t; }
   if (s2 > s1) { const double t = s1; s1 = s2; s2 = t; }
   if (s1 > s0) { const double t = s0; s0 = s1; s1 = t; }
@@ -484,11 +553,11 @@ struct Moments {
 // estimate_plane (S:47-75) from the moment sums. n == 0 must be handled by the caller (S:49: keep
 // the previous plane). mean = c + s1/n ; cov = (s2 - s1 s1^T / n) / (n-1).
 PW_HD void plane_from_moments(const Moments& m, const double c[3], Plane& pl) {
-  const double inv_n = 1.0 / (double) m.n;
+  const double inv_n = rcp_d((double) m.n);
   const double m0 = m.s1[0] * inv_n, m1 = m.s1[1] * inv_n, m2 = m.s1[2] * inv_n;
   pl.mean[0] = c[0] + m0; pl.mean[1] = c[1] + m1; pl.mean[2] = c[2] + m2;
   // n == 1: 0 * inf = NaN covariance, like the 0/0 of S:57
-  const double inv_dn = 1.0 / (double) (m.n - 1);
+  const double inv_dn = rcp_d((double) (m.n - 1));
   const double cxx = (m.s2[0] - m.s1[0] * m0) * inv_dn;
   const double cxy = (m.s2[1] - m.s1[0] * m1) * inv_dn;
   const double cxz = (m.s2[2] - m.s1[0] * m2) * inv_dn;

@@ -233,4 +233,11 @@ void twin_history(void* h, int ring, int which, double* dst) {
   const int n = which ? t->st.n_flat[ring] : t->st.n_elev[ring];
   std::memcpy(dst, t->hist.data() + ((size_t) which * 4 + ring) * t->hcap, (size_t) n * 8);
 }
+// batch access to the two 3x3 solvers for tests/test_host_twin.py: cov = n x 6 (xx xy xz yy yz zz), out = n x 6 (sv, vector)
+void twin_sym_eig3(const double* cov, long long n, double* out) {
+  for (long long i = 0; i < n; ++i) sym_eig3(cov[i * 6], cov[i * 6 + 1], cov[i * 6 + 2], cov[i * 6 + 3], cov[i * 6 + 4], cov[i * 6 + 5], out + i * 6, out + i * 6 + 3);
+}
+void twin_jacobi_svd3(const double* cov, long long n, double* out) {
+  for (long long i = 0; i < n; ++i) jacobi_svd3(cov[i * 6], cov[i * 6 + 1], cov[i * 6 + 2], cov[i * 6 + 3], cov[i * 6 + 4], cov[i * 6 + 5], out + i * 6, out + i * 6 + 3);
+}
 }  // extern "C"

@@ -69,3 +69,64 @@ def test_binning_filter_exact_on_adversarial_points():
     orc.estimate(a); tw.estimate(a)
     assert np.array_equal(orc.bin_ids(), tw.bin_ids())
     assert tw.fast_mismatches() == 0
+
+
+def _random_spd(rng, n):
+    """n symmetric PSD 3x3 matrices with prescribed spectra: generic, clustered low pair, clustered high pair, rank 1/2, scaled."""
+    q, _ = np.linalg.qr(rng.normal(size=(n, 3, 3)))
+    lam = np.sort(rng.uniform(0.0, 1.0, size=(n, 3)), axis=1)
+    kind = rng.integers(0, 6, size=n)
+    lam[kind == 1, 1] = lam[kind == 1, 0] * (1 + 10.0 ** rng.uniform(-12, -1, size=(kind == 1).sum()))     # low pair clustered
+    lam[kind == 2, 1] = lam[kind == 2, 2] * (1 - 10.0 ** rng.uniform(-12, -1, size=(kind == 2).sum()))     # high pair clustered
+    lam[kind == 3, 0] = 0.0                                                                               # rank 2 (flat patch)
+    lam[kind == 4, :2] *= 10.0 ** rng.uniform(-10, -2, size=((kind == 4).sum(), 1))                          # nearly a line
+    lam = np.sort(lam, axis=1)
+    scale = 10.0 ** rng.uniform(-8, 6, size=(n, 1))
+    lam = lam * scale
+    a = np.einsum("nij,nj,nkj->nik", q, lam, q)
+    a = 0.5 * (a + a.transpose(0, 2, 1))
+    return a, lam
+
+
+def test_closed_form_eigensolver_against_lapack_and_jacobi():
+    """The device's 3x3 solver (csrc/pwpp_math.cuh sym_eig3: Newton root of the characteristic cubic + 2x2 deflation)
+    vs numpy's eigh and the Jacobi SVD the oracle uses. Tolerances are the conditioning limit of the problem:
+    singular values to 16 eps * lambda_max, the normal to 16 eps * lambda_max / (lambda_mid - lambda_min)."""
+    import ctypes as C
+    from helpers import HERE
+    import os
+    lib = C.CDLL(os.path.join(HERE, "_build", "libpwpp_twin.so"))
+    for f in (lib.twin_sym_eig3, lib.twin_jacobi_svd3): f.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
+    rng = np.random.default_rng(5)
+    n = 200_000
+    a, _ = _random_spd(rng, n)
+    cov = np.ascontiguousarray(np.stack([a[:, 0, 0], a[:, 0, 1], a[:, 0, 2], a[:, 1, 1], a[:, 1, 2], a[:, 2, 2]], axis=1))
+    out = np.empty((n, 6)); jac = np.empty((n, 6))
+    lib.twin_sym_eig3(cov.ctypes.data, n, out.ctypes.data)
+    lib.twin_jacobi_svd3(cov.ctypes.data, n, jac.ctypes.data)
+    w, v = np.linalg.eigh(a)                      # ascending
+    eps = np.finfo(float).eps
+    lmax = np.abs(w).max(axis=1)
+    sv_ref = np.sort(np.abs(w), axis=1)[:, ::-1]
+    assert (np.abs(out[:, :3] - sv_ref).max(axis=1) <= 16 * eps * lmax).all()
+    assert (np.abs(jac[:, :3] - sv_ref).max(axis=1) <= 64 * eps * lmax).all()
+    vec = out[:, 3:]
+    assert np.abs(np.linalg.norm(vec, axis=1) - 1).max() < 8 * eps
+    # residual of the eigen-pair: |A v - l v| <= 16 eps lmax — holds regardless of clustering
+    lmin = out[:, 2]
+    res = np.linalg.norm(np.einsum("nij,nj->ni", a, vec) - lmin[:, None] * vec, axis=1)
+    assert (res <= 16 * eps * lmax).all(), float((res / (eps * lmax)).max())
+    gap = w[:, 1] - w[:, 0]
+    ok = gap > 1e3 * eps * lmax
+    ref = v[:, :, 0]
+    sgn = np.sign(np.einsum("ni,ni->n", ref, vec)); sgn[sgn == 0] = 1
+    err = np.linalg.norm(vec - sgn[:, None] * ref, axis=1)
+    assert (err[ok] <= 16 * eps * lmax[ok] / gap[ok]).all(), float((err[ok] * gap[ok] / (eps * lmax[ok])).max())
+    # degenerate inputs keep the contract of jacobi_svd3
+    special = np.array([[0, 0, 0, 0, 0, 0], [2, 0, 0, 2, 0, 2], [3, 0, 0, 1, 0, 2], [np.nan, 0, 0, 1, 0, 1], [np.inf, 0, 0, 1, 0, 1],
+                        [1e-300, 0, 0, 1e-300, 1e-301, 1e-300], [1e300, 1e299, 0, 1e300, 0, 1e300]], dtype=float)
+    o2 = np.empty((len(special), 6)); lib.twin_sym_eig3(special.ctypes.data, len(special), o2.ctypes.data)
+    assert np.array_equal(o2[0], [0, 0, 0, 0, 0, 1])
+    assert np.allclose(o2[1, :3], 2) and np.allclose(o2[2, :3], [3, 2, 1]) and np.allclose(np.abs(o2[2, 3:]), [0, 1, 0])
+    assert np.isnan(o2[3, :3]).all() and np.isnan(o2[4, :3]).all() and np.array_equal(o2[3, 3:], [0, 0, 1])
+    assert np.isfinite(o2[5:]).all() and np.allclose(o2[6, :3] / 1e300, [1.1, 1.0, 0.9])
