@@ -79,6 +79,13 @@ struct PinBuf {
 
 }  // namespace
 
+typedef void (*FitKernel)(const float4*, FrameTable, const StreamState*, Geometry, AlgoParams, int, const int*, WorkQueues, int*, BinFit*);
+struct FitLaunch {
+  FitKernel fn = nullptr;
+  int grid = 0, threads = 0;
+  size_t smem = 0;
+};
+
 struct pwpp_ctx {
   pwpp_params prm;
   Geometry g;
@@ -89,8 +96,8 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 1, sw_scatter_pipe = 1, sw_warp_top = 2, sw_m_u = 4;
-  bool sw_l1_warp = true, sw_serial_fit = false;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 1, sw_emit_rows = -1;
+  bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
@@ -118,8 +125,7 @@ struct pwpp_ctx {
   DevBuf<BinSeg> d_segs;          // [F][nbins+3]
   DevBuf<int4> d_wq_items[NUM_CLASSES];  // fit work queues
   DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES]: counts, heads
-  int fit_grid[NUM_CLASSES] = {0, 0, 0, 0, 0, 0};  // persistent grid sizes
-  int fit_grid_l1w = 0;
+  FitLaunch fit[NUM_CLASSES];   // persistent fit kernel of every patch-size class (variant chosen in pwpp_create)
   int max_sectors = 0;
   DevBuf<int> d_out_idx;
   DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
@@ -250,7 +256,6 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     const size_t sm_h = nbp * sizeof(unsigned int);
     if (!ctx->fast_bin) k_bin_hist<false, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
     else if (hist_pipe == 0) k_bin_hist<true, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
-    else if (hist_pipe == 1) k_bin_hist<true, 1><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
     else k_bin_hist<true, 2><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
 #undef HIST_ARGS
     ++ctx->launches;
@@ -265,10 +270,16 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   STAGE_MARK();
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
-    const bool scatter_pipe = ctx->sw_scatter_pipe != 0;
     const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
-    if (scatter_pipe) k_scatter<true><<<grid, CHUNK_THREADS, sm_sc, s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
-    else k_scatter<false><<<grid, CHUNK_THREADS, sm_sc, s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
+#define SC_ARGS d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p
+    switch (ctx->sw_scatter_pipe) {   // PWPP_SCATTER_V: load schedule x CTAs per SM the registers are sized for
+      case 0: k_scatter<false, 2><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
+      case 2: k_scatter<false, 3><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
+      case 3: k_scatter<false, 4><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
+      case 4: k_scatter<true, 3><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
+      default: k_scatter<true, 2><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
+    }
+#undef SC_ARGS
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -277,52 +288,20 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   // left) overlaps the start of the next.
 #define FIT_ARGS ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits
   const bool serial_fit = ctx->sw_serial_fit;   // PWPP_SERIAL_FIT: diagnostic switch
-  // Experiment switches (defaults = the measured best):
-  //   PWPP_WARP_TOP=2|3|4  largest class drained by the barrier-free streaming warp kernel (2: 513..2048-point patches,
-  //                        measured 0.88 vs 1.23 ms per 1024 frames against the CTA kernel; 3/4 also take the 4096 / 8192 classes)
-  //   PWPP_L1_CTA=1        class 2 back on the CTA kernel
-  //   PWPP_M_U=1|2|4       pass unrolling of the staged warp kernel (65..512-point patches)
-  const int warp_top = ctx->sw_warp_top;
-  const bool l1_warp = ctx->sw_l1_warp;
-  const int m_u = ctx->sw_m_u;
-  const size_t sm_l1 = 3 * 2048 * sizeof(float), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
-  const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4);
-  auto launch_l3 = [&](cudaStream_t st) { if (warp_top < 4 || !l1_warp) k_fit_cta<8192, 4><<<ctx->fit_grid[4], FIT_THREADS, sm_l3, st>>>(FIT_ARGS); };
-  auto launch_l2 = [&](cudaStream_t st) { if (warp_top < 3 || !l1_warp) k_fit_cta<4096, 3><<<ctx->fit_grid[3], FIT_THREADS, sm_l2, st>>>(FIT_ARGS); };
-  auto launch_l1 = [&](cudaStream_t st) {
-    if (!l1_warp) k_fit_cta<2048, 2><<<ctx->fit_grid[2], FIT_THREADS, sm_l1, st>>>(FIT_ARGS);
-    else if (warp_top == 4) k_fit_warp<false, 4, 2, FITW_U><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, st>>>(FIT_ARGS);
-    else if (warp_top == 3) k_fit_warp<false, 3, 2, FITW_U><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, st>>>(FIT_ARGS);
-    else k_fit_warp<false, 2, 2, FITW_U><<<ctx->fit_grid_l1w, FITW_WARPS * 32, 0, st>>>(FIT_ARGS);
-  };
-  auto launch_m = [&](cudaStream_t st) {
-    if (m_u == 1) k_fit_warp<true, 1, 1, 1><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, st>>>(FIT_ARGS);
-    else if (m_u == 2) k_fit_warp<true, 1, 1, 2><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, st>>>(FIT_ARGS);
-    else k_fit_warp<true, 1, 1, 4><<<ctx->fit_grid[1], FITW_WARPS * 32, sm_m, st>>>(FIT_ARGS);
-  };
+  auto launch_fit = [&](int c, cudaStream_t st) { const FitLaunch& k = ctx->fit[c]; k.fn<<<k.grid, k.threads, k.smem, st>>>(FIT_ARGS); };
   if (prof || serial_fit) {
-    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, s>>>(FIT_ARGS);
-    STAGE_MARK();
-    launch_l3(s);
-    STAGE_MARK();
-    launch_l2(s);
-    STAGE_MARK();
-    launch_l1(s);
-    STAGE_MARK();
-    launch_m(s);
-    STAGE_MARK();
-    k_fit_stream<<<ctx->fit_grid[5], 128, 0, s>>>(FIT_ARGS);
-    STAGE_MARK();
+    static const int order[NUM_CLASSES] = {0, 4, 3, 2, 1, 5};   // stage slots: S, L3, L2, L1, M, X
+    for (int q = 0; q < NUM_CLASSES; ++q) { launch_fit(order[q], s); STAGE_MARK(); }
   } else {
     CU_TRY(cudaEventRecord(ctx->ev_fork, s));
     for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
     // longest classes first
-    launch_l3(s);
-    launch_l2(ctx->side[0]);
-    launch_l1(ctx->side[1]);
-    launch_m(ctx->side[2]);
-    k_fit_resident<8, 8, 0><<<ctx->fit_grid[0], FIT_THREADS, 0, ctx->side[3]>>>(FIT_ARGS);
-    k_fit_stream<<<ctx->fit_grid[5], 128, 0, ctx->side[4]>>>(FIT_ARGS);
+    launch_fit(4, s);
+    launch_fit(3, ctx->side[0]);
+    launch_fit(2, ctx->side[1]);
+    launch_fit(1, ctx->side[2]);
+    launch_fit(0, ctx->side[3]);
+    launch_fit(5, ctx->side[4]);
     for (int q = 0; q < 5; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
     stage += 6;
   }
@@ -338,8 +317,16 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   }
   STAGE_MARK();
   if (max_chunks > 0) {
-    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
-    k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    // a warp per bin gives the most parallelism for a few frames; a warp per 32 consecutive bins streams better once
+    // the batch alone fills the GPU (PWPP_EMIT_ROWS=0|1 forces one form)
+    const bool rows = ctx->sw_emit_rows < 0 ? nframes >= 32 : ctx->sw_emit_rows != 0;
+    if (rows) {
+      dim3 grid((nb_all + 32 * EMIT_WARPS - 1) / (32 * EMIT_WARPS), nframes);
+      k_emit_rows<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    } else {
+      dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
+      k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    }
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -461,11 +448,9 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->device = device;
   ctx->num_streams = num_streams;
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
-  ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", 1, 0, 2);
-  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_PIPE", 1, 0, 1);
-  ctx->sw_warp_top = env_int("PWPP_WARP_TOP", 2, 2, 4);
-  ctx->sw_m_u = env_int("PWPP_M_U", 4, 1, 4);
-  ctx->sw_l1_warp = std::getenv("PWPP_L1_CTA") == nullptr;
+  ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", 2, 0, 2);
+  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", 1, 0, 4);
+  ctx->sw_emit_rows = env_int("PWPP_EMIT_ROWS", -1, -1, 1);
   ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
@@ -507,32 +492,35 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   {
     cudaDeviceProp prop;
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
-    int per_sm[NUM_CLASSES] = {1, 1, 1, 1, 1, 1};
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<8192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 8192 * sizeof(float))));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_cta<4096, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (3 * 4096 * sizeof(float))));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
-    CU_TRY_CTX(cudaFuncSetAttribute(k_fit_warp<true, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FITW_WARPS * CLS_M_MAX * sizeof(float4))));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_fit_resident<8, 8, 0>, FIT_THREADS, 0));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fit_warp<true, 1, 1, 4>, FITW_WARPS * 32, FITW_WARPS * CLS_M_MAX * sizeof(float4)));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fit_cta<2048, 2>, FIT_THREADS, 3 * 2048 * sizeof(float)));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_fit_cta<4096, 3>, FIT_THREADS, 3 * 4096 * sizeof(float)));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_fit_cta<8192, 4>, FIT_THREADS, 3 * 8192 * sizeof(float)));
-    CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[5], k_fit_stream, 128, 0));
-    {
-      int l1w = 1;
-      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&l1w, k_fit_warp<false, 4, 2, FITW_U>, FITW_WARPS * 32, 0));
-      ctx->fit_grid_l1w = std::max(1, l1w) * prop.multiProcessorCount;
+    // Fit kernel of every class. The *_MINB switches pick the launch-bounds variant (CTAs per SM the register
+    // allocation is sized for): these kernels are latency-bound, so more resident warps can pay for a few spills.
+    const int s_minb = env_int("PWPP_S_MINB", 2, 2, 4), m_minb = env_int("PWPP_M_MINB", 2, 2, 3);
+    const int l1_minb = env_int("PWPP_L1_MINB", 2, 2, 4), l2_minb = env_int("PWPP_L2_MINB", 4, 3, 4);   // measured: 4 CTAs/SM on the 4096 class: 1.31 -> 1.23 ms
+    const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
+    ctx->fit[0] = {s_minb == 4 ? k_fit_resident<8, 8, 0, 4> : s_minb == 3 ? k_fit_resident<8, 8, 0, 3> : k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
+    ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3> : k_fit_warp<true, 1, 1, 2, 2>, 0, FITW_WARPS * 32, sm_m};
+    ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3> : k_fit_warp<false, 2, 2, FITW_U, 2>, 0, FITW_WARPS * 32, 0};
+    ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4> : k_fit_cta<4096, 3, 3>, 0, FIT_THREADS, sm_l2};
+    ctx->fit[4] = {k_fit_cta<8192, 4, 2>, 0, FIT_THREADS, sm_l3};
+    ctx->fit[5] = {k_fit_stream, 0, 128, 0};
+    for (int c = 0; c < NUM_CLASSES; ++c) {
+      FitLaunch& k = ctx->fit[c];
+      if (k.smem > 0) CU_TRY_CTX(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k.smem));
+      int per_sm = 1;
+      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.threads, k.smem));
+      k.grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
-    for (int c = 0; c < NUM_CLASSES; ++c) ctx->fit_grid[c] = std::max(1, per_sm[c]) * prop.multiProcessorCount;
     const size_t gle_smem = (size_t) 6 * max_sectors * sizeof(double) + (size_t) 2 * max_sectors * sizeof(int);
     if (gle_smem > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_gle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gle_smem));
   }
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
     if (scat > 48 * 1024) {
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
     }
   }
   *out = ctx;

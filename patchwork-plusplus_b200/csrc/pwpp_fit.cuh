@@ -148,8 +148,8 @@ enum FitState { ST_RVPF = 0, ST_SEED = 1, ST_GPF = 2, ST_FINAL = 3, ST_DONE = 4 
 // own work items from the queue and every lane of a group evaluates the 3x3 eigen-problem of its patch redundantly
 // (the butterfly reductions leave bit-identical moments in all lanes of the group).
 // Point j of a patch lives in lane (j % G) of the group at register slot (j / G).
-template <int G, int K, int CLS>
-__global__ void __launch_bounds__(FIT_THREADS, 2) k_fit_resident(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+template <int G, int K, int CLS, int MINB>
+__global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_resident(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                  Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                  int* __restrict__ part, BinFit* __restrict__ fits) {
   static_assert(G == 8 || G == 32, "group is a warp or a quarter warp");
@@ -379,8 +379,8 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // cross-warp prefix. The LPR selection is two-level: the num_lpr-th smallest of the 256 per-thread minima bounds
 // the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
 // selected exactly by one warp.
-template <int CAP, int CLS>
-__global__ void __launch_bounds__(FIT_THREADS, (CAP <= 4096 ? 3 : 2)) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+template <int CAP, int CLS, int MINB>
+__global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
   constexpr int ITERS = CAP / FIT_THREADS;   // 8 or 32 slots per thread
@@ -1010,8 +1010,8 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-template <bool STAGE, int CLS_HI, int CLS_LO, int U>
-__global__ void __launch_bounds__(FITW_WARPS * 32, 2) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB>
+__global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
   constexpr int CAP = STAGE ? CLS_M_MAX : (CLS_HI == 2 ? CLS_L1_MAX : WARP_CAP);
