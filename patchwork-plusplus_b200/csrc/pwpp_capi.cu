@@ -96,7 +96,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 1, sw_emit_rows = -1;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 0;
   bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -272,13 +272,8 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     dim3 grid(max_chunks, nframes);
     const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
 #define SC_ARGS d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p
-    switch (ctx->sw_scatter_pipe) {   // PWPP_SCATTER_V: load schedule x CTAs per SM the registers are sized for
-      case 0: k_scatter<false, 2><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
-      case 2: k_scatter<false, 3><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
-      case 3: k_scatter<false, 4><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
-      case 4: k_scatter<true, 3><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
-      default: k_scatter<true, 2><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS); break;
-    }
+    if (ctx->sw_scatter_pipe) k_scatter<true, 3><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS);   // PWPP_SCATTER_V=1
+    else k_scatter<false, 4><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS);
 #undef SC_ARGS
     ++ctx->launches;
   }
@@ -317,16 +312,8 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   }
   STAGE_MARK();
   if (max_chunks > 0) {
-    // a warp per bin gives the most parallelism for a few frames; a warp per 32 consecutive bins streams better once
-    // the batch alone fills the GPU (PWPP_EMIT_ROWS=0|1 forces one form)
-    const bool rows = ctx->sw_emit_rows < 0 ? nframes >= 32 : ctx->sw_emit_rows != 0;
-    if (rows) {
-      dim3 grid((nb_all + 32 * EMIT_WARPS - 1) / (32 * EMIT_WARPS), nframes);
-      k_emit_rows<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
-    } else {
-      dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
-      k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
-    }
+    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
+    k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -449,8 +436,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->num_streams = num_streams;
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
   ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", 2, 0, 2);
-  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", 1, 0, 4);
-  ctx->sw_emit_rows = env_int("PWPP_EMIT_ROWS", -1, -1, 1);
+  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", 0, 0, 1);
   ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
@@ -500,8 +486,10 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     ctx->fit[0] = {s_minb == 4 ? k_fit_resident<8, 8, 0, 4> : s_minb == 3 ? k_fit_resident<8, 8, 0, 3> : k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
     ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3> : k_fit_warp<true, 1, 1, 2, 2>, 0, FITW_WARPS * 32, sm_m};
     ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3> : k_fit_warp<false, 2, 2, FITW_U, 2>, 0, FITW_WARPS * 32, 0};
-    ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4> : k_fit_cta<4096, 3, 3>, 0, FIT_THREADS, sm_l2};
-    ctx->fit[4] = {k_fit_cta<8192, 4, 2>, 0, FIT_THREADS, sm_l3};
+    ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8> : k_fit_cta<4096, 3, 3, 8>, 0, FIT_THREADS, sm_l2};
+    if (env_int("PWPP_L2_NW", 8, 8, 16) == 16) ctx->fit[3] = {k_fit_cta<4096, 3, 2, 16>, 0, 512, sm_l2};
+    ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8>, 0, FIT_THREADS, sm_l3};
+    if (env_int("PWPP_L3_NW", 8, 8, 16) == 16) ctx->fit[4] = {k_fit_cta<8192, 4, 2, 16>, 0, 512, sm_l3};
     ctx->fit[5] = {k_fit_stream, 0, 128, 0};
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];
@@ -516,10 +504,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
     if (scat > 48 * 1024) {
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
       CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
       CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
     }
   }

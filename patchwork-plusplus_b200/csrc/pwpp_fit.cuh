@@ -379,23 +379,25 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // cross-warp prefix. The LPR selection is two-level: the num_lpr-th smallest of the 256 per-thread minima bounds
 // the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
 // selected exactly by one warp.
-template <int CAP, int CLS, int MINB>
-__global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
+template <int CAP, int CLS, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
-  constexpr int ITERS = CAP / FIT_THREADS;   // 8 or 32 slots per thread
+  constexpr int NT = NW * 32;                // NW warps per patch (8 or 16)
+  static_assert(NW == 8 || NW == 16, "warp 0 keeps NW minima per lane and splits a patch into NW contiguous chunks");
+  static_assert(CAP / NT <= 32, "slot masks are 32-bit");
   constexpr int CCAP = 512;
   extern __shared__ float s_pts[];
   float* sx = s_pts;
   float* sy = sx + CAP;
   float* sz = sy + CAP;
-  __shared__ double s_part[2][8][9];   // per-warp partial moments, double-buffered by round parity
-  __shared__ int s_pcnt[2][8], s_pchg[2][8];
-  __shared__ int s_cnt[8][2];
-  __shared__ unsigned s_min[FIT_THREADS];
+  __shared__ double s_part[2][NW][9];   // per-warp partial moments, double-buffered by round parity
+  __shared__ int s_pcnt[2][NW], s_pchg[2][NW];
+  __shared__ int s_cnt[NW][2];
+  __shared__ unsigned s_min[NT];
   __shared__ unsigned s_cand[CCAP];
   __shared__ double s_lpr;
-  __shared__ double s_fb[8];
+  __shared__ double s_fb[NW];
   __shared__ unsigned s_T;
   __shared__ int s_ccount, s_mn, s_fix, s_refit;
   __shared__ int4 s_item;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
   // Queue protocol: the last warp claims one patch AHEAD — the atomic at the top of a patch, the descriptor load after
   // the staging loads, an L2 prefetch of that patch's points while warp 0 solves the first plane (when the other
   // warps idle anyway) — and publishes the descriptor through s_item at the end of the patch; x < 0 = queue drained.
-  constexpr int LOOK_W = FIT_THREADS / 32 - 1, LOOK_TID = LOOK_W * 32;
+  constexpr int LOOK_W = NW - 1, LOOK_TID = LOOK_W * 32;
   if (tid == 0) {
     const int t = atomicAdd(&wq.head[CLS], 1);
     s_item = t < count ? wq.items[CLS][t] : no_item;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
     const long long start = work_item_start(cur);
     const float4* P = sorted + start;
     int* out = part + start;
-    const int chunk = (((n + 7) >> 3) + 31) & ~31;   // points per warp, multiple of 32
+    const int chunk = (((n + NW - 1) / NW) + 31) & ~31;   // points per warp, multiple of 32
     const int nit = chunk >> 5;                      // slots per thread actually used (<= ITERS)
     const int jbase = w * chunk + lane;
     unsigned vmask = 0;
@@ -485,25 +487,25 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
         __syncthreads();
         int nvalid = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) nvalid += s_cnt[q][0];
+        for (int q = 0; q < NW; ++q) nvalid += s_cnt[q][0];
         const int target = nvalid < ap.num_lpr ? nvalid : ap.num_lpr;
         if (w == 0) {
-          unsigned mk[8];
+          unsigned mk[NW];
           int have = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { mk[q] = s_min[lane * 8 + q]; have += mk[q] != 0xffffffffu; }
+          for (int q = 0; q < NW; ++q) { mk[q] = s_min[lane * NW + q]; have += mk[q] != 0xffffffffu; }
           have = __reduce_add_sync(0xffffffffu, have);
           unsigned ans = 0xffffffffu;   // fewer candidate-holding threads than target: keep everything
           if (target > 0 && have >= target) {
             unsigned kmn = 0xffffffffu, kmx = 0u;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) if (mk[q] != 0xffffffffu) { kmn = min(kmn, mk[q]); kmx = max(kmx, mk[q]); }
+            for (int q = 0; q < NW; ++q) if (mk[q] != 0xffffffffu) { kmn = min(kmn, mk[q]); kmx = max(kmx, mk[q]); }
             kmn = __reduce_min_sync(0xffffffffu, kmn);
             kmx = __reduce_max_sync(0xffffffffu, kmx);
             ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
               int cnt = 0;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) cnt += mk[q] < cand;
+              for (int q = 0; q < NW; ++q) cnt += mk[q] < cand;
               return __reduce_add_sync(0xffffffffu, cnt);
             });
           }
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
             __syncthreads();
             int tot = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) tot += s_cnt[q][1];
+            for (int q = 0; q < NW; ++q) tot += s_cnt[q][1];
             __syncthreads();
             if (tot < target) ans = cand;
           }
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
           __syncthreads();
           if (tid == 0) {
             double tps = 0.0; int tlt = 0;
-            for (int q = 0; q < 8; ++q) { tps += s_fb[q]; tlt += s_cnt[q][1]; }
+            for (int q = 0; q < NW; ++q) { tps += s_fb[q]; tlt += s_cnt[q][1]; }
             s_lpr = target > 0 ? (tps + (double) (target - tlt) * (double) key_to_float(ans)) / (double) target : 0.0;
           }
           __syncthreads();
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
         s_pchg[buf][w] = nchg;
       }
       __syncthreads();
-      // warp 0 combines the 8 partials (lane q sums quantity q over the warps in a fixed order: bit-reproducible),
+      // warp 0 combines the NW partials (lane q sums quantity q over the warps in a fixed order: bit-reproducible),
       // keeps the running sums of the R-GPF phase, solves the 3x3 problem once and publishes the plane; the other
       // warps wait at the second barrier
       if (w == 0) {
@@ -651,13 +653,13 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_cta(const float4* __r
         int cn = 0;
         if (lane < 9) {
 #pragma unroll
-          for (int ww = 0; ww < 8; ++ww) v += s_part[buf][ww][lane];
+          for (int ww = 0; ww < NW; ++ww) v += s_part[buf][ww][lane];
         } else if (lane == 9) {
 #pragma unroll
-          for (int ww = 0; ww < 8; ++ww) cn += s_pcnt[buf][ww];
+          for (int ww = 0; ww < NW; ++ww) cn += s_pcnt[buf][ww];
         } else if (lane == 10) {
 #pragma unroll
-          for (int ww = 0; ww < 8; ++ww) cn += s_pchg[buf][ww];
+          for (int ww = 0; ww < NW; ++ww) cn += s_pchg[buf][ww];
         }
         Moments m;
 #pragma unroll

@@ -163,10 +163,10 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
 // among the frame's points of that bin in ascending point index.
 //   rank = cbase[chunk][bin] + (#points of bin in lower warps of the chunk)
 //        + (#points of bin in earlier iterations of this warp) + (#lower lanes with the same bin)
-// PIPE = true: the point loads are software-pipelined in two groups of SB and the first two groups are issued before
-// the histogram / prefix phases, so that 4..8 loads per lane are in flight from the first instruction to the last
-// (the kernel is latency-bound: 23 % active warps, 52 % long-scoreboard stalls in the r01 capture). PIPE = false is the
-// previous schedule (kept for A/B runs: PWPP_SCATTER_PIPE=0).
+// The kernel is latency-bound (r01 capture: 23 % active warps, 52 % long-scoreboard stalls, DRAM at 43 %), so what pays is
+// resident warps: sized for 4 CTAs per SM (64 registers) it runs 15 % faster than at 2 (0.83 vs 0.98 ms per 1024
+// frames). PIPE = true additionally software-pipelines the point loads in two groups of SB, the first two issued
+// before the histogram / prefix phases; measured equal at 3 CTAs per SM, kept as the PWPP_SCATTER_V=1 variant.
 template <bool PIPE, int MINB>
 __global__ void __launch_bounds__(CHUNK_THREADS, MINB) k_scatter(const float4* __restrict__ pts, FrameTable ft, int nbp,
                                                                const unsigned short* __restrict__ bin_ids, const unsigned int* __restrict__ cbase,
@@ -582,63 +582,6 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit(FrameTable ft, Geometr
     if (sg.ng_dst < 0) return;  // dropped points (S:591)
     const float4* src = sorted + p0 + off;
     for (int j = j0 + lane; j < j1; j += 32) out_idx[p0 + sg.ng_dst + j] = __float_as_int(src[j].w);
-  }
-}
-
-// k_emit_rows: the batch-throughput form of k_emit. One warp copies 32 CONSECUTIVE bins of a frame: their points are
-// one contiguous range of `part` / `sorted`, so the warp streams over that range with four loads in flight per lane
-// instead of paying several dependent round trips per bin; lane l keeps the metadata of bin b0 + l, and every
-// position finds its bin with a 5-step binary search over the lanes' offsets (indexed shuffles). Empty bins share
-// their offset with the next non-empty one, so "the last lane whose offset is <= j" is always the owning bin.
-__global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit_rows(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
-                                                               const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
-                                                               int* __restrict__ out_idx) {
-  const int f = blockIdx.y;
-  const int nb_all = g.nbins + PW_NUM_PSEUDO;
-  const int b0 = (blockIdx.x * EMIT_WARPS + (threadIdx.x >> 5)) * 32;
-  if (b0 >= nb_all) return;
-  const int lane = lane_id();
-  const long long p0 = ft.pt_off[f];
-  const int* bo = bin_off + (size_t) f * (nbp + 1);
-  const int b = b0 + lane;
-  const bool bv = b < nb_all;
-  const int bend = (b0 + 32 < nb_all) ? b0 + 32 : nb_all;
-  const int off = bv ? bo[b] : 0x7fffffff;
-  const int j_end = bo[bend];
-  const int j_begin = __shfl_sync(0xffffffffu, off, 0);
-  int nxt = __shfl_down_sync(0xffffffffu, off, 1);
-  if (b + 1 >= bend) nxt = j_end;
-  int ng = -1, g_dst = 0, ng_dst = -1;   // ng < 0: not fitted (everything goes to ng_dst, or is dropped when ng_dst < 0)
-  if (bv && nxt > off) {
-    const BinSeg sg = segs[(size_t) f * nb_all + b];
-    g_dst = sg.g_dst; ng_dst = sg.ng_dst;
-    if (b < g.nbins) { const BinFit& r = fits[(size_t) f * g.nbins + b]; if (r.fitted) ng = r.n_ground; }
-  }
-  for (int j0 = j_begin; j0 < j_end; j0 += 128) {
-    int v[4], dst[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int jj = j0 + lane + 32 * u;
-      const bool valid = jj < j_end;
-      const int jc = valid ? jj : j_end - 1;
-      int lo = 0;
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int probe = lo + step;            // <= 31
-        const int pv = __shfl_sync(0xffffffffu, off, probe);
-        if (pv <= jc) lo = probe;
-      }
-      const int o = __shfl_sync(0xffffffffu, off, lo), n_g = __shfl_sync(0xffffffffu, ng, lo);
-      const int gd = __shfl_sync(0xffffffffu, g_dst, lo), nd = __shfl_sync(0xffffffffu, ng_dst, lo);
-      const int r = jc - o;
-      dst[u] = -1; v[u] = 0;
-      if (valid) {
-        if (n_g >= 0) { v[u] = part[p0 + jc]; dst[u] = (r < n_g) ? (gd + r) : (nd + (r - n_g)); }
-        else if (nd >= 0) { v[u] = __float_as_int(sorted[p0 + jc].w); dst[u] = nd + r; }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (dst[u] >= 0) out_idx[p0 + dst[u]] = v[u];
   }
 }
 

@@ -8,15 +8,13 @@ sys.path.insert(0, os.path.join(REPO, "patchwork-plusplus_b200"))
 import pwpp_b200, synth
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-SWITCHES = ["PWPP_HIST_PIPE", "PWPP_SCATTER_V", "PWPP_SERIAL_FIT", "PWPP_S_MINB", "PWPP_M_MINB", "PWPP_L1_MINB", "PWPP_L2_MINB", "PWPP_EMIT_ROWS"]
+SWITCHES = ["PWPP_HIST_PIPE", "PWPP_SCATTER_V", "PWPP_SERIAL_FIT", "PWPP_S_MINB", "PWPP_M_MINB", "PWPP_L1_MINB", "PWPP_L2_MINB", "PWPP_L2_NW", "PWPP_L3_NW"]
 CONFIGS = [
     {},
-    {"PWPP_EMIT_ROWS": "0"},
-    {"PWPP_SCATTER_V": "0"},
-    {"PWPP_SCATTER_V": "2"},
-    {"PWPP_SCATTER_V": "3"},
-    {"PWPP_SCATTER_V": "4"},
-    {"PWPP_L2_MINB": "3"},
+    {"PWPP_L3_NW": "16"},
+    {"PWPP_L2_NW": "16"},
+    {"PWPP_L3_NW": "16", "PWPP_L2_NW": "16"},
+    {"PWPP_SCATTER_V": "1"},
     {},
 ]
 pts, offs = synth.make_batch(20260922, 0, F, "kitti64", "cuda")
