@@ -20,6 +20,13 @@ struct FrameTable {            // per call, device arrays indexed by frame
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#if defined(PWPP_SIMT_EMU)   // tests/simt: the kernels compiled by g++ and run lane by lane on the CPU (test infrastructure only)
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) { return *p; }
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
+// dynamic shared memory of a kernel, typed (tests/simt/cuda_runtime.h defines the CPU counterpart)
+#define PW_DYN_SHARED(T, name) extern __shared__ T name[]
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
@@ -28,5 +35,7 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 }  // namespace pwpp

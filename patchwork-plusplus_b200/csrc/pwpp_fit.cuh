@@ -48,7 +48,7 @@ __device__ __forceinline__ long long work_item_start(const int4& w) { return ((l
 // Pull the lines of a patch that will be processed next towards L2 (fire and forget): lanes stride over 128-byte lines.
 __device__ __forceinline__ void prefetch_patch_l2(const float4* P, int n, int lane, int nlanes) {
   const int lines = (n + 7) >> 3;
-  for (int l = lane; l < lines; l += nlanes) asm volatile("prefetch.global.L2 [%0];" ::"l"(P + (size_t) l * 8));
+  for (int l = lane; l < lines; l += nlanes) prefetch_l2(P + (size_t) l * 8);
 }
 
 __device__ __forceinline__ unsigned order_key(float z) {
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
   static_assert(NW == 8 || NW == 16, "warp 0 keeps NW minima per lane and splits a patch into NW contiguous chunks");
   static_assert(CAP / NT <= 32, "slot masks are 32-bit");
   constexpr int CCAP = 512;
-  extern __shared__ float s_pts[];
+  PW_DYN_SHARED(float, s_pts);
   float* sx = s_pts;
   float* sy = sx + CAP;
   float* sz = sy + CAP;
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
   __shared__ unsigned s_alive[FITW_WARPS][CAP / 32];
   __shared__ unsigned s_member[FITW_WARPS][CAP / 32];
   __shared__ float s_sel[FITW_WARPS][128];
-  extern __shared__ float4 s_stage[];           // STAGE: [FITW_WARPS][CLS_M_MAX]
+  PW_DYN_SHARED(float4, s_stage);              // STAGE: [FITW_WARPS][CLS_M_MAX]
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const unsigned lt = lanemask_lt();
   unsigned* alive_w = s_alive[warp];

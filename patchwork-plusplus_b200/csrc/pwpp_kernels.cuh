@@ -34,7 +34,7 @@ template <bool FAST, int PIPE>
 __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states,
                                                              Geometry g, AlgoParams ap, int has_intensity, int nbp,
                                                              unsigned short* __restrict__ bin_ids, unsigned short* __restrict__ chist) {
-  extern __shared__ unsigned int s_hist[];  // [nbp]
+  PW_DYN_SHARED(unsigned int, s_hist);  // [nbp]
   const int f = blockIdx.y;
   const long long p0 = ft.pt_off[f];
   const int n = (int) (ft.pt_off[f + 1] - p0);
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __r
 // num_min_pts are not fitted) and initialises the BinFit records of the patches that will not be fitted.
 __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, const unsigned short* __restrict__ chist, unsigned int* __restrict__ cbase,
                            int* __restrict__ bin_off, WorkQueues wq, BinFit* __restrict__ fits) {
-  extern __shared__ int s_scan[];  // [nbp + 1]
+  PW_DYN_SHARED(int, s_scan);  // [nbp + 1]
   __shared__ int s_cls_cnt[NUM_CLASSES], s_cls_base[NUM_CLASSES], s_cls_pos[NUM_CLASSES];
   const int f = blockIdx.x;
   const int c0 = ft.chunk_off[f], c1 = ft.chunk_off[f + 1];
@@ -171,7 +171,7 @@ template <bool PIPE, int MINB>
 __global__ void __launch_bounds__(CHUNK_THREADS, MINB) k_scatter(const float4* __restrict__ pts, FrameTable ft, int nbp,
                                                                const unsigned short* __restrict__ bin_ids, const unsigned int* __restrict__ cbase,
                                                                float4* __restrict__ sorted) {
-  extern __shared__ unsigned int s_wcnt[];  // [8][nbp]: per-warp histograms, then per-warp running positions
+  PW_DYN_SHARED(unsigned int, s_wcnt);  // [8][nbp]: per-warp histograms, then per-warp running positions
   const int f = blockIdx.y;
   const long long p0 = ft.pt_off[f];
   const int n = (int) (ft.pt_off[f + 1] - p0);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restri
                                             int nbp, int max_sectors, const int* __restrict__ bin_off, BinFit* __restrict__ fits, BinSeg* __restrict__ segs,
                                             int* __restrict__ num_ground, int* __restrict__ num_patches, float* __restrict__ centers, float* __restrict__ normals,
                                             int* __restrict__ num_dropped) {
-  extern __shared__ double s_gle[];
+  PW_DYN_SHARED(double, s_gle);
   double* s_rf = s_gle;                               // ringwise_flatness (S:182): [4 * max_sectors]
   double* s_clv = s_rf + 4 * max_sectors;             // candidates of the ring: line_variable [max_sectors]
   double* s_cfl = s_clv + max_sectors;                //                         flatness      [max_sectors]

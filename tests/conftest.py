@@ -38,6 +38,7 @@ def _build_checkers():
     import oracle_py
     oracle_py.build()
     build_twin()
+    build_simt()
 
 
 def build_twin(force=False):
@@ -50,6 +51,19 @@ def build_twin(force=False):
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",
                                "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I" + os.path.join(REPO, "include"),
                                "-I" + os.path.join(REPO, "patchwork-plusplus_b200", "csrc"), "-o", out, src])
+    return out
+
+
+def build_simt(force=False):
+    """The CUDA kernels compiled by g++ against the SIMT stand-in (tests/simt/cuda_runtime.h) for CPU execution."""
+    out = os.path.join(HERE, "_build", "libpwpp_simt.so")
+    csrc = os.path.join(REPO, "patchwork-plusplus_b200", "csrc")
+    deps = [os.path.join(HERE, "simt", f) for f in ("simt_twin.cpp", "cuda_runtime.h")] + \
+           [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp"))]
+    if force or not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(HERE, "simt"),
+                               "-I" + os.path.join(REPO, "include"), "-I" + csrc, "-o", out, os.path.join(HERE, "simt", "simt_twin.cpp")])
     return out
 
 

@@ -103,3 +103,56 @@ def assert_state_close(sa, sb, what=""):
         assert abs(sa.elevation_thr[i] - sb.elevation_thr[i]) <= TOL_STATE, f"{what} elevation_thr[{i}]"
         assert abs(sa.flatness_thr[i] - sb.flatness_thr[i]) <= 1e-6 * max(abs(sb.flatness_thr[i]), 1e-12), f"{what} flatness_thr[{i}]"
     assert list(sa.n_elevation) == list(sb.n_elevation) and list(sa.n_flatness) == list(sb.n_flatness), f"{what} history sizes"
+
+
+class SimtTwin(_Base):
+    """tests/simt/simt_twin.cpp: the CUDA kernels themselves, executed on the CPU by the fiber-based SIMT stand-in."""
+
+    def __init__(self, params=None, num_streams=1, **options):
+        lib = C.CDLL(os.path.join(HERE, "_build", "libpwpp_simt.so"))
+        self._bind(lib, "simt_")
+        lib.simt_create.argtypes = [C.POINTER(PwppParams), C.c_int]; lib.simt_create.restype = C.c_void_p
+        lib.simt_bin_ids.argtypes = [C.c_void_p, C.c_void_p]
+        lib.simt_bin_results.argtypes = [C.c_void_p, C.c_void_p]
+        lib.simt_num_bins.argtypes = [C.c_void_p]
+        lib.simt_select.argtypes = [C.c_void_p, C.c_int]
+        lib.simt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.simt_queue_sizes.argtypes = [C.c_void_p]; lib.simt_queue_sizes.restype = C.c_char_p
+        lib.simt_estimate_multi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        self._lib = lib
+        self.params = params if params is not None else default_params()
+        self._h = lib.simt_create(C.byref(self.params), num_streams)
+        self.nbins = lib.simt_num_bins(self._h)
+        self._ns = [0] * num_streams
+        for k, v in options.items():
+            assert lib.simt_set_option(self._h, k.encode(), int(v)) == 0, k
+
+    def estimate(self, pts):
+        super().estimate(pts)
+        self._ns[0] = self._n
+
+    def estimate_multi(self, frames):
+        frames = [np.ascontiguousarray(a, dtype=np.float32) for a in frames]
+        cols = frames[0].shape[1]
+        ptrs = (C.c_void_p * len(frames))(*[a.ctypes.data for a in frames])
+        ns = (C.c_int64 * len(frames))(*[a.shape[0] for a in frames])
+        self._lib.simt_estimate_multi(self._h, len(frames), ptrs, ns, cols)
+        self._ns[:len(frames)] = [a.shape[0] for a in frames]
+        self.select(0)
+
+    def select(self, f):
+        self._lib.simt_select(self._h, f)
+        self._n = self._ns[f]
+
+    def queue_sizes(self):
+        return self._lib.simt_queue_sizes(self._h).decode()
+
+    def bin_ids(self):
+        out = np.empty(self._n, dtype=np.uint16)
+        self._lib.simt_bin_ids(self._h, out.ctypes.data)
+        return out
+
+    def bin_results(self):
+        arr = (PwppBinResult * self.nbins)()
+        self._lib.simt_bin_results(self._h, C.byref(arr))
+        return arr

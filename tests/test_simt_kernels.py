@@ -1,0 +1,107 @@
+"""The CUDA kernels themselves, executed on the CPU, vs the oracle (CANON64).
+
+tests/simt/ compiles csrc/pwpp_kernels.cuh + csrc/pwpp_fit.cuh with g++ against a stand-in for <cuda_runtime.h> that
+runs every thread of a CTA as a fiber and implements warp shuffles / ballots / match / reduce and block barriers as
+rendezvous (tests/simt/cuda_runtime.h). The launch sequence is the one of launch_range() in csrc/pwpp_capi.cu.
+This is the GPU parity suite's bar (tests/test_gpu_parity.py) applied to the kernel code in the GPU-less build
+container: bin ids bit-exact, index sets identical, per-patch planes and adaptive state within the CANON64 tolerances.
+It cannot see data races or anything about speed; the `-m gpu` suite on a B200 remains the parity gate."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import SimtTwin, assert_bins_close, assert_sets_equal, assert_state_close
+from param_sets import PARAM_SETS
+
+
+def _check(orc, tw, a, what, allow_degenerate=False):
+    ids = orc.bin_ids()
+    assert np.array_equal(ids, tw.bin_ids()), f"{what}: polar bin ids differ"
+    g_o, ng_o, g_t, ng_t = orc.getGroundIndices(), orc.getNongroundIndices(), tw.getGroundIndices(), tw.getNongroundIndices()
+    assert len(g_o) + len(ng_o) == len(g_t) + len(ng_t), what
+    degenerate = orc.bin_min_fit_n() < 3
+    if allow_degenerate:
+        degenerate |= np.array([orc.bin_results()[b].n < 5 for b in range(orc.nbins)])
+    if not degenerate.any():
+        assert_sets_equal(g_o, ng_o, g_t, ng_t, len(a), what)
+        assert_bins_close(orc.bin_results(), tw.bin_results(), orc.nbins, what)
+        assert_state_close(orc.state(), tw.state(), what)
+        assert np.abs(orc.getCenters().astype(np.float64) - tw.getCenters()).max(initial=0) <= 1e-6
+        assert np.abs(orc.getNormals().astype(np.float64) - tw.getNormals()).max(initial=0) <= 1e-6
+        return 0
+    keep = ~np.r_[degenerate, np.zeros(3, bool)][ids]
+    mo = np.zeros(len(a), bool); mo[g_o] = True
+    mt = np.zeros(len(a), bool); mt[g_t] = True
+    assert np.array_equal(mo[keep], mt[keep]), f"{what}: labels differ outside degenerate patches"
+    return int(degenerate.sum())
+
+
+def test_fixture_sequence_default(kitti):
+    """One stream over the six fixture scans: every kernel incl. the temporal state carried by k_gle."""
+    orc, tw = O.Oracle(arith=O.ARITH_CANON64), SimtTwin()
+    for f, a in enumerate(kitti):
+        orc.estimate(a); tw.estimate(a)
+        assert _check(orc, tw, a, f"seq/{f}") == 0
+        for r in range(4):
+            for w in (0, 1):
+                assert np.allclose(tw.history(r, w), orc.history(r, w), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("pname", ["ros", "no_rvpf_tgr"])
+def test_fixture_other_parameter_sets(kitti, pname):
+    mk, cols = PARAM_SETS[pname]
+    for f in (0, 4):
+        a = kitti[f][:, :cols]
+        orc, tw = O.Oracle(mk(), O.ARITH_CANON64), SimtTwin(mk())
+        orc.estimate(a); tw.estimate(a)
+        _check(orc, tw, a, f"{pname}/{f}", allow_degenerate=True)
+
+
+def test_batched_call_with_mixed_frames(kitti):
+    """Several frames in one launch sequence (frame tables, shared work queues, per-frame state), including an empty
+    frame, a one-point frame and a synthetic frame; more persistent CTAs than there is work for."""
+    import synth
+    frames = [kitti[1], np.zeros((0, 4), np.float32), synth.make_frame(5, 1).numpy(), np.array([[5, 0, -1.7, 0.5]], np.float32), kitti[2][:50000]]
+    tw = SimtTwin(num_streams=len(frames), persistent_ctas=3)
+    tw.estimate_multi(frames)
+    for f, a in enumerate(frames):
+        orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(a)
+        tw.select(f)
+        _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
+
+
+@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0)])
+def test_kernel_variants(kitti, opts):
+    """The A/B variants selectable through PWPP_* switches give the same result as the defaults."""
+    a = kitti[3]
+    orc, tw = O.Oracle(arith=O.ARITH_CANON64), SimtTwin(**opts)
+    orc.estimate(a); tw.estimate(a)
+    assert _check(orc, tw, a, f"variant/{opts}") == 0
+
+
+def test_edge_cases():
+    rng = np.random.default_rng(11)
+    fill = lambda n, y0: [[5 + 0.01 * i, y0 + rng.random() * 0.3, -1.7 + rng.normal(0, 0.01), .5] for i in range(n)]  # noqa: E731
+    cases = {
+        "nine_in_one_bin": np.c_[5 + rng.random(9) * 0.1, rng.random(9) * 0.1, -1.7 + rng.random(9) * 0.01, rng.random(9)].astype(np.float32),
+        "ten_in_one_bin": np.c_[5 + rng.random(10) * 0.1, rng.random(10) * 0.1, -1.7 + rng.random(10) * 0.01, rng.random(10)].astype(np.float32),
+        "all_out_of_range": np.c_[rng.random((50, 2)) * 1.0, rng.random((50, 2))].astype(np.float32),
+        "flat_plane": np.c_[(rng.random((5000, 2)) - 0.5) * 60, np.full(5000, -1.723), rng.random(5000)].astype(np.float32),
+        "one_big_bin_20000": np.c_[5 + rng.random(20000) * 0.5, rng.random(20000) * 0.5, -1.7 + rng.normal(0, 0.02, 20000), rng.random(20000)].astype(np.float32),
+        "one_bin_6000": np.c_[5 + rng.random(6000) * 0.5, rng.random(6000) * 0.5, -1.7 + rng.normal(0, 0.02, 6000), rng.random(6000)].astype(np.float32),
+        "nonfinite": np.array([[5, 1, np.nan, .5], [np.nan, 1, -1.7, .5], [5, np.inf, -1.7, .5], [6, 1, -np.inf, .5], [6, 1, np.inf, .01], [7, 2, -1.7, np.nan]] + fill(30, 1.0), np.float32),
+        "z_equals_flt_min": np.array([[5, 1, np.finfo(np.float32).tiny, .5]] + fill(15, 1.2), np.float32),
+        "rnr_hits": np.array([[4, 0, -3.0, 0.05], [4, 0.1, -3.0, 0.5], [4, 0.2, -2.4, 0.05], [40, 0.2, -3.0, 0.05]] + fill(12, 1.0), np.float32),
+        "chunk_boundary_4097": np.c_[5 + rng.random(4097) * 30, rng.random(4097) * 30 - 15, -1.7 + rng.normal(0, 0.05, 4097), rng.random(4097)].astype(np.float32),
+        "vertical_wall_zone0": np.r_[np.c_[4 + rng.random(3000) * 0.05, rng.random(3000) * 1.5, -1.7 + rng.random(3000) * 2.0, rng.random(3000)],
+                                     np.c_[3 + rng.random(3000) * 6, rng.random(3000) * 1.5, -1.7 + rng.normal(0, 0.02, 3000), rng.random(3000)]].astype(np.float32),
+    }
+    names = list(cases)
+    tw = SimtTwin(num_streams=len(names))
+    tw.estimate_multi([cases[k] for k in names])
+    for f, k in enumerate(names):
+        orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(cases[k])
+        tw.select(f)
+        _check(orc, tw, cases[k], f"edge/{k}", allow_degenerate=True)
+    tw.select(names.index("z_equals_flt_min"))
+    assert len(tw.getGroundIndices()) + len(tw.getNongroundIndices()) == len(cases["z_equals_flt_min"]) - 1   # patchworkpp.cpp:591
