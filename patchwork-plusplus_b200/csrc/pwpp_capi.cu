@@ -79,6 +79,12 @@ struct PinBuf {
 
 }  // namespace
 
+#ifndef PWPP_X_KERNEL_DEFAULT
+#define PWPP_X_KERNEL_DEFAULT 1
+#endif
+#ifndef PWPP_FUSE_SEED_DEFAULT
+#define PWPP_FUSE_SEED_DEFAULT 0
+#endif
 typedef void (*FitKernel)(const float4*, FrameTable, const StreamState*, Geometry, AlgoParams, int, const int*, WorkQueues, int*, BinFit*);
 struct FitLaunch {
   FitKernel fn = nullptr;
@@ -491,6 +497,23 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8>, 0, FIT_THREADS, sm_l3};
     if (env_int("PWPP_L3_NW", 8, 8, 16) == 16) ctx->fit[4] = {k_fit_cta<8192, 4, 2, 16>, 0, 512, sm_l3};
     ctx->fit[5] = {k_fit_stream, 0, 128, 0};
+    // class X (> 8192 points, dense sensors): one CTA per patch streaming from L2 (pwpp_fit_big.cuh); PWPP_X_KERNEL=0 selects
+    // the one-warp-per-patch fallback, PWPP_X_NW / PWPP_X_MINB the CTA shape (A/B switches)
+    const int fuse_seed = env_int("PWPP_FUSE_SEED", PWPP_FUSE_SEED_DEFAULT, 0, 1);
+    if (env_int("PWPP_X_KERNEL", PWPP_X_KERNEL_DEFAULT, 0, 1)) {
+      const int x_nw = env_int("PWPP_X_NW", 16, 8, 32), x_minb = env_int("PWPP_X_MINB", 2, 1, 2);
+      if (x_nw >= 32) ctx->fit[5] = {fuse_seed ? k_fit_big<32, 1, true> : k_fit_big<32, 1, false>, 0, 1024, 0};
+      else if (x_nw >= 16 && x_minb == 1) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 1, true> : k_fit_big<16, 1, false>, 0, 512, 0};
+      else if (x_nw >= 16) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 2, true> : k_fit_big<16, 2, false>, 0, 512, 0};
+      else ctx->fit[5] = {fuse_seed ? k_fit_big<8, 4, true> : k_fit_big<8, 4, false>, 0, 256, 0};
+    }
+    // PWPP_FUSE_SEED: zone-0 patches fit the R-VPF plane and the R-GPF seed plane from one selection + one pass (pwpp_fit.cuh)
+    if (fuse_seed) {
+      ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3, true> : k_fit_warp<true, 1, 1, 2, 2, true>, 0, FITW_WARPS * 32, sm_m};
+      ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4, true> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3, true> : k_fit_warp<false, 2, 2, FITW_U, 2, true>, 0, FITW_WARPS * 32, 0};
+      ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true> : k_fit_cta<4096, 3, 3, 8, true>, 0, FIT_THREADS, sm_l2};
+      ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
+    }
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];
       if (k.smem > 0) CU_TRY_CTX(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k.smem));

@@ -379,7 +379,7 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // cross-warp prefix. The LPR selection is two-level: the num_lpr-th smallest of the 256 per-thread minima bounds
 // the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
 // selected exactly by one warp.
-template <int CAP, int CLS, int MINB, int NW>
+template <int CAP, int CLS, int MINB, int NW, bool FUSE = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -392,7 +392,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
   float* sy = sx + CAP;
   float* sz = sy + CAP;
   __shared__ double s_part[2][NW][9];   // per-warp partial moments, double-buffered by round parity
+  __shared__ double s_parti[FUSE ? 2 : 1][FUSE ? NW : 1][9];   // FUSE: the inner (R-GPF seed) set of a fused round
   __shared__ int s_pcnt[2][NW], s_pchg[2][NW];
+  __shared__ Plane s_plane2;            // FUSE: the R-GPF seed plane of a fused round
+  __shared__ int s_mni, s_taken;
   __shared__ int s_cnt[NW][2];
   __shared__ unsigned s_min[NT];
   __shared__ unsigned s_cand[CCAP];
@@ -463,10 +466,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
 #pragma unroll
     for (int q = 0; q < 6; ++q) tot.s2[q] = 0.0;
 
+    // FUSE: see k_fit_warp — an R-VPF round also accumulates the R-GPF seed set (same LPR height while nothing has been
+    // removed in this round) and warp 0 solves both planes in its two halves; when the R-VPF plane is upright the
+    // separate ST_SEED round (selection, pass, four barriers) is skipped.
+    const bool fuse_ok = FUSE && (ap.th_seeds <= ap.th_seeds_v);
     while (state != ST_DONE) {   // state is uniform across the CTA
       const bool seed_round = (state == ST_RVPF || state == ST_SEED);
+      const bool fused = fuse_ok && state == ST_RVPF;
       double c[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-      double zthr = 0.0;
+      double zthr = 0.0, zin = 0.0;
       if (seed_round) {
         // ---- LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103) ----
         unsigned smask = 0, kmin = 0xffffffffu;
@@ -586,6 +594,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
         }
         const double lpr = s_lpr;
         zthr = lpr + (state == ST_RVPF ? ap.th_seeds_v : ap.th_seeds);
+        zin = lpr + ap.th_seeds;
         c[0] = c0x; c[1] = c0y; c[2] = lpr;
       }
       // ---- predicate + moments ----
@@ -595,14 +604,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       // fixpoint of S:516-543.
       const bool incr = !seed_round;
       if (incr) { c[0] = c0x; c[1] = c0y; c[2] = c_lpr; }
-      else if (state == ST_SEED) c_lpr = c[2];
+      else if (state == ST_SEED || (FUSE && fused)) c_lpr = c[2];
       PlaneF pf;
       pf.n0 = (float) pl.normal[0]; pf.n1 = (float) pl.normal[1]; pf.n2 = (float) pl.normal[2]; pf.d = (float) pl.d;
-      double a[9];
+      double a[9], bi[FUSE ? 9 : 1];
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
-      int mn = 0, nchg = 0;
-      unsigned sel = 0;
+#pragma unroll
+      for (int q = 0; q < (FUSE ? 9 : 1); ++q) bi[q] = 0.0;
+      int mn = 0, nchg = 0, mni = 0;
+      unsigned sel = 0, seli = 0;
       for (int it = 0; it < nit; ++it) {
         if (!((amask >> it) & 1u)) continue;
         const int j = jbase + it * 32;
@@ -627,8 +638,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
         a[0] += wx; a[1] += wy; a[2] += wz;
         a[3] += wx * dx; a[4] += wx * dy; a[5] += wx * dz; a[6] += wy * dy; a[7] += wy * dz; a[8] += wz * dz;
         mn += in ? 1 : -1;
+        if (FUSE && fused && ((double) z < zin)) {   // also a seed of the R-GPF seed fit (in is true here)
+          seli |= 1u << it;
+          bi[0] += dx; bi[1] += dy; bi[2] += dz;
+          bi[3] += dx * dx; bi[4] += dx * dy; bi[5] += dx * dz; bi[6] += dy * dy; bi[7] += dy * dz; bi[8] += dz * dz;
+          ++mni;
+        }
       }
-      member = sel;
+      member = (FUSE && fused) ? seli : sel;   // a fused round that is not taken recomputes everything in the next round
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
 #pragma unroll
@@ -638,6 +655,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       nchg = __reduce_add_sync(0xffffffffu, nchg);
       const int buf = round & 1;
       ++round;
+      if (FUSE && fused) {
+#pragma unroll
+        for (int q = 0; q < (FUSE ? 9 : 1); ++q) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) bi[q] += __shfl_xor_sync(0xffffffffu, bi[q], o);
+        }
+        mni = __reduce_add_sync(0xffffffffu, mni);
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < (FUSE ? 9 : 1); ++q) s_parti[FUSE ? buf : 0][FUSE ? w : 0][q] = bi[q];
+          s_cnt[w][1] = mni;
+        }
+      }
       if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) s_part[buf][w][q] = a[q];
@@ -648,6 +678,40 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       // warp 0 combines the NW partials (lane q sums quantity q over the warps in a fixed order: bit-reproducible),
       // keeps the running sums of the R-GPF phase, solves the 3x3 problem once and publishes the plane; the other
       // warps wait at the second barrier
+      if (FUSE && fused) {
+        if (w == 0) {
+          // lanes 0..8 / 16..24 combine the moments of all seeds / the inner seeds; lanes 9 / 25 the counts
+          double v = 0.0;
+          int cn = 0;
+          const int ql = lane & 15;
+          const bool hi = lane >= 16;
+          if (ql < 9) {
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) v += hi ? s_parti[FUSE ? buf : 0][FUSE ? ww : 0][ql] : s_part[buf][ww][ql];
+          } else if (ql == 9) {
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) cn += hi ? s_cnt[ww][1] : s_pcnt[buf][ww];
+          }
+          Moments mv, mi;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) { mv.s1[q] = __shfl_sync(0xffffffffu, v, q); mi.s1[q] = __shfl_sync(0xffffffffu, v, 16 + q); }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { mv.s2[q] = __shfl_sync(0xffffffffu, v, 3 + q); mi.s2[q] = __shfl_sync(0xffffffffu, v, 19 + q); }
+          mv.n = __shfl_sync(0xffffffffu, cn, 9);
+          mi.n = __shfl_sync(0xffffffffu, cn, 25);
+          Moments ms = hi ? mi : mv;
+          Plane mine = pl;
+          if (ms.n > 0) plane_from_moments(ms, c, mine);
+          const double vz = __shfl_sync(0xffffffffu, mine.normal[2], 0);
+          const bool hv = have_plane || mv.n > 0;
+          const bool taken = !(hv && (mv.n > 0 ? vz : pl.normal[2]) < ap.uprightness_thr);   // S:489 false -> S:506 break
+          if (taken) tot = mi; else tot = mv;
+          if (lane == 0) { s_plane = mine; s_mn = mv.n; s_refit = mv.n > 0 ? 1 : 0; s_fix = 0; s_taken = taken ? 1 : 0; }
+          if (lane == 16) { s_plane2 = mine; s_mni = mi.n; }
+        } else if (w == LOOK_W && rvpf_it == 0) {
+          if (nxt.x >= 0) prefetch_patch_l2(sorted + work_item_start(nxt), nxt.y, lane, 32);
+        }
+      } else
       if (w == 0) {
         double v = 0.0;
         int cn = 0;
@@ -689,10 +753,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
         if (nxt.x >= 0) prefetch_patch_l2(sorted + work_item_start(nxt), nxt.y, lane, 32);
       }
       __syncthreads();
-      const int tot_n = s_mn;
+      int tot_n = s_mn;
       const bool fixpoint = s_fix != 0;
       if (s_refit) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
       // ---- state transition (same machine as k_fit_resident) ----
+      if (FUSE && fused && s_taken) {   // upright R-VPF plane (S:506 break) + the seed fit of S:513-514 from the same pass
+        tot_n = s_mni;
+        if (tot_n > 0) { pl = s_plane2; have_plane = true; }
+        state = (ap.num_iter > 1) ? ST_GPF : ST_FINAL;
+        gpf_it = 0;
+      } else
       if (state == ST_RVPF) {
         if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489
           for (int it = 0; it < nit; ++it) {
@@ -1012,7 +1082,7 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB>
+template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false>
 __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -1088,11 +1158,20 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
     //      followed by the R-GPF seed fit (S:484-514). Each is a selection pass + a full accumulation pass. ----
     Moments tot;   // running sums of the current member set (valid after the last seed round)
     int rvpf_left = (ap.enable_RVPF && zone0) ? ap.num_iter : 0;
+    // FUSE: an R-VPF round that removes nothing is followed by the R-GPF seed fit over the SAME alive set with the
+    // same margin, hence the same LPR height (S:84-103 depend on nothing else); its seed set {z < lpr + th_seeds} is a
+    // subset of the R-VPF seed set {z < lpr + th_seeds_v} when th_seeds <= th_seeds_v. Such a round therefore
+    // accumulates both sets in one pass (same summation order as two passes: bit-identical moments), solves the two
+    // planes side by side in the two halves of the warp, and skips the second selection + pass when the R-VPF plane
+    // turns out upright (the common case).
+    const bool fuse_ok = FUSE && (ap.th_seeds <= ap.th_seeds_v);
     for (;;) {
       const bool rvpf_round = rvpf_left > 0;
+      const bool fused = fuse_ok && rvpf_round;
       // LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103)
       const double lpr = warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
       const double zthr = lpr + (rvpf_round ? ap.th_seeds_v : ap.th_seeds);
+      const double zin = lpr + ap.th_seeds;   // inner (R-GPF seed) threshold of a fused round
       c[2] = lpr;
       if (!looked_ahead) {   // the claim issued at the top has returned by now: fetch the next patch's descriptor
         const int t_next = __shfl_sync(0xffffffffu, next_raw, 0);
@@ -1100,12 +1179,12 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
         looked_ahead = true;
       }
       // full accumulation over {alive, z < lpr + th}; the ballots become the member set
-      Moments m;
-      m.n = 0;
+      Moments m, mi;   // mi: the inner set of a fused round
+      m.n = 0; mi.n = 0;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) m.s1[q] = 0.0;
+      for (int q = 0; q < 3; ++q) { m.s1[q] = 0.0; mi.s1[q] = 0.0; }
 #pragma unroll
-      for (int q = 0; q < 6; ++q) m.s2[q] = 0.0;
+      for (int q = 0; q < 6; ++q) { m.s2[q] = 0.0; mi.s2[q] = 0.0; }
       for (int it = 0; it < nit; it += U) {
         float4 q[U];
 #pragma unroll
@@ -1117,7 +1196,10 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
           bool in = (j < n) && ((double) p.z < zthr);                                     // S:108 / S:145
           if (any_removed && it + u < nit) in = in && ((alive_w[it + u] >> lane) & 1u);
           const unsigned bal = __ballot_sync(0xffffffffu, in);
-          if (lane == 0 && it + u < nit) member_w[it + u] = bal;
+          unsigned bal_in = bal;   // what becomes the member set: the inner set in a fused round
+          bool inner = in;
+          if (FUSE && fused) { inner = in && ((double) p.z < zin); bal_in = __ballot_sync(0xffffffffu, inner); }
+          if (lane == 0 && it + u < nit) member_w[it + u] = bal_in;
           if (bal) {
             const double w = in ? 1.0 : 0.0;   // unselected lanes add exact zeros
             const double dx = ((double) p.x - c[0]) * w, dy = ((double) p.y - c[1]) * w, dz = ((double) p.z - c[2]) * w;
@@ -1125,6 +1207,14 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
             m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
             m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
             m.n += in ? 1 : 0;
+            if (FUSE && fused && bal_in) {
+              const double wi = inner ? 1.0 : 0.0;
+              const double ex = dx * wi, ey = dy * wi, ez = dz * wi;
+              mi.s1[0] += ex; mi.s1[1] += ey; mi.s1[2] += ez;
+              mi.s2[0] += ex * ex; mi.s2[1] += ex * ey; mi.s2[2] += ex * ez;
+              mi.s2[3] += ey * ey; mi.s2[4] += ey * ez; mi.s2[5] += ez * ez;
+              mi.n += inner ? 1 : 0;
+            }
           }
         }
       }
@@ -1133,9 +1223,40 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
 #pragma unroll
       for (int q = 0; q < 6; ++q) m.s2[q] = warp_sum(m.s2[q]);
       m.n = warp_sum_i(m.n);
-      if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
-      tot = m;
-      if (!rvpf_round) break;
+      if (FUSE && fused) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mi.s1[q] = warp_sum(mi.s1[q]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) mi.s2[q] = warp_sum(mi.s2[q]);
+        mi.n = warp_sum_i(mi.n);
+        // lanes 0..15 solve the R-VPF plane (all seeds), lanes 16..31 the R-GPF seed plane (inner seeds)
+        const bool hi = lane >= 16;
+        Moments ms;
+        ms.n = hi ? mi.n : m.n;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ms.s1[q] = hi ? mi.s1[q] : m.s1[q];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ms.s2[q] = hi ? mi.s2[q] : m.s2[q];
+        Plane mine = pl;
+        if (ms.n > 0) plane_from_moments(ms, c, mine);
+        auto bcast = [&](int src) {
+          Plane t;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) { t.mean[q] = __shfl_sync(0xffffffffu, mine.mean[q], src); t.normal[q] = __shfl_sync(0xffffffffu, mine.normal[q], src); t.sv[q] = __shfl_sync(0xffffffffu, mine.sv[q], src); }
+          t.d = __shfl_sync(0xffffffffu, mine.d, src);
+          return t;
+        };
+        if (m.n > 0) { pl = bcast(0); have_plane = true; }     // the R-VPF fit (S:486); S:49 keeps the previous plane otherwise
+        if (!(have_plane && pl.normal[2] < ap.uprightness_thr)) {   // S:506 break: nothing removed, the seed fit follows
+          if (mi.n > 0) { pl = bcast(16); have_plane = true; }  // S:513-514 on the same alive set
+          tot = mi;
+          break;
+        }
+      } else {
+        if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
+        tot = m;
+        if (!rvpf_round) break;
+      }
       if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489: remove the vertical structure, iterate
         for (int it = 0; it < nit; ++it) {
           const int j = it * 32 + lane;

@@ -22,6 +22,7 @@
 
 #include "pwpp_common.cuh"
 #include "pwpp_fit.cuh"
+#include "pwpp_fit_big.cuh"
 
 namespace pwpp {
 

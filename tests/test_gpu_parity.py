@@ -161,6 +161,11 @@ def test_edge_cases():
         "flat_plane": np.c_[(rng.random((5000, 2)) - 0.5) * 60, np.full(5000, -1.723), rng.random(5000)].astype(np.float32),
         "axis_points": np.array([[10, 0, -1.7, .5], [-10, 0, -1.7, .5], [0, 10, -1.7, .5], [0, -10, -1.7, .5], [3, -0.0, -1.7, .5]] * 4, np.float32),
         "one_big_bin_20000": big_bin,
+        # class X selections with more ties than the candidate buffer holds (CTA-wide bisection path of k_fit_big)
+        "flat_big_bin_9000": np.c_[5 + rng.random(9000) * 0.5, rng.random(9000) * 0.5, np.full(9000, -1.723), rng.random(9000)].astype(np.float32),
+        "two_level_big_bin_9000": np.c_[5 + rng.random(9000) * 0.5, rng.random(9000) * 0.5, np.where(rng.random(9000) < 0.6, -1.75, -1.70), rng.random(9000)].astype(np.float32),
+        "wall_in_big_zone0_bin": np.r_[np.c_[4 + rng.random(6000) * 0.05, rng.random(6000) * 0.6, -1.7 + rng.random(6000) * 2.0, rng.random(6000)],
+                                       np.c_[3 + rng.random(6000) * 4, rng.random(6000) * 0.6, -1.7 + rng.normal(0, 0.02, 6000), rng.random(6000)]].astype(np.float32),
         "nonfinite": nonfinite,
         "z_equals_flt_min": tomb,
         "rnr_hits": rnr,

@@ -70,13 +70,59 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0)])
+@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=1)])
 def test_kernel_variants(kitti, opts):
     """The A/B variants selectable through PWPP_* switches give the same result as the defaults."""
     a = kitti[3]
     orc, tw = O.Oracle(arith=O.ARITH_CANON64), SimtTwin(**opts)
     orc.estimate(a); tw.estimate(a)
     assert _check(orc, tw, a, f"variant/{opts}") == 0
+
+
+def test_fused_seed_rounds_are_bit_identical(kitti):
+    """PWPP_FUSE_SEED: the R-VPF and the R-GPF seed plane of a zone-0 patch from one selection and one pass. The fused
+    rounds accumulate in the same order as the two separate passes, so every patch record is bit-identical."""
+    for f in (1, 5):
+        a, b = SimtTwin(), SimtTwin(fuse_seed=1)
+        a.estimate(kitti[f]); b.estimate(kitti[f])
+        assert bytes(a.bin_results()) == bytes(b.bin_results())
+        assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and np.array_equal(a.getNongroundIndices(), b.getNongroundIndices())
+
+
+def _big_patch_cases():
+    rng = np.random.default_rng(3)
+    two_level = np.c_[5 + rng.random(9000) * 0.5, rng.random(9000) * 0.5, np.where(rng.random(9000) < 0.6, -1.75, -1.70), rng.random(9000)]
+    return {
+        "big_bin_20000": np.c_[5 + rng.random(20000) * 0.5, rng.random(20000) * 0.5, -1.7 + rng.normal(0, 0.02, 20000), rng.random(20000)].astype(np.float32),
+        "flat_9000": np.c_[5 + rng.random(9000) * 0.5, rng.random(9000) * 0.5, np.full(9000, -1.723), rng.random(9000)].astype(np.float32),
+        "two_level_9000": two_level.astype(np.float32),
+        "wall_zone0_12000": np.r_[np.c_[4 + rng.random(6000) * 0.05, rng.random(6000) * 0.6, -1.7 + rng.random(6000) * 2.0, rng.random(6000)],
+                                  np.c_[3 + rng.random(6000) * 4, rng.random(6000) * 0.6, -1.7 + rng.normal(0, 0.02, 6000), rng.random(6000)]].astype(np.float32),
+        "zone2_10000": np.c_[30 + rng.random(10000) * 2, rng.random(10000) * 2, -1.7 + rng.normal(0, 0.03, 10000), rng.random(10000)].astype(np.float32),
+    }
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(fuse_seed=1), dict(x_nw=8, fuse_seed=1), dict(x_nw=32), dict(x_kernel=0)])
+def test_big_patches(opts):
+    """Class X (more than 8192 points in one patch): k_fit_big in its CTA shapes and the one-warp fallback, including
+    the tie-heavy selections that overflow the candidate buffer and an R-VPF wall removal in zone 0."""
+    cases = _big_patch_cases()
+    names = list(cases)
+    tw = SimtTwin(num_streams=len(names), **opts)
+    tw.estimate_multi([cases[k] for k in names])
+    for f, k in enumerate(names):
+        orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(cases[k])
+        tw.select(f)
+        assert _check(orc, tw, cases[k], f"big/{k}/{opts}") == 0
+
+
+def test_dense_frame():
+    """BASELINE config-5 shape: one ~1.4M-point frame (27 class-X patches) through every kernel."""
+    import synth
+    a = synth.make_frame(5, 0, "dense1m").numpy()
+    orc, tw = O.Oracle(arith=O.ARITH_CANON64), SimtTwin(fuse_seed=1)
+    orc.estimate(a); tw.estimate(a)
+    _check(orc, tw, a, "dense1m", allow_degenerate=True)
 
 
 def test_edge_cases():
