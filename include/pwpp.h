@@ -216,6 +216,15 @@ int64_t pwpp_launch_count(const pwpp_ctx* ctx);
 int pwpp_get_state(pwpp_ctx* ctx, int f, pwpp_state* out);
 /* Histories: ring r of update_elevation_ / update_flatness_ (H:174-175); dst holds n_* doubles. */
 int pwpp_copy_history(pwpp_ctx* ctx, int f, int ring, int which /*0=elevation,1=flatness*/, double* dst);
+/* Checkpoint / migration of one stream: the COMPLETE temporal state the reference object carries from
+ * frame to frame — adaptive sensor height and thresholds (S:347-350, S:368), both history arrays (H:174-175) and the
+ * plane members left by the last estimate_plane call (S:49 keeps them when a patch's seed set is empty) — as one
+ * opaque blob. A blob exported from stream f of one ctx can be imported into any stream of any ctx created with the
+ * same parameters (another GPU, another process, a later run): the next frame then gives bit-identical results.
+ * pwpp_export_state synchronizes with the last estimate call; pwpp_import_state takes effect before the next one. */
+size_t pwpp_state_blob_size(const pwpp_ctx* ctx);
+int pwpp_export_state(pwpp_ctx* ctx, int f, void* blob /* [pwpp_state_blob_size] */);
+int pwpp_import_state(pwpp_ctx* ctx, int f, const void* blob, size_t bytes);
 /* Re-initialises stream f / all streams to the constructor state (a fresh PatchWorkpp instance).
  * Stream-ordered: enqueued behind the last estimate call, no host synchronization. */
 int pwpp_reset_stream(pwpp_ctx* ctx, int f);

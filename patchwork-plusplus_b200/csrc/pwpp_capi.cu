@@ -13,6 +13,7 @@
 
 #include "pwpp.h"
 #include "pwpp_kernels.cuh"
+#include "pwpp_tuning.h"
 #include "pwpp_host.hpp"
 
 using namespace pwpp;
@@ -79,12 +80,6 @@ struct PinBuf {
 
 }  // namespace
 
-#ifndef PWPP_X_KERNEL_DEFAULT
-#define PWPP_X_KERNEL_DEFAULT 1
-#endif
-#ifndef PWPP_FUSE_SEED_DEFAULT
-#define PWPP_FUSE_SEED_DEFAULT 0
-#endif
 typedef void (*FitKernel)(const float4*, FrameTable, const StreamState*, Geometry, AlgoParams, int, const int*, WorkQueues, int*, BinFit*);
 struct FitLaunch {
   FitKernel fn = nullptr;
@@ -441,8 +436,8 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->device = device;
   ctx->num_streams = num_streams;
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
-  ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", 2, 0, 2);
-  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", 0, 0, 1);
+  ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", PWPP_HIST_PIPE_DEFAULT, 0, 2);
+  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", PWPP_SCATTER_V_DEFAULT, 0, 1);
   ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
@@ -486,22 +481,22 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
     // Fit kernel of every class. The *_MINB switches pick the launch-bounds variant (CTAs per SM the register
     // allocation is sized for): these kernels are latency-bound, so more resident warps can pay for a few spills.
-    const int s_minb = env_int("PWPP_S_MINB", 2, 2, 4), m_minb = env_int("PWPP_M_MINB", 2, 2, 3);
-    const int l1_minb = env_int("PWPP_L1_MINB", 2, 2, 4), l2_minb = env_int("PWPP_L2_MINB", 4, 3, 4);   // measured: 4 CTAs/SM on the 4096 class: 1.31 -> 1.23 ms
+    const int s_minb = env_int("PWPP_S_MINB", PWPP_S_MINB_DEFAULT, 2, 4), m_minb = env_int("PWPP_M_MINB", PWPP_M_MINB_DEFAULT, 2, 3);
+    const int l1_minb = env_int("PWPP_L1_MINB", PWPP_L1_MINB_DEFAULT, 2, 4), l2_minb = env_int("PWPP_L2_MINB", PWPP_L2_MINB_DEFAULT, 3, 4);   // measured: 4 CTAs/SM on the 4096 class: 1.31 -> 1.23 ms
     const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
     ctx->fit[0] = {s_minb == 4 ? k_fit_resident<8, 8, 0, 4> : s_minb == 3 ? k_fit_resident<8, 8, 0, 3> : k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
     ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3> : k_fit_warp<true, 1, 1, 2, 2>, 0, FITW_WARPS * 32, sm_m};
     ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3> : k_fit_warp<false, 2, 2, FITW_U, 2>, 0, FITW_WARPS * 32, 0};
     ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8> : k_fit_cta<4096, 3, 3, 8>, 0, FIT_THREADS, sm_l2};
-    if (env_int("PWPP_L2_NW", 8, 8, 16) == 16) ctx->fit[3] = {k_fit_cta<4096, 3, 2, 16>, 0, 512, sm_l2};
+    if (env_int("PWPP_L2_NW", PWPP_L2_NW_DEFAULT, 8, 16) == 16) ctx->fit[3] = {k_fit_cta<4096, 3, 2, 16>, 0, 512, sm_l2};
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8>, 0, FIT_THREADS, sm_l3};
-    if (env_int("PWPP_L3_NW", 8, 8, 16) == 16) ctx->fit[4] = {k_fit_cta<8192, 4, 2, 16>, 0, 512, sm_l3};
+    if (env_int("PWPP_L3_NW", PWPP_L3_NW_DEFAULT, 8, 16) == 16) ctx->fit[4] = {k_fit_cta<8192, 4, 2, 16>, 0, 512, sm_l3};
     ctx->fit[5] = {k_fit_stream, 0, 128, 0};
     // class X (> 8192 points, dense sensors): one CTA per patch streaming from L2 (pwpp_fit_big.cuh); PWPP_X_KERNEL=0 selects
     // the one-warp-per-patch fallback, PWPP_X_NW / PWPP_X_MINB the CTA shape (A/B switches)
     const int fuse_seed = env_int("PWPP_FUSE_SEED", PWPP_FUSE_SEED_DEFAULT, 0, 1);
     if (env_int("PWPP_X_KERNEL", PWPP_X_KERNEL_DEFAULT, 0, 1)) {
-      const int x_nw = env_int("PWPP_X_NW", 16, 8, 32), x_minb = env_int("PWPP_X_MINB", 2, 1, 2);
+      const int x_nw = env_int("PWPP_X_NW", PWPP_X_NW_DEFAULT, 8, 32), x_minb = env_int("PWPP_X_MINB", PWPP_X_MINB_DEFAULT, 1, 2);
       if (x_nw >= 32) ctx->fit[5] = {fuse_seed ? k_fit_big<32, 1, true> : k_fit_big<32, 1, false>, 0, 1024, 0};
       else if (x_nw >= 16 && x_minb == 1) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 1, true> : k_fit_big<16, 1, false>, 0, 512, 0};
       else if (x_nw >= 16) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 2, true> : k_fit_big<16, 2, false>, 0, 512, 0};
@@ -828,6 +823,46 @@ int pwpp_copy_history(pwpp_ctx* ctx, int f, int ring, int which, double* dst) {
   if (rc) return rc;
   const int n = which ? s.n_flatness[ring] : s.n_elevation[ring];
   if (n > 0) CU_TRY(cudaMemcpy(dst, ctx->d_hist.p + (((size_t) f * 2 + which) * 4 + ring) * ctx->hcap, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost));
+  return PWPP_OK;
+}
+
+namespace {
+struct StateBlobHeader { uint32_t magic, version; int32_t hcap, state_bytes; };
+constexpr uint32_t STATE_BLOB_MAGIC = 0x50575354u;  // "PWST"
+}  // namespace
+size_t pwpp_state_blob_size(const pwpp_ctx* ctx) {
+  return ctx ? sizeof(StateBlobHeader) + sizeof(StreamState) + (size_t) 2 * 4 * ctx->hcap * sizeof(double) : 0;
+}
+int pwpp_export_state(pwpp_ctx* ctx, int f, void* blob) {
+  if (!ctx || !blob || f < 0 || f >= ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "bad argument");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  if (ctx->last_stream) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  char* b = static_cast<char*>(blob);
+  const StateBlobHeader h{STATE_BLOB_MAGIC, (uint32_t) PWPP_ABI_VERSION, ctx->hcap, (int32_t) sizeof(StreamState)};
+  std::memcpy(b, &h, sizeof h);
+  CU_TRY(cudaMemcpy(b + sizeof h, ctx->d_states.p + f, sizeof(StreamState), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(b + sizeof h + sizeof(StreamState), ctx->d_hist.p + (size_t) f * 2 * 4 * ctx->hcap, (size_t) 2 * 4 * ctx->hcap * sizeof(double),
+                    cudaMemcpyDeviceToHost));
+  return PWPP_OK;
+}
+int pwpp_import_state(pwpp_ctx* ctx, int f, const void* blob, size_t bytes) {
+  if (!ctx || !blob || f < 0 || f >= ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "bad argument");
+  if (bytes != pwpp_state_blob_size(ctx)) return fail(PWPP_ERR_INVALID_ARG, "state blob has the wrong size for this context (different storage parameters?)");
+  const char* b = static_cast<const char*>(blob);
+  StateBlobHeader h;
+  std::memcpy(&h, b, sizeof h);
+  if (h.magic != STATE_BLOB_MAGIC || h.version != (uint32_t) PWPP_ABI_VERSION || h.hcap != ctx->hcap || h.state_bytes != (int32_t) sizeof(StreamState))
+    return fail(PWPP_ERR_INVALID_ARG, "not a state blob of this library version / parameter set");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  // after everything already enqueued (a synchronous copy from pageable memory: the blob may be freed on return)
+  if (ctx->last_stream) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaMemcpy(ctx->d_states.p + f, b + sizeof h, sizeof(StreamState), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(ctx->d_hist.p + (size_t) f * 2 * 4 * ctx->hcap, b + sizeof h + sizeof(StreamState), (size_t) 2 * 4 * ctx->hcap * sizeof(double),
+                    cudaMemcpyHostToDevice));
   return PWPP_OK;
 }
 

@@ -46,6 +46,9 @@ def load_library():
     lib.pwpp_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]; lib.pwpp_device_results.restype = i32
     lib.pwpp_get_state.argtypes = [vp, i32, C.POINTER(PwppState)]; lib.pwpp_get_state.restype = i32
     lib.pwpp_copy_history.argtypes = [vp, i32, i32, i32, vp]; lib.pwpp_copy_history.restype = i32
+    lib.pwpp_state_blob_size.argtypes = [vp]; lib.pwpp_state_blob_size.restype = C.c_size_t
+    lib.pwpp_export_state.argtypes = [vp, i32, vp]; lib.pwpp_export_state.restype = i32
+    lib.pwpp_import_state.argtypes = [vp, i32, vp, C.c_size_t]; lib.pwpp_import_state.restype = i32
     lib.pwpp_reset_stream.argtypes = [vp, i32]; lib.pwpp_reset_stream.restype = i32
     lib.pwpp_reset_all.argtypes = [vp]; lib.pwpp_reset_all.restype = i32
     lib.pwpp_host_alloc.argtypes = [C.c_size_t]; lib.pwpp_host_alloc.restype = vp
@@ -179,6 +182,30 @@ class Engine:
         out = np.empty(n, dtype=np.float64)
         _check(self.lib.pwpp_copy_history(self._h, f, ring, which, out.ctypes.data))
         return out
+
+    def export_state(self, f=0) -> bytes:
+        """Complete temporal state of stream f as an opaque blob (checkpoint / migration to another ctx or GPU)."""
+        buf = C.create_string_buffer(self.lib.pwpp_state_blob_size(self._h))
+        _check(self.lib.pwpp_export_state(self._h, f, buf))
+        return buf.raw
+
+    def import_state(self, f, blob: bytes):
+        _check(self.lib.pwpp_import_state(self._h, f, blob, len(blob)))
+
+    def device_index_lists(self):
+        """Zero-copy view of the last call's results on the device: (indices, num_ground) as torch int32 CUDA tensors.
+        indices is laid out like the input (frame f's region starts at its point offset): ground list, then non-ground
+        list. Valid until the next estimate call; the caller synchronizes with its stream (or Engine.synchronize())."""
+        import torch
+        d_idx, d_ng = self.device_results()
+        total, nf = int(sum(self._n)), len(self._n)
+
+        class _View:   # __cuda_array_interface__ v3: torch.as_tensor wraps the memory without copying
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 3, "strides": None}
+        idx = torch.as_tensor(_View(d_idx, total), device="cuda") if total > 0 else torch.empty(0, dtype=torch.int32, device="cuda")
+        ng = torch.as_tensor(_View(d_ng, nf), device="cuda")
+        return idx, ng
 
     def device_results(self):
         a, b = C.c_void_p(), C.c_void_p()

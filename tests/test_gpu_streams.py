@@ -1,0 +1,59 @@
+"""Stream-level features next to the hot path: state checkpoint / migration and zero-copy device results.
+Runs after tests/test_gpu_parity.py (the parity gate) in the same `-m gpu` session."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(num_streams=1):
+    import pwpp_b200
+    return pwpp_b200.Engine(device=0, num_streams=num_streams)
+
+
+def test_state_export_import_migrates_a_stream(kitti):
+    """Frames 0..2 on ctx A; the stream's blob is imported into stream 1 of a fresh ctx B; frame 3 on both gives
+    bit-identical index lists, patch records, adaptive state and histories (a migrated sensor stream continues exactly)."""
+    a = _engine()
+    for f in range(3):
+        a.estimate_host([kitti[f]])
+    blob = a.export_state(0)
+    b = _engine(num_streams=2)
+    b.import_state(1, blob)
+    a.estimate_host([kitti[3]])
+    b.estimate_host([kitti[5], kitti[3]])    # stream 0 of B is an unrelated fresh stream
+    assert np.array_equal(a.ground_indices(0), b.ground_indices(1)) and np.array_equal(a.nonground_indices(0), b.nonground_indices(1))
+    assert bytes(a.bin_results(0)) == bytes(b.bin_results(1))
+    sa, sb = a.state(0), b.state(1)
+    assert bytes(sa) == bytes(sb)
+    for r in range(4):
+        for w in (0, 1):
+            assert np.array_equal(a.history(0, r, w), b.history(1, r, w))
+    # and the fresh neighbour stream was not disturbed
+    c = _engine(); c.estimate_host([kitti[5]])
+    assert np.array_equal(c.ground_indices(0), b.ground_indices(0))
+    # the exported state differs from a fresh one (the test would be vacuous otherwise) and a wrong-size blob is refused
+    assert blob != _engine().export_state(0)
+    import pwpp_b200
+    with pytest.raises(pwpp_b200.PwppError):
+        b.import_state(0, blob[:-8])
+    with pytest.raises(pwpp_b200.PwppError):
+        b.import_state(0, b"\0" * len(blob))
+
+
+def test_device_index_lists_are_the_host_getters(kitti):
+    """pwpp_device_results through __cuda_array_interface__: the device-side lists equal what the copy_* getters return."""
+    import torch
+    frames = [kitti[0], kitti[1][:30000], np.zeros((0, 4), np.float32), kitti[2]]
+    eng = _engine(num_streams=len(frames))
+    eng.estimate_host(frames)
+    eng.synchronize()
+    idx, ng = eng.device_index_lists()
+    assert idx.is_cuda and idx.dtype == torch.int32 and ng.dtype == torch.int32
+    idx, ng = idx.cpu().numpy(), ng.cpu().numpy()
+    offs = np.cumsum([0] + [len(f) for f in frames])
+    for f in range(len(frames)):
+        g, n = eng.ground_indices(f), eng.nonground_indices(f)
+        assert ng[f] == len(g)
+        assert np.array_equal(idx[offs[f]:offs[f] + len(g)], g)
+        assert np.array_equal(idx[offs[f] + len(g):offs[f] + len(g) + len(n)], n)

@@ -11,6 +11,7 @@ t0=$SECONDS; timeout 110 python tools/gpu_tune.py 1024 5 32 > gpurun_out/tune.lo
 [ -f gpurun_out/chosen.env ] && source gpurun_out/chosen.env
 env | grep '^PWPP_' | sort > gpurun_out/chosen_effective.txt
 t0=$SECONDS; timeout 150 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; leg pytest $?
+t0=$SECONDS; timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; leg smoke $?
 t0=$SECONDS; timeout 100 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; leg bench $?
 t0=$SECONDS; timeout 60 python bench.py --sensor dense1m --frames-per-gpu 32 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_dense1m.json 2> gpurun_out/bench_dense1m.err; leg dense $?
 t0=$SECONDS; timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 33 -c 11 --csv --log-file gpurun_out/launches_1024frames.csv \
