@@ -17,7 +17,10 @@ t0=$SECONDS; timeout 60 python bench.py --sensor dense1m --frames-per-gpu 32 --s
 t0=$SECONDS; timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 33 -c 11 --csv --log-file gpurun_out/launches_1024frames.csv \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; leg ncu-launches $?
 CMD="python bench.py --frames-per-gpu 128 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-t0=$SECONDS; timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_ -s 33 -c 11 -f -o gpurun_out/full128 $CMD > gpurun_out/ncu_full.log 2>&1; leg ncu-full $?
+# the capture gets what is left of the session's time budget (DEADLINE seconds after start, default 250), minus the export
+left=$(( ${DEADLINE:-250} - SECONDS - 35 ))
+t0=$SECONDS
+if [ $left -gt 30 ]; then timeout $left ncu --set full --clock-control none --import-source on -k regex:k_ -s 33 -c 11 -f -o gpurun_out/full128 $CMD > gpurun_out/ncu_full.log 2>&1; leg ncu-full $?; else echo "ncu-full skipped (no time left)" | tee -a gpurun_out/legs.txt; fi
 if [ -f gpurun_out/full128.ncu-rep ]; then
   t0=$SECONDS
   timeout 60 ncu -i gpurun_out/full128.ncu-rep --page raw --csv > gpurun_out/full128_raw.csv 2> /dev/null
