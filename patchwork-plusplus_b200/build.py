@@ -56,9 +56,22 @@ def build_pybind(force=False):
     return out
 
 
+def build_examples(force=False):
+    """examples/pwpp_sequence.cpp -> lib/pwpp_sequence (the demo_sequential equivalent: directory of KITTI scans, one stream)."""
+    src = os.path.join(REPO, "examples", "pwpp_sequence.cpp")
+    hdr = os.path.join(REPO, "include", "patchwork", "patchworkpp.h")
+    out = os.path.join(LIB, "pwpp_sequence")
+    core = build_core()
+    if force or _newer(out, [src, hdr, core]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"), src, "-o", out,
+                               "-L" + LIB, "-lpwpp_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return out
+
+
 def build_all(force=False):
     build_core(force)
     build_pybind(force)
+    build_examples(force)
 
 
 if __name__ == "__main__":
