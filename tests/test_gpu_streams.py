@@ -57,3 +57,27 @@ def test_device_index_lists_are_the_host_getters(kitti):
         assert ng[f] == len(g)
         assert np.array_equal(idx[offs[f]:offs[f] + len(g)], g)
         assert np.array_equal(idx[offs[f] + len(g):offs[f] + len(g) + len(n)], n)
+
+
+def test_sequence_runner_matches_the_engine(tmp_path, kitti):
+    """examples/pwpp_sequence.cpp (double-buffered page-locked reader -> PatchWorkpp drop-in class) over three scans twice:
+    per-frame counts and adaptive sensor height equal a stream fed the same frames through the C-ABI."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(os.path.dirname(here), "patchwork-plusplus_b200", "lib", "pwpp_sequence")
+    if not os.path.exists(exe):
+        import build as pw_build
+        pw_build.build_examples()
+    for f in range(3):
+        np.ascontiguousarray(kitti[f]).tofile(tmp_path / f"{f:06d}.bin")
+    out = subprocess.run([exe, str(tmp_path), "--repeat", "2"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.splitlines() if l.startswith("0000")]
+    assert len(lines) == 6
+    eng = _engine()
+    for t, tok in enumerate(lines):
+        eng.estimate_host([kitti[t % 3]])
+        assert int(tok[2]) == len(kitti[t % 3])
+        assert int(tok[4]) == eng.num_ground(0) and int(tok[6]) == eng.num_nonground(0) and int(tok[8]) == eng.num_patches(0)
+        assert abs(float(tok[10]) - eng.height(0)) < 1e-4
