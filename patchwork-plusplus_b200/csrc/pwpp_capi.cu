@@ -494,7 +494,12 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     ctx->fit[5] = {k_fit_stream, 0, 128, 0};
     // class X (> 8192 points, dense sensors): one CTA per patch streaming from L2 (pwpp_fit_big.cuh); PWPP_X_KERNEL=0 selects
     // the one-warp-per-patch fallback, PWPP_X_NW / PWPP_X_MINB the CTA shape (A/B switches)
-    const int fuse_seed = env_int("PWPP_FUSE_SEED", PWPP_FUSE_SEED_DEFAULT, 0, 1);
+    // PWPP_FUSE_SEED is a bit mask: 1 = the CTA kernels (classes L2, L3, X), 2 = the warp kernels (classes M, L1).
+    // r01 measurement (profiles/r01_tune.jsonl): fused CTA kernels gain 5-10 %, fused warp kernels lose 3-10 % (their
+    // code grows by a quarter and they already stall on instruction fetch), hence the default 1.
+    const int fuse_mask = env_int("PWPP_FUSE_SEED", PWPP_FUSE_SEED_DEFAULT, 0, 3);
+    const int fuse_seed = fuse_mask & 1, fuse_warp = fuse_mask & 2;
+    const int solve_call = env_int("PWPP_SOLVE_CALL", PWPP_SOLVE_CALL_DEFAULT, 0, 1);   // 1: warp kernels call one out-of-line plane solver
     if (env_int("PWPP_X_KERNEL", PWPP_X_KERNEL_DEFAULT, 0, 1)) {
       const int x_nw = env_int("PWPP_X_NW", PWPP_X_NW_DEFAULT, 8, 32), x_minb = env_int("PWPP_X_MINB", PWPP_X_MINB_DEFAULT, 1, 2);
       if (x_nw >= 32) ctx->fit[5] = {fuse_seed ? k_fit_big<32, 1, true> : k_fit_big<32, 1, false>, 0, 1024, 0};
@@ -503,9 +508,14 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       else ctx->fit[5] = {fuse_seed ? k_fit_big<8, 4, true> : k_fit_big<8, 4, false>, 0, 256, 0};
     }
     // PWPP_FUSE_SEED: zone-0 patches fit the R-VPF plane and the R-GPF seed plane from one selection + one pass (pwpp_fit.cuh)
-    if (fuse_seed) {
+    if (fuse_warp) {
       ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3, true> : k_fit_warp<true, 1, 1, 2, 2, true>, 0, FITW_WARPS * 32, sm_m};
       ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4, true> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3, true> : k_fit_warp<false, 2, 2, FITW_U, 2, true>, 0, FITW_WARPS * 32, 0};
+    } else if (solve_call) {
+      ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3, false, true> : k_fit_warp<true, 1, 1, 2, 2, false, true>, 0, FITW_WARPS * 32, sm_m};
+      ctx->fit[2] = {l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3, false, true> : k_fit_warp<false, 2, 2, FITW_U, 2, false, true>, 0, FITW_WARPS * 32, 0};
+    }
+    if (fuse_seed) {
       ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true> : k_fit_cta<4096, 3, 3, 8, true>, 0, FIT_THREADS, sm_l2};
       ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
     }

@@ -143,6 +143,19 @@ struct GroupOps<256> {
 
 enum FitState { ST_RVPF = 0, ST_SEED = 1, ST_GPF = 2, ST_FINAL = 3, ST_DONE = 4 };
 
+// The plane solve (estimate_plane, S:47-75, from moment sums) is ~1.5k SASS instructions. Inlined at every call site it
+// makes the warp kernels 8-10k instructions (126-160 KB) and k_fit_big 20k: the r01 ncu capture shows 27 % of the class-M
+// kernel's stall samples as "no instruction" (instruction-cache misses). NL = true calls ONE out-of-line copy instead.
+__device__ __noinline__ void plane_from_moments_call(const Moments& m, const double* c, Plane& pl) {
+  const double cc[3] = {c[0], c[1], c[2]};
+  plane_from_moments(m, cc, pl);
+}
+template <bool NL>
+__device__ __forceinline__ void solve_plane(const Moments& m, const double* c, Plane& pl) {
+  if (NL) plane_from_moments_call(m, c, pl);
+  else plane_from_moments(m, c, pl);
+}
+
 // The register-resident fit kernel (classes S and M). G lanes cooperate on one patch, K points per lane; a warp
 // holds 32/G patches and is completely independent of the other warps of its CTA (no block barriers): it pulls its
 // own work items from the queue and every lane of a group evaluates the 3x3 eigen-problem of its patch redundantly
@@ -1082,7 +1095,7 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false>
+template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false, bool NL = false>
 __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -1238,7 +1251,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
 #pragma unroll
         for (int q = 0; q < 6; ++q) ms.s2[q] = hi ? mi.s2[q] : m.s2[q];
         Plane mine = pl;
-        if (ms.n > 0) plane_from_moments(ms, c, mine);
+        if (ms.n > 0) solve_plane<NL>(ms, c, mine);
         auto bcast = [&](int src) {
           Plane t;
 #pragma unroll
@@ -1253,7 +1266,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
           break;
         }
       } else {
-        if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
+        if (m.n > 0) { solve_plane<NL>(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
         tot = m;
         if (!rvpf_round) break;
       }
@@ -1323,7 +1336,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
 #pragma unroll
       for (int q = 0; q < 6; ++q) tot.s2[q] += warp_sum(dm.s2[q]);
       tot.n += warp_sum_i(dm.n);
-      if (tot.n > 0) plane_from_moments(tot, c, pl);   // S:49 otherwise
+      if (tot.n > 0) solve_plane<NL>(tot, c, pl);   // S:49 otherwise
       __syncwarp();
     }
     const int n_ground = have_plane ? tot.n : 0;

@@ -25,7 +25,7 @@ namespace pwpp {
 constexpr int BIG_CCAP = 512;   // candidate buffer of the LPR selection (16 keys per lane of warp 0)
 constexpr int BIG_U = 4;        // loads in flight per thread
 
-template <int NW, int MINB, bool FUSE>
+template <int NW, int MINB, bool FUSE, bool NL = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g,
                                                             AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq, int* __restrict__ part,
                                                             BinFit* __restrict__ fits) {
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
         for (int q = 0; q < 6; ++q) ms.s2[q] = __shfl_sync(0xffffffffu, v, half + 3 + q);
         ms.n = __shfl_sync(0xffffffffu, cn, half + 9);
         Plane mine = pl;
-        if (ms.n > 0) plane_from_moments(ms, cc, mine);
+        if (ms.n > 0) solve_plane<NL>(ms, cc, mine);
         if (lane == 0) { s_plane = mine; s_n[0] = ms.n; }
         if (lane == 16) { s_plane2 = mine; s_n[1] = (FUSE && fused) ? ms.n : 0; }
       }

@@ -1,16 +1,19 @@
 // pwpp_tuning.h — compiled-in defaults of the kernel-variant switches (each can be overridden by the environment variable
-// of the same name without the _DEFAULT suffix when a context is created). Written by tools/apply_chosen.py from the
-// gpurun_out/chosen.env that tools/gpu_tune.py measured on a B200; the GPU parity suite ran under exactly these values.
+// of the same name without the _DEFAULT suffix when a context is created). tools/apply_chosen.py writes the values of a
+// gpurun_out/chosen.env measured by tools/gpu_tune.py on a B200. r01: chosen.env was FUSE_SEED=1 (then one switch for all
+// classes), L2_MINB=3, X_KERNEL=1, X_MINB=1 and the GPU parity suite passed under it; the per-stage times of that run
+// (profiles/r01_tune.jsonl) show the fused WARP kernels slower than the unfused ones, so fusion is on for the CTA kernels only.
 #pragma once
 #define PWPP_HIST_PIPE_DEFAULT 2    /* k_bin_hist load pipelining: 0 none, 1 groups of 4, 2 groups of 2 */
 #define PWPP_SCATTER_V_DEFAULT 0    /* 1: software-pipelined k_scatter at 3 CTAs/SM */
 #define PWPP_S_MINB_DEFAULT 2       /* launch-bounds CTAs/SM of the class-S kernel */
 #define PWPP_M_MINB_DEFAULT 2
 #define PWPP_L1_MINB_DEFAULT 2
-#define PWPP_L2_MINB_DEFAULT 4
+#define PWPP_L2_MINB_DEFAULT 3
 #define PWPP_L2_NW_DEFAULT 8        /* warps per patch of the class-L2 CTA kernel */
 #define PWPP_L3_NW_DEFAULT 8
-#define PWPP_FUSE_SEED_DEFAULT 0    /* 1: R-VPF + R-GPF seed fit of zone-0 patches from one selection and one pass */
+#define PWPP_FUSE_SEED_DEFAULT 1    /* bit mask: R-VPF + R-GPF seed fit of zone-0 patches from one selection and one pass; 1 = CTA kernels (L2, L3, X), 2 = warp kernels (M, L1) */
+#define PWPP_SOLVE_CALL_DEFAULT 0   /* 1: the warp kernels call one out-of-line plane solver (instruction-cache footprint; not yet measured) */
 #define PWPP_X_KERNEL_DEFAULT 1     /* class X (> 8192 points): 1 = CTA per patch (k_fit_big), 0 = one warp per patch */
 #define PWPP_X_NW_DEFAULT 16
-#define PWPP_X_MINB_DEFAULT 2
+#define PWPP_X_MINB_DEFAULT 1

@@ -202,7 +202,7 @@ class Engine:
 
         class _View:   # __cuda_array_interface__ v3: torch.as_tensor wraps the memory without copying
             def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 3, "strides": None}
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3, "strides": None}
         idx = torch.as_tensor(_View(d_idx, total), device="cuda") if total > 0 else torch.empty(0, dtype=torch.int32, device="cuda")
         ng = torch.as_tensor(_View(d_ng, nf), device="cuda")
         return idx, ng

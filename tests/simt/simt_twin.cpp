@@ -160,7 +160,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 0, x_kernel = 1, x_nw = 16;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16;
   int cls_max[5] = {CLS_S_MAX, CLS_M_MAX, CLS_L1_MAX, CLS_L2_MAX, CLS_L3_MAX};
   std::string last_launches;
 };
@@ -197,6 +197,7 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "l3_nw") t->l3_nw = v;
   else if (n == "persistent_ctas") t->persistent_ctas = v;
   else if (n == "fuse_seed") t->fuse_seed = v;
+  else if (n == "solve_call") t->solve_call = v;
   else if (n == "x_kernel") t->x_kernel = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
@@ -270,11 +271,17 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
-  if (t->fuse_seed) {
+  // fuse_seed is the PWPP_FUSE_SEED bit mask: 1 = CTA kernels (L2, L3, X), 2 = warp kernels (M, L1); solve_call = PWPP_SOLVE_CALL
+  if (t->fuse_seed & 1) {
     simt::launch("k_fit_cta<8192,4,2,8,fuse>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true>(FIT_ARGS); });
-    simt::launch("k_fit_cta<4096,3,4,8,fuse>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8, true>(FIT_ARGS); });
+    simt::launch("k_fit_cta<4096,3,3,8,fuse>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true>(FIT_ARGS); });
+  }
+  if (t->fuse_seed & 2) {
     simt::launch("k_fit_warp<false,2,2,fuse>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2, true>(FIT_ARGS); });
     simt::launch("k_fit_warp<true,1,1,fuse>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2, true>(FIT_ARGS); });
+  } else if (t->solve_call) {
+    simt::launch("k_fit_warp<false,2,2,call>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2, false, true>(FIT_ARGS); });
+    simt::launch("k_fit_warp<true,1,1,call>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2, false, true>(FIT_ARGS); });
   }
   if (t->l3_nw == 16) simt::launch("k_fit_cta<8192,4,2,16>", pg, 512, sm_l3, [&] { k_fit_cta<8192, 4, 2, 16>(FIT_ARGS); });
   else simt::launch("k_fit_cta<8192,4,2,8>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8>(FIT_ARGS); });
@@ -284,9 +291,9 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   simt::launch("k_fit_warp<true,1,1>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2>(FIT_ARGS); });
   simt::launch("k_fit_resident<8,8,0>", pg, FIT_THREADS, 0, [&] { k_fit_resident<8, 8, 0, 2>(FIT_ARGS); });
   if (t->x_kernel) {
-    if (t->x_nw == 32) { if (t->fuse_seed) simt::launch("k_fit_big<32,1,fuse>", pg, 1024, 0, [&] { k_fit_big<32, 1, true>(FIT_ARGS); }); else simt::launch("k_fit_big<32,1>", pg, 1024, 0, [&] { k_fit_big<32, 1, false>(FIT_ARGS); }); }
-    else if (t->x_nw == 8) { if (t->fuse_seed) simt::launch("k_fit_big<8,4,fuse>", pg, 256, 0, [&] { k_fit_big<8, 4, true>(FIT_ARGS); }); else simt::launch("k_fit_big<8,4>", pg, 256, 0, [&] { k_fit_big<8, 4, false>(FIT_ARGS); }); }
-    else { if (t->fuse_seed) simt::launch("k_fit_big<16,2,fuse>", pg, 512, 0, [&] { k_fit_big<16, 2, true>(FIT_ARGS); }); else simt::launch("k_fit_big<16,2>", pg, 512, 0, [&] { k_fit_big<16, 2, false>(FIT_ARGS); }); }
+    if (t->x_nw == 32) { if (t->fuse_seed & 1) simt::launch("k_fit_big<32,1,fuse>", pg, 1024, 0, [&] { k_fit_big<32, 1, true>(FIT_ARGS); }); else simt::launch("k_fit_big<32,1>", pg, 1024, 0, [&] { k_fit_big<32, 1, false>(FIT_ARGS); }); }
+    else if (t->x_nw == 8) { if (t->fuse_seed & 1) simt::launch("k_fit_big<8,4,fuse>", pg, 256, 0, [&] { k_fit_big<8, 4, true>(FIT_ARGS); }); else simt::launch("k_fit_big<8,4>", pg, 256, 0, [&] { k_fit_big<8, 4, false>(FIT_ARGS); }); }
+    else { if (t->fuse_seed & 1) simt::launch("k_fit_big<16,2,fuse>", pg, 512, 0, [&] { k_fit_big<16, 2, true>(FIT_ARGS); }); else simt::launch("k_fit_big<16,2>", pg, 512, 0, [&] { k_fit_big<16, 2, false>(FIT_ARGS); }); }
   }
   simt::launch("k_fit_stream", pg, 128, 0, [&] { k_fit_stream(FIT_ARGS); });
 #undef FIT_ARGS
