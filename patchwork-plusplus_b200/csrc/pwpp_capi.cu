@@ -97,7 +97,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 0;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1;
   bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -313,8 +313,9 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   }
   STAGE_MARK();
   if (max_chunks > 0) {
-    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
-    k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, ctx->sw_emit_split);
+    if (ctx->sw_emit_split > 1) k_emit<true><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    else k_emit<false><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -439,6 +440,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", PWPP_HIST_PIPE_DEFAULT, 0, 2);
   ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", PWPP_SCATTER_V_DEFAULT, 0, 1);
   ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
+  ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", PWPP_EMIT_SPLIT_DEFAULT, 1, 32);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -492,6 +494,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8>, 0, FIT_THREADS, sm_l3};
     if (env_int("PWPP_L3_NW", PWPP_L3_NW_DEFAULT, 8, 16) == 16) ctx->fit[4] = {k_fit_cta<8192, 4, 2, 16>, 0, 512, sm_l3};
     ctx->fit[5] = {k_fit_stream, 0, 128, 0};
+    const int part_ilp = env_int("PWPP_PART_ILP", PWPP_PART_ILP_DEFAULT, 0, 1);   // batched index loads in the final partition (default shapes only)
     // class X (> 8192 points, dense sensors): one CTA per patch streaming from L2 (pwpp_fit_big.cuh); PWPP_X_KERNEL=0 selects
     // the one-warp-per-patch fallback, PWPP_X_NW / PWPP_X_MINB the CTA shape (A/B switches)
     // PWPP_FUSE_SEED is a bit mask: 1 = the CTA kernels (classes L2, L3, X), 2 = the warp kernels (classes M, L1).
@@ -518,6 +521,12 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     if (fuse_seed) {
       ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true> : k_fit_cta<4096, 3, 3, 8, true>, 0, FIT_THREADS, sm_l2};
       ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
+    }
+    if (part_ilp) {
+      if (!fuse_warp && !solve_call && m_minb == 2) ctx->fit[1].fn = k_fit_warp<true, 1, 1, 2, 2, false, false, true>;
+      if (!fuse_warp && !solve_call && l1_minb == 2) ctx->fit[2].fn = k_fit_warp<false, 2, 2, FITW_U, 2, false, false, true>;
+      if (fuse_seed && l2_minb == 3 && ctx->fit[3].threads == FIT_THREADS) ctx->fit[3].fn = k_fit_cta<4096, 3, 3, 8, true, true>;
+      if (fuse_seed && ctx->fit[4].threads == FIT_THREADS) ctx->fit[4].fn = k_fit_cta<8192, 4, 2, 8, true, true>;
     }
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];

@@ -392,7 +392,7 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // cross-warp prefix. The LPR selection is two-level: the num_lpr-th smallest of the 256 per-thread minima bounds
 // the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
 // selected exactly by one warp.
-template <int CAP, int CLS, int MINB, int NW, bool FUSE = false>
+template <int CAP, int CLS, int MINB, int NW, bool FUSE = false, bool PILP = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -808,6 +808,32 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       int g_run = 0, ng_run = 0;
       for (int q = 0; q < w; ++q) { g_run += s_cnt[q][0]; ng_run += s_cnt[q][1]; }
       const unsigned lt = lanemask_lt();
+      if (PILP) {
+        // PWPP_PART_ILP: the point indices of four slots are requested before the first one is stored (the r01 capture
+        // shows 7-9 % of this kernel's stall samples on the index load that feeds each store)
+        for (int it0 = 0; it0 < nit; it0 += 4) {
+          int idxv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u;
+            idxv[u] = (it < nit && ((vmask >> it) & 1u)) ? __float_as_int(P[jbase + it * 32].w) : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u;
+            if (it >= nit) break;   // uniform
+            const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
+            const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
+            const unsigned bn = __ballot_sync(0xffffffffu, v && !isg);
+            if (v) {
+              if (isg) out[g_run + __popc(bg & lt)] = idxv[u];
+              else out[n_ground + ng_run + __popc(bn & lt)] = idxv[u];
+            }
+            g_run += __popc(bg);
+            ng_run += __popc(bn);
+          }
+        }
+      } else
       for (int it = 0; it < nit; ++it) {
         const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
         const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
@@ -1095,7 +1121,7 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false, bool NL = false>
+template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false, bool NL = false, bool PILP = false>
 __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -1344,6 +1370,29 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
     // stable partition: ground indices ascending, then non-ground indices ascending
     {
       int g_run = 0, ng_run = 0;
+      if (PILP) {   // PWPP_PART_ILP: four index loads in flight per lane (see k_fit_cta)
+        for (int it0 = 0; it0 < nit; it0 += 4) {
+          int idxv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const int j = (it0 + u) * 32 + lane; idxv[u] = j < n ? __float_as_int(P[j].w) : 0; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u;
+            if (it >= nit) break;   // uniform
+            const int j = it * 32 + lane;
+            const bool v = j < n;
+            const unsigned bg = have_plane ? member_w[it] : 0u;
+            const unsigned bv = __ballot_sync(0xffffffffu, v);
+            const unsigned bn = bv & ~bg;
+            if (v) {
+              if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idxv[u];
+              else out[n_ground + ng_run + __popc(bn & lt)] = idxv[u];
+            }
+            g_run += __popc(bg);
+            ng_run += __popc(bn);
+          }
+        }
+      } else
       for (int it = 0; it < nit; ++it) {
         const int j = it * 32 + lane;
         const bool v = j < n;

@@ -551,6 +551,7 @@ constexpr int EMIT_WARPS = 8;     // bins per CTA: every warp copies the two par
 // One warp per (frame, bin): the ground part and the non-ground part of a bin are contiguous both in `part` /
 // `sorted` and in the output lists, so the copy is two coalesced streams (typical bins: a few to a few thousand
 // points; a pathological bin holding a whole frame is copied by one warp, which is slow but correct).
+template <bool SPLIT>
 __global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
                                                           const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
                                                           int* __restrict__ out_idx) {
@@ -566,7 +567,17 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit(FrameTable ft, Geometr
   const BinSeg sg = segs[(size_t) f * nb_all + b];
   int ng = -1;
   if (b < g.nbins) { const BinFit& r = fits[(size_t) f * g.nbins + b]; if (r.fitted) ng = r.n_ground; }
-  const int j0 = 0, j1 = nbin;
+  // gridDim.z > 1 (PWPP_EMIT_SPLIT): a bin is copied in gridDim.z slices of at least 1024 entries, so that the 20k..40k-point
+  // bins of a dense frame are not left to one warp each (r01: k_emit is 28 % of a dense step, 5 % of a KITTI step)
+  int j0 = 0, j1 = nbin;
+  if (SPLIT && gridDim.z > 1) {
+    int seg = (nbin + (int) gridDim.z - 1) / (int) gridDim.z;
+    seg = (seg + 127) & ~127;
+    if (seg < 1024) seg = 1024;
+    j0 = (int) blockIdx.z * seg;
+    if (j0 >= nbin) return;
+    j1 = j0 + seg < nbin ? j0 + seg : nbin;
+  }
   if (ng >= 0) {
     const int* src = part + p0 + off;
     for (int j = j0 + lane; j < j1; j += 128) {   // four independent loads in flight per lane

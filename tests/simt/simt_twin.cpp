@@ -160,7 +160,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0;
   int cls_max[5] = {CLS_S_MAX, CLS_M_MAX, CLS_L1_MAX, CLS_L2_MAX, CLS_L3_MAX};
   std::string last_launches;
 };
@@ -199,6 +199,8 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "fuse_seed") t->fuse_seed = v;
   else if (n == "solve_call") t->solve_call = v;
   else if (n == "x_kernel") t->x_kernel = v;
+  else if (n == "emit_split") t->emit_split = v;
+  else if (n == "part_ilp") t->part_ilp = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -271,6 +273,12 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
+  if (t->part_ilp) {   // PWPP_PART_ILP variants of the default shapes drain the queues first
+    simt::launch("k_fit_cta<8192,4,2,8,fuse,pilp>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true, true>(FIT_ARGS); });
+    simt::launch("k_fit_cta<4096,3,3,8,fuse,pilp>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true, true>(FIT_ARGS); });
+    simt::launch("k_fit_warp<false,2,2,pilp>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2, false, false, true>(FIT_ARGS); });
+    simt::launch("k_fit_warp<true,1,1,pilp>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2, false, false, true>(FIT_ARGS); });
+  }
   // fuse_seed is the PWPP_FUSE_SEED bit mask: 1 = CTA kernels (L2, L3, X), 2 = warp kernels (M, L1); solve_call = PWPP_SOLVE_CALL
   if (t->fuse_seed & 1) {
     simt::launch("k_fit_cta<8192,4,2,8,fuse>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true>(FIT_ARGS); });
@@ -314,8 +322,9 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     });
   }
   if (max_chunks > 0) {
-    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes);
-    simt::launch("k_emit", grid, EMIT_WARPS * 32, 0, [&] { k_emit(ft, g, nbp, bin_off.data(), fits.data(), segs.data(), part.data(), sorted.data(), out_idx.data()); });
+    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, t->emit_split);
+    if (t->emit_split > 1) simt::launch("k_emit<split>", grid, EMIT_WARPS * 32, 0, [&] { k_emit<true>(ft, g, nbp, bin_off.data(), fits.data(), segs.data(), part.data(), sorted.data(), out_idx.data()); });
+    else simt::launch("k_emit", grid, EMIT_WARPS * 32, 0, [&] { k_emit<false>(ft, g, nbp, bin_off.data(), fits.data(), segs.data(), part.data(), sorted.data(), out_idx.data()); });
   }
   for (int f = 0; f < nframes; ++f) {
     FrameOut& o = t->out[f];

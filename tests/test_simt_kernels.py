@@ -70,7 +70,7 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1)])
+@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1), dict(emit_split=8), dict(part_ilp=1)])
 def test_kernel_variants(kitti, opts):
     """The A/B variants selectable through PWPP_* switches give the same result as the defaults."""
     a = kitti[3]
@@ -102,7 +102,7 @@ def _big_patch_cases():
     }
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(fuse_seed=0), dict(x_nw=8, fuse_seed=3), dict(x_nw=32), dict(x_kernel=0)])
+@pytest.mark.parametrize("opts", [dict(), dict(fuse_seed=0), dict(x_nw=8, fuse_seed=3), dict(x_nw=32, emit_split=5), dict(x_kernel=0)])
 def test_big_patches(opts):
     """Class X (more than 8192 points in one patch): k_fit_big in its CTA shapes and the one-warp fallback, including
     the tie-heavy selections that overflow the candidate buffer and an R-VPF wall removal in zone 0."""
@@ -143,11 +143,12 @@ def test_edge_cases():
                                      np.c_[3 + rng.random(3000) * 6, rng.random(3000) * 1.5, -1.7 + rng.normal(0, 0.02, 3000), rng.random(3000)]].astype(np.float32),
     }
     names = list(cases)
-    tw = SimtTwin(num_streams=len(names))
-    tw.estimate_multi([cases[k] for k in names])
-    for f, k in enumerate(names):
-        orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(cases[k])
-        tw.select(f)
-        _check(orc, tw, cases[k], f"edge/{k}", allow_degenerate=True)
+    for opts in (dict(), dict(part_ilp=1, emit_split=3, fuse_seed=3)):
+        tw = SimtTwin(num_streams=len(names), **opts)
+        tw.estimate_multi([cases[k] for k in names])
+        for f, k in enumerate(names):
+            orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(cases[k])
+            tw.select(f)
+            _check(orc, tw, cases[k], f"edge/{k}/{opts}", allow_degenerate=True)
     tw.select(names.index("z_equals_flt_min"))
     assert len(tw.getGroundIndices()) + len(tw.getNongroundIndices()) == len(cases["z_equals_flt_min"]) - 1   # patchworkpp.cpp:591
