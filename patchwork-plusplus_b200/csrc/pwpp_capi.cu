@@ -13,6 +13,7 @@
 
 #include "pwpp.h"
 #include "pwpp_kernels.cuh"
+#include "pwpp_front.cuh"
 #include "pwpp_tuning.h"
 #include "pwpp_host.hpp"
 
@@ -97,7 +98,10 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0;
+  int front_grid = 0;
+  DevBuf<FrontItem> d_front_items;
+  DevBuf<int> d_front_ctr;
   bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -250,6 +254,28 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   int stage = 0;
 #define STAGE_MARK() do { if (prof) CU_TRY(cudaEventRecord(ctx->stage_ev[stage], s)); ++stage; } while (0)
   STAGE_MARK();
+  WorkQueues wq;
+  for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = ctx->d_wq_items[c].p;
+  wq.count = ctx->d_wq_ctr.p;
+  wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
+  if (ctx->sw_front) {
+    // PWPP_FRONT: binning, scan and scatter as one persistent kernel pipelined through L2 (pwpp_front.cuh)
+    const int total_chunks = ctx->chunk_off[f0 + nf] - ctx->chunk_off[f0];
+    const int nitems = 2 * total_chunks + nf;
+    const long long pts_in_range = ctx->pt_off[f0 + nf] - ctx->pt_off[f0];
+    const long long per_frame = std::max(1LL, pts_in_range / nf) * 16;
+    const int W = (int) std::max(1LL, std::min((long long) nf, (32LL << 20) / per_frame));   // scatter runs ~32 MB of points behind the binning pass
+    CU_TRY(ctx->d_front_items.reserve((size_t) nitems + 1));
+    CU_TRY(ctx->d_front_ctr.reserve((size_t) 1 + 2 * nf));
+    CU_TRY(cudaMemsetAsync(ctx->d_front_ctr.p, 0, ((size_t) 1 + 2 * nf) * sizeof(int), s));
+    k_front_plan<<<(nf + W + 127) / 128, 128, 0, s>>>(ft.chunk_off, nf, W, ctx->d_front_items.p);
+    FrontArgs fa{d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->fast_bin ? 1 : 0, ctx->d_bin_ids.p, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits,
+                 ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->d_front_ctr.p, nf};
+    const size_t sm_f = std::max((size_t) (CHUNK_THREADS / 32) * nbp, (size_t) nbp + 1) * sizeof(unsigned int);
+    k_front<<<ctx->front_grid, FRONT_THREADS, sm_f, s>>>(fa);
+    ctx->launches += 2;
+    STAGE_MARK(); STAGE_MARK(); STAGE_MARK();
+  } else {
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     const int hist_pipe = ctx->sw_hist_pipe;
@@ -262,10 +288,6 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     ++ctx->launches;
   }
   STAGE_MARK();
-  WorkQueues wq;
-  for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = ctx->d_wq_items[c].p;
-  wq.count = ctx->d_wq_ctr.p;
-  wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
   k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
   ++ctx->launches;
   STAGE_MARK();
@@ -279,6 +301,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     ++ctx->launches;
   }
   STAGE_MARK();
+  }   // !sw_front
   // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan). The classes are independent:
   // unless per-stage timing is requested they run on side streams so that the tail of one class (few long patches
   // left) overlaps the start of the next.
@@ -441,6 +464,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", PWPP_SCATTER_V_DEFAULT, 0, 1);
   ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
   ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", PWPP_EMIT_SPLIT_DEFAULT, 1, 32);
+  ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -540,6 +564,15 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   }
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
+    if (ctx->sw_front) {
+      const size_t sm_f = std::max(scat, ((size_t) ctx->nbp + 1) * sizeof(unsigned int));
+      if (sm_f > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
+      cudaDeviceProp prop;
+      CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
+      int per_sm = 1;
+      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, sm_f));
+      ctx->front_grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
     if (scat > 48 * 1024) {
       CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
       CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
@@ -569,7 +602,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int q = 0; q < 5; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
-  ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release();
+  ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release(); ctx->d_front_items.release(); ctx->d_front_ctr.release();
   for (int c = 0; c < NUM_CLASSES; ++c) ctx->d_wq_items[c].release();
   ctx->d_out_idx.release(); ctx->d_counts.release();
   ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();

@@ -13,6 +13,7 @@
 #include "pwpp.h"
 #include "pwpp_host.hpp"
 #include "pwpp_kernels.cuh"
+#include "pwpp_front.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // runtime of the stand-in
@@ -160,7 +161,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2;
   int cls_max[5] = {CLS_S_MAX, CLS_M_MAX, CLS_L1_MAX, CLS_L2_MAX, CLS_L3_MAX};
   std::string last_launches;
 };
@@ -201,6 +202,8 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "x_kernel") t->x_kernel = v;
   else if (n == "emit_split") t->emit_split = v;
   else if (n == "part_ilp") t->part_ilp = v;
+  else if (n == "front") t->front = v;
+  else if (n == "front_w") t->front_w = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -247,6 +250,22 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   FrameTable ft{pt_off.data(), chunk_off.data()};
   StreamState* states = t->states.data();
   const float4* d_pts = pts.data();
+  WorkQueues wq;
+  for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = items[c].data();
+  wq.count = ctr.data();
+  wq.head = ctr.data() + NUM_CLASSES;
+  if (t->front) {   // PWPP_FRONT: the three front-end kernels as one persistent, L2-pipelined kernel
+    const int nitems = 2 * total_chunks + nframes, W = std::max(1, std::min(nframes, t->front_w));
+    std::vector<FrontItem> fitems((size_t) nitems + 1, FrontItem{-1, -1});
+    std::vector<int> fctr(1 + 2 * nframes, 0);
+    simt::launch("k_front_plan", (nframes + W + 127) / 128, 128, 0, [&] { k_front_plan(chunk_off.data(), nframes, W, fitems.data()); });
+    for (int k = 0; k < nitems; ++k) if (fitems[k].tf < 0) { std::fprintf(stderr, "simt_twin: k_front_plan left item %d unset\n", k); std::abort(); }
+    FrontArgs fa{d_pts, ft, states, g, ap, has_intensity, nbp, nb, t->fast ? 1 : 0, bin_ids.data(), chist.data(), cbase.data(), bin_off.data(), wq, fits.data(),
+                 sorted.data(), fitems.data(), nitems, fctr.data(), nframes};
+    const size_t sm_f = std::max((size_t) (CHUNK_THREADS / 32) * nbp, (size_t) nbp + 1) * sizeof(unsigned int);
+    simt::launch("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });
+    if (fctr[0] < nitems) { std::fprintf(stderr, "simt_twin: k_front stopped at item %d of %d\n", fctr[0], nitems); std::abort(); }
+  } else {
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     const size_t sm_h = nbp * sizeof(unsigned int);
@@ -256,10 +275,6 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     else simt::launch("k_bin_hist<true,2>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 2>(HIST_ARGS); });
 #undef HIST_ARGS
   }
-  WorkQueues wq;
-  for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = items[c].data();
-  wq.count = ctr.data();
-  wq.head = ctr.data() + NUM_CLASSES;
   simt::launch("k_bin_scan", nframes, 512, (nbp + 1) * sizeof(int),
                [&] { k_bin_scan(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
   if (max_chunks > 0) {
@@ -270,6 +285,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     else simt::launch("k_scatter<false,4>", grid, CHUNK_THREADS, sm_sc, [&] { k_scatter<false, 4>(SC_ARGS); });
 #undef SC_ARGS
   }
+  }   // !front
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);

@@ -79,6 +79,24 @@ def test_kernel_variants(kitti, opts):
     assert _check(orc, tw, a, f"variant/{opts}") == 0
 
 
+def test_persistent_front_end_is_identical(kitti):
+    """PWPP_FRONT: binning + scan + scatter as one persistent kernel over an ordered work list (pwpp_front.cuh), for several
+    pipeline depths W, with empty / one-point / ragged frames: bin ids, index lists and patch records identical to the
+    three stand-alone kernels. (The twin runs CTAs one after another, so an item that had to wait for a LATER item would be
+    reported as a deadlock: the list order is what is checked here; the spin-waits themselves need a GPU.)"""
+    import synth
+    frames = [kitti[1], np.zeros((0, 4), np.float32), synth.make_frame(5, 1).numpy(), np.array([[5, 0, -1.7, 0.5]], np.float32), kitti[2][:50000],
+              synth.make_frame(5, 2).numpy()[:4096]]
+    a = SimtTwin(num_streams=len(frames)); a.estimate_multi(frames)
+    for w in (1, 2, 5, 20):
+        b = SimtTwin(num_streams=len(frames), front=1, front_w=w, persistent_ctas=3); b.estimate_multi(frames)
+        for f in range(len(frames)):
+            a.select(f); b.select(f)
+            assert np.array_equal(a.bin_ids(), b.bin_ids())
+            assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and np.array_equal(a.getNongroundIndices(), b.getNongroundIndices()), (w, f)
+            assert bytes(a.bin_results()) == bytes(b.bin_results())
+
+
 def test_fused_seed_rounds_are_bit_identical(kitti):
     """PWPP_FUSE_SEED: the R-VPF and the R-GPF seed plane of a zone-0 patch from one selection and one pass. The fused
     rounds accumulate in the same order as the two separate passes, so every patch record is bit-identical."""
@@ -175,7 +193,7 @@ def test_random_parameter_sets(kitti, seed):
     p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([4, 8, 16, 32, 54, 64], 4)]
     p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 6, 4)]
     opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 3, 8])), solve_call=int(rng.integers(0, 2)),
-                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])))
+                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
     pool = [kitti[0], kitti[4], synth.make_frame(7, 0).numpy()]
     orc, tw = O.Oracle(p, O.ARITH_CANON64), SimtTwin(p, **opts)
