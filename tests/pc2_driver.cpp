@@ -1,0 +1,42 @@
+// TEST-ONLY driver for include/patchwork/pointcloud2.hpp (tests/test_examples.py): reads a scan (float32 x,y,z,i records),
+// lays it out as several PointCloud2-style messages (different point_step / field offsets), runs each through
+// patchwork::estimateGround(pw, view) and prints "layout zero_copy ground nonground payload_bytes".
+#include <patchwork/pointcloud2.hpp>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  FILE* f = std::fopen(argv[1], "rb");
+  if (!f) return 2;
+  std::vector<float> scan(4 * 200000);
+  const size_t n = std::fread(scan.data(), 16, 200000, f);
+  std::fclose(f);
+  struct Layout { const char* name; uint32_t step; int ox, oy, oz, oi; };
+  const Layout layouts[] = {
+      {"xyz12", 12, 0, 4, 8, -1},            // what the reference node consumes
+      {"xyzi16", 16, 0, 4, 8, 12},           // packed with intensity
+      {"pcl_xyzi32", 32, 0, 4, 8, 16},       // PCL PointXYZI: padding before intensity -> gather
+      {"velodyne22", 22, 0, 4, 8, 12},       // x,y,z,intensity,ring(u16),time... unaligned step -> gather
+      {"ouster48_noint", 48, 16, 20, 24, -1} // fields in the middle of a wide point, no intensity -> strided
+  };
+  patchwork::Params params;
+  params.verbose = false;
+  for (const Layout& L : layouts) {
+    std::vector<uint8_t> msg((size_t) n * L.step + 8, 0xAB);
+    for (size_t i = 0; i < n; ++i) {
+      uint8_t* p = msg.data() + i * L.step;
+      std::memcpy(p + L.ox, &scan[4 * i], 4); std::memcpy(p + L.oy, &scan[4 * i + 1], 4); std::memcpy(p + L.oz, &scan[4 * i + 2], 4);
+      if (L.oi >= 0) std::memcpy(p + L.oi, &scan[4 * i + 3], 4);
+    }
+    patchwork::PatchWorkpp pw(params);
+    patchwork::PointCloud2View v;
+    v.data = msg.data(); v.num_points = (int64_t) n; v.point_step = L.step; v.off_x = L.ox; v.off_y = L.oy; v.off_z = L.oz; v.off_intensity = L.oi;
+    const bool zc = patchwork::estimateGround(pw, v);
+    const patchwork::PointCloud2Payload g = patchwork::makeCloudPayload(pw, true), ng = patchwork::makeCloudPayload(pw, false);
+    std::printf("%s %d %u %u %zu\n", L.name, zc ? 1 : 0, g.width, ng.width, g.data.size() + ng.data.size());
+  }
+  return 0;
+}

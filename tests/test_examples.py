@@ -56,3 +56,28 @@ def test_sequence_runner_fails_loudly_without_a_gpu(tmp_path, kitti):
     _scans(tmp_path, kitti, [1000])
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "no CUDA device" in out.stderr and "no CPU path" in out.stderr
+
+
+def test_pointcloud2_adaptor_with_stub(tmp_path, kitti):
+    """include/patchwork/pointcloud2.hpp (the ROS 2 node's message handling without ROS) against the C-ABI
+    stub: every message layout reaches the engine with the right coordinates (the stub labels by z), aligned equally
+    spaced fields go through as a strided view without a gather, and the outgoing payloads are packed x/y/z."""
+    build = os.path.join(HERE, "_build")
+    os.makedirs(build, exist_ok=True)
+    stub = os.path.join(build, "libpwpp_stub.so")
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-I" + os.path.join(REPO, "include"), os.path.join(HERE, "stub_pwpp.c"), "-o", stub])
+    exe = os.path.join(build, "pc2_driver_stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(REPO, "include"), os.path.join(HERE, "pc2_driver.cpp"), "-o", exe, stub,
+                           "-Wl,-rpath," + build])
+    a = kitti[2][:30000]
+    np.ascontiguousarray(a).tofile(tmp_path / "scan.bin")
+    out = subprocess.run([exe, str(tmp_path / "scan.bin")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    names = {"xyz12", "xyzi16", "pcl_xyzi32", "velodyne22", "ouster48_noint"}
+    rows = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.stdout.splitlines() if l.split() and l.split()[0] in names}
+    ng = int((a[:, 2] < -1.5).sum())
+    assert set(rows) == names
+    for name, (zero_copy, g, n, payload) in rows.items():
+        assert (g, n) == (ng, len(a) - ng), name
+        assert payload == 12 * len(a), name
+        assert zero_copy == (0 if name in ("pcl_xyzi32", "velodyne22") else 1), name
