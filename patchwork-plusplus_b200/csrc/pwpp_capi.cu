@@ -271,7 +271,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     k_front_plan<<<(nf + W + 127) / 128, 128, 0, s>>>(ft.chunk_off, nf, W, ctx->d_front_items.p);
     FrontArgs fa{d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->fast_bin ? 1 : 0, ctx->d_bin_ids.p, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits,
                  ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->d_front_ctr.p, nf};
-    const size_t sm_f = std::max((size_t) (CHUNK_THREADS / 32) * nbp, (size_t) nbp + 1) * sizeof(unsigned int);
+    const size_t sm_f = front_smem_bytes(nbp);
     k_front<<<ctx->front_grid, FRONT_THREADS, sm_f, s>>>(fa);
     ctx->launches += 2;
     STAGE_MARK(); STAGE_MARK(); STAGE_MARK();
@@ -565,7 +565,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
     if (ctx->sw_front) {
-      const size_t sm_f = std::max(scat, ((size_t) ctx->nbp + 1) * sizeof(unsigned int));
+      const size_t sm_f = front_smem_bytes(ctx->nbp);
       if (sm_f > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
       cudaDeviceProp prop;
       CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));

@@ -33,7 +33,9 @@ __device__ __forceinline__ unsigned short ldcg_u16(const unsigned short* p) { re
 __device__ __forceinline__ unsigned int ldcg_u32(const unsigned int* p) { return *p; }
 __device__ __forceinline__ float4 ldcg_f4(const float4* p) { return *p; }
 __device__ __forceinline__ void __threadfence() {}
-__device__ __forceinline__ void front_spin_pause() { simt::deadlock("k_front: an item waits for a later one (the work list is out of order)"); }
+__device__ __forceinline__ void front_spin_pause() {   // concurrent CTAs: let the others run; sequential CTAs: nobody could ever satisfy the wait
+  if (simt::g_concurrent) simt::yield_(); else simt::deadlock("k_front: an item waits for a later one (the work list is out of order)");
+}
 #else
 __device__ __forceinline__ int ld_acquire_i(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned short ldcg_u16(const unsigned short* p) { unsigned short v; asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
@@ -41,6 +43,10 @@ __device__ __forceinline__ unsigned int ldcg_u32(const unsigned int* p) { return
 __device__ __forceinline__ float4 ldcg_f4(const float4* p) { return __ldcg(p); }
 __device__ __forceinline__ void front_spin_pause() { __nanosleep(64); }
 #endif
+
+// shared-memory words of k_front: the largest body scratch (8 x nbp for the scatter, nbp + 1 for the scan) + 1 + 3 x classes
+__host__ __device__ inline int front_body_words(int nbp) { return (CHUNK_THREADS / 32) * nbp > nbp + 1 ? (CHUNK_THREADS / 32) * nbp : nbp + 1; }
+__host__ __device__ inline size_t front_smem_bytes(int nbp) { return (size_t) (front_body_words(nbp) + 1 + 3 * NUM_CLASSES) * sizeof(unsigned int); }
 
 struct FrontArgs {
   const float4* pts;
@@ -109,8 +115,10 @@ __device__ __forceinline__ void front_hist_chunk(const FrontArgs& a, int f, int 
 }
 
 // ---- S: k_bin_scan's body for one frame. smem: nbp + 1 ints ----
-__device__ __forceinline__ void front_scan_frame(const FrontArgs& a, int f, int* s_scan) {
-  __shared__ int s_cls_cnt[NUM_CLASSES], s_cls_base[NUM_CLASSES], s_cls_pos[NUM_CLASSES];
+__device__ __forceinline__ void front_scan_frame(const FrontArgs& a, int f, int* s_scan, int* s_cls) {
+  int* s_cls_cnt = s_cls;                       // [NUM_CLASSES] each
+  int* s_cls_base = s_cls + NUM_CLASSES;
+  int* s_cls_pos = s_cls + 2 * NUM_CLASSES;
   const int nbp = a.nbp, nbins = a.nbins;
   const int c0 = a.ft.chunk_off[f], c1 = a.ft.chunk_off[f + 1];
   if (threadIdx.x < NUM_CLASSES) { s_cls_cnt[threadIdx.x] = 0; s_cls_pos[threadIdx.x] = 0; }
@@ -254,8 +262,12 @@ __global__ void k_front_plan(const int* __restrict__ chunk_off, int F, int W, Fr
 }
 
 __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(FrontArgs a) {
-  PW_DYN_SHARED(unsigned int, s_dyn);   // max(8 * nbp, nbp + 1) words
-  __shared__ int s_k;
+  // dynamic shared memory only (the SIMT twin can then run several CTAs of this kernel concurrently):
+  // [0, front_body_words) the bodies' scratch, then the claimed item index, then the scan's class counters
+  PW_DYN_SHARED(unsigned int, s_dyn);
+  const int body_words = front_body_words(a.nbp);
+  int& s_k = *reinterpret_cast<int*>(s_dyn + body_words);
+  int* s_cls = reinterpret_cast<int*>(s_dyn + body_words + 1);
   int* hist_done = a.ctr + 1;
   int* scan_done = a.ctr + 1 + a.nframes;
   for (;;) {
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(FrontArgs a) {
       const int need = a.ft.chunk_off[f + 1] - a.ft.chunk_off[f];
       if (threadIdx.x == 0) { while (ld_acquire_i(&hist_done[f]) < need) front_spin_pause(); }
       __syncthreads();
-      front_scan_frame(a, f, reinterpret_cast<int*>(s_dyn));
+      front_scan_frame(a, f, reinterpret_cast<int*>(s_dyn), s_cls);
       __syncthreads();
       if (threadIdx.x == 0) { __threadfence(); atomicAdd(&scan_done[f], 1); }
     } else {

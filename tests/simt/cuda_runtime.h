@@ -2,7 +2,9 @@
 //
 // The build container has no GPU. This header lets g++ compile csrc/*.cuh unchanged (it is found first on the include
 // path of tests/simt/simt_twin.cpp) and executes a kernel launch as follows:
-//   * CTAs run one after another on the calling OS thread (so `__shared__` variables may be plain statics);
+//   * CTAs run one after another on the calling OS thread (so `__shared__` variables may be plain statics); a kernel whose
+//     CTAs wait for each other (k_front) is launched with simt::launch_concurrent: all CTAs live at once, fibers of all
+//     of them scheduled round-robin — such a kernel must keep everything in dynamic shared memory;
 //   * every thread of a CTA is a fiber with its own stack (hand-written x86-64 context switch); a fiber runs until it
 //     reaches a warp collective or a block barrier, where it waits for the other participants round-robin;
 //   * __shfl*_sync / __ballot_sync / __any_sync / __match_any_sync / __reduce_*_sync / __syncwarp are rendezvous of the
@@ -89,15 +91,19 @@ struct Cta {
   const char* kernel_name = "";
   std::function<void()> body;
   std::vector<char> dyn_smem;
+  uint3 bid = {0, 0, 0};       // blockIdx of this CTA (concurrent launches)
 };
 
-extern Cta g_cta;
+extern Cta* g_cta_p;            // the CTA of the running fiber
+#define g_cta (*simt::g_cta_p)
 extern uint3 g_tid[MAX_THREADS];
+extern bool g_concurrent;       // launch_concurrent(): all CTAs of the grid are live at once (kernels that wait for each other)
 
 extern "C" void simt_switch(void** save_sp, void* load_sp);
 void yield_();
 [[noreturn]] void deadlock(const char* what);
 void launch_impl(const char* name, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem, const std::function<void()>& body);
 
 }  // namespace simt
 
@@ -106,7 +112,7 @@ extern uint3 threadIdx;   // rewritten on every fiber switch
 extern uint3 blockIdx;
 extern dim3 blockDim, gridDim;
 
-static inline void* simt_dyn_smem() { return simt::g_cta.dyn_smem.data(); }
+static inline void* simt_dyn_smem() { return g_cta.dyn_smem.data(); }
 // `extern __shared__ T name[];` of the device build
 #define PW_DYN_SHARED(T, name) T* name = reinterpret_cast<T*>(simt_dyn_smem())
 
@@ -235,7 +241,7 @@ static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width =
 
 // ---- block barrier: all threads of the CTA that have not returned ----
 static inline void __syncthreads() {
-  simt::Cta& c = simt::g_cta;
+  simt::Cta& c = g_cta;
   ++c.progress;
   const unsigned long long g = c.bar_gen;
   if (++c.bar_arrived >= c.alive) { c.bar_arrived = 0; ++c.bar_gen; return; }
@@ -283,4 +289,6 @@ static inline float fminf_(float a, float b) { return a < b ? a : b; }
 namespace simt {
 template <typename F>
 static inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, F&& f) { launch_impl(name, grid, block, smem, std::function<void()>(f)); }
+template <typename F>
+static inline void launch_concurrent(const char* name, int nctas, dim3 block, size_t smem, F&& f) { launch_concurrent_impl(name, nctas, block, smem, std::function<void()>(f)); }
 }

@@ -22,9 +22,14 @@ uint3 blockIdx;
 dim3 blockDim, gridDim;
 
 namespace simt {
-Cta g_cta;
+static Cta g_cta_seq;                 // the one CTA of sequential launches
+Cta* g_cta_p = &g_cta_seq;
 uint3 g_tid[MAX_THREADS];
-static unsigned long long g_spins = 0, g_last_progress = 0;
+bool g_concurrent = false;
+static std::vector<Cta*> g_ctas;      // live CTAs of the current launch (1 for sequential launches)
+static int g_cur_cta = 0;
+static void* g_main_sp = nullptr;
+static unsigned long long g_spins = 0, g_last_progress = 0, g_progress_base = 0;
 static unsigned long long g_switches = 0;
 
 asm(R"(
@@ -51,90 +56,137 @@ simt_switch:
 )");
 
 [[noreturn]] void deadlock(const char* what) {
-  std::fprintf(stderr, "simt: DEADLOCK in kernel %s, block (%u,%u): %s (thread %d waits; %d of %d threads alive)\n", g_cta.kernel_name, blockIdx.x, blockIdx.y,
-               what, g_cta.cur, g_cta.alive, g_cta.nthreads);
+  std::fprintf(stderr, "simt: DEADLOCK in kernel %s, block (%u,%u): %s (thread %d waits; %d of %d threads of its CTA alive, %zu CTA(s) live)\n", g_cta.kernel_name,
+               blockIdx.x, blockIdx.y, what, g_cta.cur, g_cta.alive, g_cta.nthreads, g_ctas.size());
   std::abort();
 }
 
-static void switch_to(int next) {
-  Cta& c = g_cta;
-  const int prev = c.cur;
-  c.cur = next;
-  threadIdx = g_tid[next];
+static unsigned long long total_progress() {
+  unsigned long long p = 0;
+  for (Cta* c : g_ctas) p += c->progress;
+  return p;
+}
+
+// next live fiber after (cta ci, thread ti) in round-robin order over all live CTAs; false if there is none but itself
+static bool next_fiber(int ci, int ti, int& nci, int& nti) {
+  const int nc = (int) g_ctas.size();
+  int c = ci, t = ti;
+  for (int steps = 0; steps < nc * MAX_THREADS + MAX_THREADS; ++steps) {
+    ++t;
+    if (t >= g_ctas[c]->nthreads) { t = 0; c = (c + 1) % nc; }
+    if (c == ci && t == ti) return false;
+    if (!g_ctas[c]->fib[t].done) { nci = c; nti = t; return true; }
+  }
+  return false;
+}
+
+static void switch_from(Fiber& me, int nci, int nti) {
+  Cta* n = g_ctas[nci];
+  g_cur_cta = nci;
+  g_cta_p = n;
+  n->cur = nti;
+  threadIdx = g_tid[nti];
+  blockIdx = n->bid;
   ++g_switches;
-  simt_switch(&c.fib[prev].sp, c.fib[next].sp);
+  simt_switch(&me.sp, n->fib[nti].sp);
 }
 
 void yield_() {
   Cta& c = g_cta;
-  if (c.progress != g_last_progress) { g_last_progress = c.progress; g_spins = 0; }
-  else if (++g_spins > 64ull * (unsigned long long) c.nthreads + 4096ull) deadlock("no thread can make progress");
-  int next = c.cur;
-  for (int k = 1; k <= c.nthreads; ++k) {
-    const int t = (c.cur + k) % c.nthreads;
-    if (!c.fib[t].done) { next = t; break; }
-  }
-  if (next == c.cur) return;
-  switch_to(next);
+  const unsigned long long p = total_progress();
+  if (p != g_last_progress) { g_last_progress = p; g_spins = 0; }
+  else if (++g_spins > 64ull * (unsigned long long) c.nthreads * g_ctas.size() + 4096ull) deadlock("no thread can make progress");
+  int nci, nti;
+  if (!next_fiber(g_cur_cta, c.cur, nci, nti)) return;
+  switch_from(c.fib[c.cur], nci, nti);
 }
 
 static void fiber_main() {
-  Cta& c = g_cta;
-  c.body();
+  {
+    Cta& c = g_cta;
+    c.body();
+  }
   // the thread returned from the kernel
-  const int me = c.cur;
+  Cta& c = g_cta;
+  const int me = c.cur, myc = g_cur_cta;
   c.fib[me].done = true;
   --c.alive;
   ++c.progress;
-  if (c.alive == 0) {
-    threadIdx = g_tid[0];
-    simt_switch(&c.fib[me].sp, c.main_sp);
-  }
   for (;;) {
-    int next = -1;
-    for (int k = 1; k <= c.nthreads; ++k) {
-      const int t = (me + k) % c.nthreads;
-      if (!c.fib[t].done) { next = t; break; }
-    }
-    if (next < 0) simt_switch(&c.fib[me].sp, c.main_sp);
-    else { c.cur = next; threadIdx = g_tid[next]; simt_switch(&c.fib[me].sp, c.fib[next].sp); }
+    int nci, nti;
+    if (next_fiber(myc, me, nci, nti)) switch_from(c.fib[me], nci, nti);
+    else { threadIdx = g_tid[0]; simt_switch(&c.fib[me].sp, g_main_sp); }
   }
 }
 
-void launch_impl(const char* name, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
-  Cta& c = g_cta;
-  const int nt = (int) (block.x * block.y * block.z);
-  if (nt <= 0 || nt > MAX_THREADS) { std::fprintf(stderr, "simt: bad block size %d\n", nt); std::abort(); }
-  blockDim = block; gridDim = grid;
+static void init_cta(Cta& c, const char* name, int nt, size_t smem, const std::function<void()>& body, uint3 bid) {
   c.kernel_name = name;
   c.body = body;
   c.dyn_smem.assign(smem + 64, 0);
+  c.nthreads = nt; c.alive = nt; c.bar_arrived = 0; c.bid = bid; c.cur = 0;
+  for (int w = 0; w < (nt + 31) / 32; ++w) { c.warps[w].nslots = 0; for (auto& s : c.warps[w].slots) { s.mask = 0; s.arrived = 0; s.departed = 0; s.draining = false; } }
   for (int t = 0; t < nt; ++t) {
-    if (!c.fib[t].stack) c.fib[t].stack = (char*) std::malloc(STACK_BYTES);
-    g_tid[t].x = t % block.x; g_tid[t].y = (t / block.x) % block.y; g_tid[t].z = t / (block.x * block.y);
+    Fiber& f = c.fib[t];
+    if (!f.stack) f.stack = (char*) std::malloc(STACK_BYTES);
+    f.done = false;
+    uintptr_t top = ((uintptr_t) (f.stack + STACK_BYTES)) & ~(uintptr_t) 15;
+    void** sp = (void**) top;
+    *--sp = nullptr;                    // fake return address of fiber_main (keeps the ABI stack alignment)
+    *--sp = (void*) &fiber_main;        // popped by `ret` in simt_switch
+    for (int k = 0; k < 6; ++k) *--sp = nullptr;   // rbp rbx r12 r13 r14 r15
+    f.sp = sp;
   }
+}
+
+static void run_live_ctas() {
+  g_spins = 0;
+  g_last_progress = total_progress();
+  g_cur_cta = 0;
+  g_cta_p = g_ctas[0];
+  g_cta_p->cur = 0;
+  threadIdx = g_tid[0];
+  blockIdx = g_cta_p->bid;
+  simt_switch(&g_main_sp, g_cta_p->fib[0].sp);
+  for (Cta* c : g_ctas) if (c->alive != 0) { g_cta_p = c; deadlock("returned to the launcher with live threads"); }
+}
+
+static void set_tids(dim3 block, int nt) {
+  for (int t = 0; t < nt; ++t) { g_tid[t].x = t % block.x; g_tid[t].y = (t / block.x) % block.y; g_tid[t].z = t / (block.x * block.y); }
+}
+
+void launch_impl(const char* name, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  const int nt = (int) (block.x * block.y * block.z);
+  if (nt <= 0 || nt > MAX_THREADS) { std::fprintf(stderr, "simt: bad block size %d\n", nt); std::abort(); }
+  blockDim = block; gridDim = grid;
+  set_tids(block, nt);
+  g_concurrent = false;
+  g_ctas.assign(1, &g_cta_seq);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-        c.nthreads = nt; c.alive = nt; c.bar_arrived = 0;
-        for (int w = 0; w < (nt + 31) / 32; ++w) { c.warps[w].nslots = 0; for (auto& s : c.warps[w].slots) { s.mask = 0; s.arrived = 0; s.departed = 0; s.draining = false; } }
-        for (int t = 0; t < nt; ++t) {
-          Fiber& f = c.fib[t];
-          f.done = false;
-          uintptr_t top = ((uintptr_t) (f.stack + STACK_BYTES)) & ~(uintptr_t) 15;
-          void** sp = (void**) top;
-          *--sp = nullptr;                    // fake return address of fiber_main (keeps the ABI stack alignment)
-          *--sp = (void*) &fiber_main;        // popped by `ret` in simt_switch
-          for (int k = 0; k < 6; ++k) *--sp = nullptr;   // rbp rbx r12 r13 r14 r15
-          f.sp = sp;
-        }
-        g_spins = 0;
-        c.cur = 0;
-        threadIdx = g_tid[0];
-        simt_switch(&c.main_sp, c.fib[0].sp);
-        if (c.alive != 0) deadlock("returned to the launcher with live threads");
+        uint3 bid; bid.x = bx; bid.y = by; bid.z = bz;
+        init_cta(g_cta_seq, name, nt, smem, body, bid);
+        run_live_ctas();
       }
+  g_cta_p = &g_cta_seq;
+}
+
+// All CTAs of a 1-D grid live at once (a kernel whose CTAs wait for each other). The kernel must not use static
+// __shared__ variables (they would be shared by all CTAs here).
+void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem, const std::function<void()>& body) {
+  const int nt = (int) (block.x * block.y * block.z);
+  if (nt <= 0 || nt > MAX_THREADS || nctas < 1 || nctas > 16) { std::fprintf(stderr, "simt: bad concurrent launch (%d CTAs x %d threads)\n", nctas, nt); std::abort(); }
+  blockDim = block; gridDim = dim3(nctas, 1, 1);
+  set_tids(block, nt);
+  static std::vector<Cta*> pool;
+  while ((int) pool.size() < nctas) pool.push_back(new Cta());
+  g_ctas.assign(pool.begin(), pool.begin() + nctas);
+  for (int c = 0; c < nctas; ++c) { uint3 bid; bid.x = c; bid.y = 0; bid.z = 0; init_cta(*g_ctas[c], name, nt, smem, body, bid); }
+  g_concurrent = true;
+  run_live_ctas();
+  g_concurrent = false;
+  g_ctas.assign(1, &g_cta_seq);
+  g_cta_p = &g_cta_seq;
 }
 }  // namespace simt
 
@@ -161,7 +213,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0;
   int cls_max[5] = {CLS_S_MAX, CLS_M_MAX, CLS_L1_MAX, CLS_L2_MAX, CLS_L3_MAX};
   std::string last_launches;
 };
@@ -204,6 +256,7 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "part_ilp") t->part_ilp = v;
   else if (n == "front") t->front = v;
   else if (n == "front_w") t->front_w = v;
+  else if (n == "front_concurrent") t->front_concurrent = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -262,8 +315,9 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     for (int k = 0; k < nitems; ++k) if (fitems[k].tf < 0) { std::fprintf(stderr, "simt_twin: k_front_plan left item %d unset\n", k); std::abort(); }
     FrontArgs fa{d_pts, ft, states, g, ap, has_intensity, nbp, nb, t->fast ? 1 : 0, bin_ids.data(), chist.data(), cbase.data(), bin_off.data(), wq, fits.data(),
                  sorted.data(), fitems.data(), nitems, fctr.data(), nframes};
-    const size_t sm_f = std::max((size_t) (CHUNK_THREADS / 32) * nbp, (size_t) nbp + 1) * sizeof(unsigned int);
-    simt::launch("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });
+    const size_t sm_f = front_smem_bytes(nbp);
+    if (t->front_concurrent) simt::launch_concurrent("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });   // CTAs interleave and wait for each other
+    else simt::launch("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });
     if (fctr[0] < nitems) { std::fprintf(stderr, "simt_twin: k_front stopped at item %d of %d\n", fctr[0], nitems); std::abort(); }
   } else {
   if (max_chunks > 0) {

@@ -82,14 +82,15 @@ def test_kernel_variants(kitti, opts):
 def test_persistent_front_end_is_identical(kitti):
     """PWPP_FRONT: binning + scan + scatter as one persistent kernel over an ordered work list (pwpp_front.cuh), for several
     pipeline depths W, with empty / one-point / ragged frames: bin ids, index lists and patch records identical to the
-    three stand-alone kernels. (The twin runs CTAs one after another, so an item that had to wait for a LATER item would be
-    reported as a deadlock: the list order is what is checked here; the spin-waits themselves need a GPU.)"""
+    three stand-alone kernels."""
     import synth
     frames = [kitti[1], np.zeros((0, 4), np.float32), synth.make_frame(5, 1).numpy(), np.array([[5, 0, -1.7, 0.5]], np.float32), kitti[2][:50000],
               synth.make_frame(5, 2).numpy()[:4096]]
     a = SimtTwin(num_streams=len(frames)); a.estimate_multi(frames)
-    for w in (1, 2, 5, 20):
-        b = SimtTwin(num_streams=len(frames), front=1, front_w=w, persistent_ctas=3); b.estimate_multi(frames)
+    # (W, CTAs, concurrent): sequential CTAs check the list order; concurrent CTAs (all live at once, fibers of all of them
+    # interleaved) really wait for each other on the hist_done / scan_done counters
+    for w, nc, conc in ((1, 3, 0), (5, 3, 0), (1, 4, 1), (2, 3, 1), (20, 5, 1)):
+        b = SimtTwin(num_streams=len(frames), front=1, front_w=w, persistent_ctas=nc, front_concurrent=conc); b.estimate_multi(frames)
         for f in range(len(frames)):
             a.select(f); b.select(f)
             assert np.array_equal(a.bin_ids(), b.bin_ids())
