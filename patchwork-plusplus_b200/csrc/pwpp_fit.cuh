@@ -3,19 +3,20 @@
 // Reference: cpp/patchworkpp/src/patchworkpp.cpp ("S:") extract_piecewiseground 467-549, extract_initial_seeds
 // 77-149, estimate_plane 47-75, calc_point_to_plane_d 551-554; the per-bin sort at S:199 is not needed (see below).
 //
-// Design (B200): a patch's points are loaded ONCE from HBM/L2 into registers and every pass of the iterative fit
-// runs out of registers. Patches are grouped by size into classes served by three persistent kernels that pull work
-// items from device-side queues built by k_bin_scan:
-//     class S   n <= 64     8 lanes x 8 points in registers,  32 patches per CTA   (k_fit_resident)
-//     class M   n <= 512    1 warp  x 16 points in registers,  8 patches per CTA   (k_fit_resident)
-//     class L1  n <= 2048   1 warp per patch, points streamed from L2, 4 loads in flight (k_fit_warp<false>)
-//     class L2  n <= 4096   1 CTA, points staged in 48 KB of shared memory         (k_fit_cta)
-//     class L3  n <= 8192   1 CTA, points staged in 96 KB of shared memory         (k_fit_cta)
-//     class X   n >  8192   streaming fallback (k_fit_stream, points re-read from L2 each pass)
-// All patches of a CTA advance in lock-step "rounds"; a round is one pass over the points (seed selection or
-// distance filter + moment accumulation in double) followed by ONE pooled eigen-solve in which lane i of warp 0
-// solves the 3x3 problem of patch i — the serial Jacobi SVD therefore costs one instruction stream per CTA and
-// round instead of one per patch.
+// Design (B200): patches are grouped by size into classes, each served by a persistent kernel that pulls self-describing
+// work items (frame, bin, size, offset) from a device-side queue filled by k_bin_scan, so that every class keeps its points
+// in the fastest storage they fit in and re-reads HBM never:
+//     class S   n <= 64     k_fit_resident: 8 lanes x 8 points in registers, 4 patches per warp, no block barriers
+//     class M   n <= 512    k_fit_warp<STAGE>: one warp per patch, patch staged once in 8 KB of shared memory
+//     class L1  n <= 2048   k_fit_warp: one warp per patch, points streamed from L2, 4 loads in flight per lane
+//     class L2  n <= 4096   k_fit_cta: one CTA per patch, SoA coordinates in 48 KB of shared memory
+//     class L3  n <= 8192   k_fit_cta: 96 KB of shared memory
+//     class X   n >  8192   k_fit_big (pwpp_fit_big.cuh): one CTA per patch streaming from L2 (dense sensors);
+//                           k_fit_stream below is the one-warp-per-patch fallback (PWPP_X_KERNEL=0)
+// A patch advances in "rounds": one pass over its points (seed selection or distance filter + moment accumulation in
+// double) followed by ONE closed-form 3x3 eigen-solve (pwpp_math.cuh). R-GPF rounds are incremental (only points whose
+// membership changed touch the double-precision sums) and stop at the exact fixpoint; zone-0 patches fuse the R-VPF fit
+// with the R-GPF seed fit (FUSE, see k_fit_warp).
 //
 // What replaces the reference's sort: the z-sorted order is only used for (a) the count of points below the
 // adaptive margin in zone 0 (S:88-96), (b) the mean of the num_lpr lowest remaining z (S:99-103) and (c) the
@@ -78,8 +79,7 @@ __device__ __forceinline__ unsigned kth_key(unsigned kmin, unsigned kmax, int ta
 }
 
 // ---- group-wide reductions -------------------------------------------------------------------------
-// G = 8: four independent groups per warp (butterfly inside 8-lane segments); G = 32: one warp;
-// G = 256: one CTA (warp butterfly + shared memory exchange, all threads get the result).
+// G = 8: four independent groups per warp (butterfly inside 8-lane segments); G = 32: one warp.
 template <int G>
 struct GroupOps;
 
@@ -113,34 +113,6 @@ struct GroupOps<32> {
     return v;
   }
 };
-template <>
-struct GroupOps<256> {
-  // scratch: 8 doubles + 8 ints of shared memory, two barriers per call
-  __device__ static __forceinline__ int sum_i(int v, void* scratch) {
-    int* s = reinterpret_cast<int*>(scratch);
-    v = __reduce_add_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int t = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += s[w];
-    __syncthreads();
-    return t;
-  }
-  __device__ static __forceinline__ double sum_d(double v, void* scratch) {
-    double* s = reinterpret_cast<double*>(scratch);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += s[w];
-    __syncthreads();
-    return t;
-  }
-};
-
 enum FitState { ST_RVPF = 0, ST_SEED = 1, ST_GPF = 2, ST_FINAL = 3, ST_DONE = 4 };
 
 // The plane solve (estimate_plane, S:47-75, from moment sums) is ~1.5k SASS instructions. Inlined at every call site it

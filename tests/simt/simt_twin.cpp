@@ -214,7 +214,6 @@ struct SimtTwin {
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
   int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0;
-  int cls_max[5] = {CLS_S_MAX, CLS_M_MAX, CLS_L1_MAX, CLS_L2_MAX, CLS_L3_MAX};
   std::string last_launches;
 };
 
