@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--ref-frames-per-step", type=int, default=0, help="--impl reference: frames per step (0 = 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streaming", default="", help="also time streaming mode 'SxT': S sensor streams x T consecutive frames each, T batched calls with the temporal state carried (SURVEY.md 8d config 3), e.g. 64x16; reported under the key 'streaming'")
     return ap.parse_args()
 
 
@@ -313,6 +314,32 @@ def run_ours(args):
                "d2h_bytes_per_step": total_pts * 4 + 3 * F * 4, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": "pwpp_estimate_host + pwpp_copy_*_indices (C-ABI), page-locked host buffers"}
 
+    # ---- optional: streaming mode, S streams x T consecutive frames (state carried from call to call) ----
+    streaming = None
+    if args.streaming:
+        try:
+            S, T = (int(x) for x in args.streaming.lower().split("x"))
+            assert 1 <= S and 1 <= T and S * T <= F, "needs S*T <= --frames-per-gpu"
+            seng = pwpp_b200.Engine(device=local, num_streams=S, max_points_per_frame=int(np.diff(offs_np).max()))
+            calls = [(int(offs_np[t * S]), (offs_np[t * S:(t + 1) * S + 1] - offs_np[t * S]).copy()) for t in range(T)]
+
+            def sequence():
+                seng.reset()
+                for first, o in calls:   # call t: frame t of every stream; stream order serialises consecutive frames
+                    seng.estimate_device(pts.data_ptr() + first * 16, o, True, stream)
+            sequence(); torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(3):
+                sequence()
+            s1.record(); torch.cuda.synchronize()
+            sms = dist.max_over_ranks(s0.elapsed_time(s1) / 3)
+            streaming = {"streams": S, "frames_per_stream": T, "ms_per_sequence": sms, "value": world * S * T / (sms / 1e3), "unit": UNIT,
+                         "ms_per_call": sms / T, "note": "T batched calls of S frames, adaptive state carried between calls"}
+            seng.close()
+        except Exception as ex:   # an extra: never costs the main line
+            streaming = {"error": repr(ex)[:200]}
+
     # ---- CPU baseline on the host cores of this box (rank 0 only) ----
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -331,6 +358,8 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {total_pts * 16 / 1e9:.2f} GB of points per step vs 126 MB L2"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if streaming is not None:
+            out["streaming"] = streaming
         print(json.dumps(out), flush=True)
     # orderly teardown: release the engine (CUDA buffers, streams) while the CUDA context is still alive
     eng.close()
