@@ -98,7 +98,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0, sw_l2_wide = 0;
   int front_grid = 0;
   DevBuf<FrontItem> d_front_items;
   DevBuf<int> d_front_ctr;
@@ -270,7 +270,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     CU_TRY(cudaMemsetAsync(ctx->d_front_ctr.p, 0, ((size_t) 1 + 2 * nf) * sizeof(int), s));
     k_front_plan<<<(nf + W + 127) / 128, 128, 0, s>>>(ft.chunk_off, nf, W, ctx->d_front_items.p);
     FrontArgs fa{d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->fast_bin ? 1 : 0, ctx->d_bin_ids.p, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits,
-                 ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->d_front_ctr.p, nf};
+                 ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->sw_l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, ctx->d_front_ctr.p, nf};
     const size_t sm_f = front_smem_bytes(nbp);
     k_front<<<ctx->front_grid, FRONT_THREADS, sm_f, s>>>(fa);
     ctx->launches += 2;
@@ -288,7 +288,8 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     ++ctx->launches;
   }
   STAGE_MARK();
-  k_bin_scan<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
+  if (ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
+  else k_bin_scan<CLS_L2_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
   ++ctx->launches;
   STAGE_MARK();
   if (max_chunks > 0) {
@@ -465,6 +466,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
   ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", PWPP_EMIT_SPLIT_DEFAULT, 1, 32);
   ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);
+  ctx->sw_l2_wide = env_int("PWPP_L2_WIDE", PWPP_L2_WIDE_DEFAULT, 0, 1);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -546,10 +548,13 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true> : k_fit_cta<4096, 3, 3, 8, true>, 0, FIT_THREADS, sm_l2};
       ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
     }
+    if (ctx->sw_l2_wide && fuse_seed && ctx->fit[3].threads == FIT_THREADS) {   // PWPP_L2_WIDE: class L2 = 2049..5888 points at 3 CTAs/SM
+      ctx->fit[3] = {k_fit_cta<CLS_L2_WIDE_MAX, 3, 3, 8, true>, 0, FIT_THREADS, (size_t) 3 * CLS_L2_WIDE_MAX * sizeof(float)};
+    } else ctx->sw_l2_wide = 0;   // (only with the fused 8-warp CTA kernel)
     if (part_ilp) {
       if (!fuse_warp && !solve_call && m_minb == 2) ctx->fit[1].fn = k_fit_warp<true, 1, 1, 2, 2, false, false, true>;
       if (!fuse_warp && !solve_call && l1_minb == 2) ctx->fit[2].fn = k_fit_warp<false, 2, 2, FITW_U, 2, false, false, true>;
-      if (fuse_seed && l2_minb == 3 && ctx->fit[3].threads == FIT_THREADS) ctx->fit[3].fn = k_fit_cta<4096, 3, 3, 8, true, true>;
+      if (fuse_seed && l2_minb == 3 && ctx->fit[3].threads == FIT_THREADS && !ctx->sw_l2_wide) ctx->fit[3].fn = k_fit_cta<4096, 3, 3, 8, true, true>;
       if (fuse_seed && ctx->fit[4].threads == FIT_THREADS) ctx->fit[4].fn = k_fit_cta<8192, 4, 2, 8, true, true>;
     }
     for (int c = 0; c < NUM_CLASSES; ++c) {

@@ -31,6 +31,10 @@ namespace pwpp {
 
 constexpr int FIT_THREADS = 256;
 constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 4096, CLS_L3_MAX = 8192;
+// PWPP_L2_WIDE: the L2 class reaches up to this many points — the largest patch whose SoA coordinates (12 B/point) still leave
+// room for 3 CTAs per SM next to the kernel's static shared memory. r01: an L3 patch (2 CTAs/SM at 96 KB) costs 3x an L2 patch
+// for 1.8x the points, and most L3 patches are below 6k points.
+constexpr int CLS_L2_WIDE_MAX = 5888;
 constexpr int NUM_CLASSES = 6;  // S, M, L1, L2, L3, X
 
 // device-side work queues, filled by k_bin_scan. An item describes one patch completely, so that a fit kernel needs

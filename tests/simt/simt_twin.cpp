@@ -213,7 +213,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0;
   std::string last_launches;
 };
 
@@ -256,6 +256,7 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "front") t->front = v;
   else if (n == "front_w") t->front_w = v;
   else if (n == "front_concurrent") t->front_concurrent = v;
+  else if (n == "l2_wide") t->l2_wide = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -313,7 +314,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     simt::launch("k_front_plan", (nframes + W + 127) / 128, 128, 0, [&] { k_front_plan(chunk_off.data(), nframes, W, fitems.data()); });
     for (int k = 0; k < nitems; ++k) if (fitems[k].tf < 0) { std::fprintf(stderr, "simt_twin: k_front_plan left item %d unset\n", k); std::abort(); }
     FrontArgs fa{d_pts, ft, states, g, ap, has_intensity, nbp, nb, t->fast ? 1 : 0, bin_ids.data(), chist.data(), cbase.data(), bin_off.data(), wq, fits.data(),
-                 sorted.data(), fitems.data(), nitems, fctr.data(), nframes};
+                 sorted.data(), fitems.data(), nitems, t->l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, fctr.data(), nframes};
     const size_t sm_f = front_smem_bytes(nbp);
     if (t->front_concurrent) simt::launch_concurrent("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });   // CTAs interleave and wait for each other
     else simt::launch("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });
@@ -328,8 +329,10 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     else simt::launch("k_bin_hist<true,2>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 2>(HIST_ARGS); });
 #undef HIST_ARGS
   }
-  simt::launch("k_bin_scan", nframes, 512, (nbp + 1) * sizeof(int),
-               [&] { k_bin_scan(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
+  if (t->l2_wide) simt::launch("k_bin_scan<5888>", nframes, 512, (nbp + 1) * sizeof(int),
+               [&] { k_bin_scan<CLS_L2_WIDE_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
+  else simt::launch("k_bin_scan", nframes, 512, (nbp + 1) * sizeof(int),
+               [&] { k_bin_scan<CLS_L2_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
   if (max_chunks > 0) {
     dim3 grid(max_chunks, nframes);
     const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
@@ -342,6 +345,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
+  if (t->l2_wide) simt::launch("k_fit_cta<5888,3,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * CLS_L2_WIDE_MAX * sizeof(float), [&] { k_fit_cta<CLS_L2_WIDE_MAX, 3, 3, 8, true>(FIT_ARGS); });
   if (t->part_ilp) {   // PWPP_PART_ILP variants of the default shapes drain the queues first
     simt::launch("k_fit_cta<8192,4,2,8,fuse,pilp>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true, true>(FIT_ARGS); });
     simt::launch("k_fit_cta<4096,3,3,8,fuse,pilp>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true, true>(FIT_ARGS); });

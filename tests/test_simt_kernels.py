@@ -70,7 +70,7 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1), dict(emit_split=8), dict(part_ilp=1)])
+@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1), dict(emit_split=8), dict(part_ilp=1), dict(l2_wide=1)])
 def test_kernel_variants(kitti, opts):
     """The A/B variants selectable through PWPP_* switches give the same result as the defaults."""
     a = kitti[3]
@@ -135,6 +135,22 @@ def test_big_patches(opts):
         assert _check(orc, tw, cases[k], f"big/{k}/{opts}") == 0
 
 
+def test_wide_l2_class_boundaries():
+    """PWPP_L2_WIDE: patches of 4097..5888 points move from the L3 to the L2 class (k_fit_cta<5888>); sizes on both sides of
+    every boundary give the same records as the default classes."""
+    rng = np.random.default_rng(2)
+    mk = lambda n: np.c_[5 + rng.random(n) * 0.5, rng.random(n) * 0.5, -1.7 + rng.normal(0, 0.02, n), rng.random(n)].astype(np.float32)  # noqa: E731
+    frames = [mk(n) for n in (4096, 4097, 5000, 5888, 5889, 8192, 8193)]
+    a, b = SimtTwin(num_streams=len(frames)), SimtTwin(num_streams=len(frames), l2_wide=1, part_ilp=1)
+    a.estimate_multi(frames); b.estimate_multi(frames)
+    assert a.queue_sizes() != b.queue_sizes()
+    for f in range(len(frames)):
+        a.select(f); b.select(f)
+        assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and bytes(a.bin_results()) == bytes(b.bin_results())
+        orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(frames[f])
+        assert _check(orc, b, frames[f], f"wide/{f}") == 0
+
+
 def test_dense_frame():
     """BASELINE config-5 shape: one ~1.4M-point frame (27 class-X patches) through every kernel."""
     import synth
@@ -194,7 +210,7 @@ def test_random_parameter_sets(kitti, seed):
     p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([4, 8, 16, 32, 54, 64], 4)]
     p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 6, 4)]
     opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 3, 8])), solve_call=int(rng.integers(0, 2)),
-                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)))
+                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
     pool = [kitti[0], kitti[4], synth.make_frame(7, 0).numpy()]
     orc, tw = O.Oracle(p, O.ARITH_CANON64), SimtTwin(p, **opts)
