@@ -1097,6 +1097,87 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
+// warp_lpr with the loads of both scans batched four at a time (PWPP_PART_ILP): the r01 capture of the L1 kernel (points
+// streamed from L2) shows 12 % of its stall samples on the one-load-per-iteration z reads of these two loops.
+__device__ double warp_lpr_batched(const float4* __restrict__ P, int n, int nit, bool any_removed, const unsigned* __restrict__ alive_w, bool zone0,
+                                   double margin_z, int num_lpr, float* sel_buf) {
+  const int lane = lane_id();
+  const unsigned lt = lanemask_lt();
+  unsigned* cbuf = reinterpret_cast<unsigned*>(sel_buf);
+  if (num_lpr > 32) return warp_lpr_fallback(P, n, nit, any_removed, alive_w, zone0, margin_z, num_lpr, sel_buf);
+  unsigned kminL = 0xffffffffu;
+  int nv = 0;
+  for (int it0 = 0; it0 < nit; it0 += 4) {
+    float zv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = (it0 + u) * 32 + lane; zv[u] = P[j < n ? j : n - 1].z; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int it = it0 + u, j = it * 32 + lane;
+      bool valid = j < n;
+      if (any_removed && it < nit) valid = valid && ((alive_w[it] >> lane) & 1u);
+      if (zone0 && ((double) zv[u] < margin_z)) valid = false;
+      if (valid) { kminL = min(kminL, order_key(zv[u])); ++nv; }
+    }
+  }
+  const int nvalid = __reduce_add_sync(0xffffffffu, nv);
+  const int target = nvalid < num_lpr ? nvalid : num_lpr;
+  if (target == 0) return 0.0;
+  const int have = __reduce_add_sync(0xffffffffu, kminL != 0xffffffffu ? 1 : 0);
+  unsigned T = 0xffffffffu;
+  if (have >= target) {
+    const unsigned gmn = __reduce_min_sync(0xffffffffu, kminL);
+    const unsigned gmx = __reduce_max_sync(0xffffffffu, kminL != 0xffffffffu ? kminL : 0u);
+    T = kth_key(gmn, gmx, target, [&](unsigned cand) { return __reduce_add_sync(0xffffffffu, kminL < cand ? 1 : 0); });
+  }
+  int cc = 0;
+  for (int it0 = 0; it0 < nit; it0 += 4) {
+    float zv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = (it0 + u) * 32 + lane; zv[u] = P[j < n ? j : n - 1].z; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int it = it0 + u, j = it * 32 + lane;
+      if (it >= nit) break;   // uniform
+      bool valid = j < n;
+      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
+      if (zone0 && ((double) zv[u] < margin_z)) valid = false;
+      const unsigned key = order_key(zv[u]);
+      const bool c = valid && key <= T;
+      const unsigned bal = __ballot_sync(0xffffffffu, c);
+      if (c) { const int pos = cc + __popc(bal & lt); if (pos < 128) cbuf[pos] = key; }
+      cc += __popc(bal);
+    }
+  }
+  __syncwarp();
+  if (cc > 128) return warp_lpr_fallback(P, n, nit, any_removed, alive_w, zone0, margin_z, num_lpr, sel_buf);
+  unsigned ck[4];
+  unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    ck[q] = i < cc ? cbuf[i] : 0xffffffffu;
+    if (i < cc) { kmn = min(kmn, ck[q]); kmx = max(kmx, ck[q]); }
+  }
+  kmn = __reduce_min_sync(0xffffffffu, kmn);
+  kmx = __reduce_max_sync(0xffffffffu, kmx);
+  const unsigned ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cnt += ck[q] < cand;
+    return __reduce_add_sync(0xffffffffu, cnt);
+  });
+  double ps = 0.0;
+  int c_lt = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (ck[q] < ans) { ps += (double) key_to_float(ck[q]); ++c_lt; }
+  ps = warp_sum(ps);
+  c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+  const double lpr = (ps + (double) (target - c_lt) * (double) key_to_float(ans)) / (double) target;
+  __syncwarp();
+  return lpr;
+}
+
 template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false, bool NL = false, bool PILP = false>
 __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
@@ -1184,7 +1265,8 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
       const bool rvpf_round = rvpf_left > 0;
       const bool fused = fuse_ok && rvpf_round;
       // LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103)
-      const double lpr = warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
+      const double lpr = (PILP && !STAGE) ? warp_lpr_batched(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf)
+                                          : warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
       const double zthr = lpr + (rvpf_round ? ap.th_seeds_v : ap.th_seeds);
       const double zin = lpr + ap.th_seeds;   // inner (R-GPF seed) threshold of a fused round
       c[2] = lpr;
