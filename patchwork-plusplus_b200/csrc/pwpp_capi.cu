@@ -264,7 +264,8 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     const int nitems = 2 * total_chunks + nf;
     const long long pts_in_range = ctx->pt_off[f0 + nf] - ctx->pt_off[f0];
     const long long per_frame = std::max(1LL, pts_in_range / nf) * 16;
-    const int W = (int) std::max(1LL, std::min((long long) nf, (32LL << 20) / per_frame));   // scatter runs ~32 MB of points behind the binning pass
+    static const long long window_mb = env_int("PWPP_FRONT_WINDOW_MB", 32, 1, 96);   // how far (MB of points) the scatter trails the binning pass: must stay L2-resident
+    const int W = (int) std::max(1LL, std::min((long long) nf, (window_mb << 20) / per_frame));
     CU_TRY(ctx->d_front_items.reserve((size_t) nitems + 1));
     CU_TRY(ctx->d_front_ctr.reserve((size_t) 1 + 2 * nf));
     CU_TRY(cudaMemsetAsync(ctx->d_front_ctr.p, 0, ((size_t) 1 + 2 * nf) * sizeof(int), s));
