@@ -3,6 +3,9 @@ default configuration returns. NOT part of the default `-m gpu` run: these varia
 twin so far (tests/test_simt_kernels.py); run it explicitly, under a timeout, with
 
     PWPP_TEST_VARIANTS=1 timeout 300 python -m pytest tests/test_gpu_variants.py -m gpu -q
+
+tools/gpu_round_end.sh runs every variant in its OWN process under its own timeout (a variant that hangs the GPU kills only
+its process) and hands the list of variants that passed to tools/gpu_tune.py.
 """
 import os
 
@@ -28,7 +31,7 @@ def _frames(kitti):
     import synth
     rng = np.random.default_rng(5)
     big = np.c_[5 + rng.random(20000) * 0.5, rng.random(20000) * 0.5, -1.7 + rng.normal(0, 0.02, 20000), rng.random(20000)].astype(np.float32)
-    return [kitti[0], kitti[3], np.zeros((0, 4), np.float32), synth.make_frame(9, 0).numpy(), big, kitti[5][:4097], synth.make_frame(5, 0, "dense1m").numpy()]
+    return [kitti[0], kitti[3], np.zeros((0, 4), np.float32), synth.make_frame(9, 0).numpy(), big, kitti[5][:4097], synth.make_frame(5, 0, "dense1m", "cuda").cpu().numpy()]
 
 
 def _run(env, frames):

@@ -7,7 +7,18 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 leg() { echo "$1 rc=$2 t=$((SECONDS-t0))s" | tee -a gpurun_out/legs.txt; }
 : > gpurun_out/legs.txt
-t0=$SECONDS; timeout 110 python tools/gpu_tune.py 1024 5 32 > gpurun_out/tune.log 2>&1; leg tune $?
+# (0) the switched-off variants, each in its own process and under its own timeout; only those that reproduce the default
+#     configuration's results bit for bit may be timed and chosen by the tuner
+: > gpurun_out/variants_ok.txt
+if [ "${SKIP_VARIANTS:-0}" != "1" ]; then
+  t0=$SECONDS
+  for v in "FRONT=1" "PART_ILP=1" "EMIT_SPLIT=8" "SOLVE_CALL=1" "L2_WIDE=1" "FUSE_SEED=3" "FUSE_SEED=0,L2_MINB=4"; do
+    if PWPP_TEST_VARIANTS=1 timeout 120 python -m pytest -m gpu -q -p no:cacheprovider "tests/test_gpu_variants.py::test_variant_equals_default[$v]" > gpurun_out/variant_${v//[=,]/_}.log 2>&1 && grep -q "1 passed" gpurun_out/variant_${v//[=,]/_}.log; then echo "$v" >> gpurun_out/variants_ok.txt; fi
+  done
+  leg variants $?; cat gpurun_out/variants_ok.txt
+fi
+export PWPP_TUNE_ALLOW_FILE=gpurun_out/variants_ok.txt
+t0=$SECONDS; timeout 150 python tools/gpu_tune.py 1024 5 32 > gpurun_out/tune.log 2>&1; leg tune $?
 [ -f gpurun_out/chosen.env ] && source gpurun_out/chosen.env
 env | grep '^PWPP_' | sort > gpurun_out/chosen_effective.txt
 t0=$SECONDS; timeout 150 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; leg pytest $?

@@ -57,6 +57,22 @@ def measure(cfg, pts, offs_np, nf, k, label):
     return line
 
 
+# Switched-off variants are only candidates when tests/test_gpu_variants.py passed for them on this GPU (one line per
+# variant id, e.g. "FRONT=1", written by tools/gpu_round_end.sh); without the file every candidate is tried.
+UNMEASURED = {"PWPP_FRONT", "PWPP_PART_ILP", "PWPP_EMIT_SPLIT", "PWPP_SOLVE_CALL", "PWPP_L2_WIDE"}
+_allow_file = os.environ.get("PWPP_TUNE_ALLOW_FILE", "")
+ALLOWED = None
+if _allow_file and os.path.exists(_allow_file):
+    ALLOWED = set()
+    for line in open(_allow_file):
+        for kv in line.strip().split(","):
+            if "=" in kv: ALLOWED.add("PWPP_" + kv.split("=")[0])
+
+
+def permitted(cfg):
+    return ALLOWED is None or all(k not in UNMEASURED or k in ALLOWED for k in cfg)
+
+
 chosen = {}
 # ---------------- BASELINE config 3: batch of KITTI-64-shaped frames ----------------
 pts, offs = synth.make_batch(20260922, 0, F, "kitti64", "cuda")
@@ -82,6 +98,8 @@ candidates = [
 best = {}   # stage group -> (gain, cfg)
 if "error" not in base:
     for cfg, stages in candidates:
+        if not permitted(cfg):
+            continue
         r = measure(cfg, pts, offs_np, F, K, "kitti/candidate")
         if "error" in r or r["sig"] != base["sig"]:
             continue
@@ -113,6 +131,8 @@ if FD > 0:
     old = measure({"PWPP_X_KERNEL": "0", **chosen}, pts, offs_np, FD, 2, "dense/one-warp-per-patch")
     res = []
     for x in ({}, {"PWPP_X_MINB": "2"}, {"PWPP_X_NW": "32"}, {"PWPP_EMIT_SPLIT": "8"}, {"PWPP_EMIT_SPLIT": "16"}):
+        if not permitted(x):
+            continue
         r = measure({"PWPP_X_KERNEL": "1", **x, **chosen}, pts, offs_np, FD, 3, "dense/cta-per-patch")
         if "error" not in r and "error" not in old and r["sig"] == old["sig"]:
             res.append((r["ms_per_step"], x))
