@@ -558,6 +558,10 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       if (fuse_seed && l2_minb == 3 && ctx->fit[3].threads == FIT_THREADS && !ctx->sw_l2_wide) ctx->fit[3].fn = k_fit_cta<4096, 3, 3, 8, true, true>;
       if (fuse_seed && ctx->fit[4].threads == FIT_THREADS) ctx->fit[4].fn = k_fit_cta<8192, 4, 2, 8, true, true>;
     }
+    // PWPP_L2_PLS: class L2 with the current plane in shared memory instead of 20 registers per thread (fewer spills at 3 and at
+    // 4 CTAs/SM); only for the plain fused 4096-point shape
+    if (env_int("PWPP_L2_PLS", PWPP_L2_PLS_DEFAULT, 0, 1) && fuse_seed && !ctx->sw_l2_wide && !part_ilp && ctx->fit[3].threads == FIT_THREADS)
+      ctx->fit[3].fn = l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true, false, true> : k_fit_cta<4096, 3, 3, 8, true, false, true>;
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];
       if (k.smem > 0) CU_TRY_CTX(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k.smem));

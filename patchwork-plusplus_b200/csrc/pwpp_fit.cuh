@@ -368,7 +368,10 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // cross-warp prefix. The LPR selection is two-level: the num_lpr-th smallest of the 256 per-thread minima bounds
 // the num_lpr-th smallest point from above, so only the few points not above that bound are gathered and
 // selected exactly by one warp.
-template <int CAP, int CLS, int MINB, int NW, bool FUSE = false, bool PILP = false>
+// PLS (PWPP_L2_PLS): the current plane lives in shared memory (s_plane) instead of 20 registers per thread — warp 0 rewrites it
+// in place between the two barriers of a round, when no other warp reads it — so that the fused kernel fits the 64-register
+// budget of 4 CTAs per SM with far fewer spills.
+template <int CAP, int CLS, int MINB, int NW, bool FUSE = false, bool PILP = false, bool PLS = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -441,10 +444,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
     int state = (ap.enable_RVPF && zone0) ? ST_RVPF : ST_SEED;
     int rvpf_it = 0, gpf_it = 0, n_ground = 0;
     bool have_plane = false;
-    Plane pl;
-    pl.d = 0.0;
+    Plane pl_reg;
+    Plane& pl = PLS ? s_plane : pl_reg;   // PLS: nobody depends on the plane before the first barrier of the first (seed) round
+    if (!PLS || tid == 0) {
+      pl.d = 0.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+      for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+    }
     unsigned gmask = 0, member = 0;
     int round = 0;
     double c_lpr = 0.0;
@@ -695,8 +701,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
           const bool hv = have_plane || mv.n > 0;
           const bool taken = !(hv && (mv.n > 0 ? vz : pl.normal[2]) < ap.uprightness_thr);   // S:489 false -> S:506 break
           if (taken) tot = mi; else tot = mv;
-          if (lane == 0) { s_plane = mine; s_mn = mv.n; s_refit = mv.n > 0 ? 1 : 0; s_fix = 0; s_taken = taken ? 1 : 0; }
-          if (lane == 16) { s_plane2 = mine; s_mni = mi.n; }
+          if (PLS) {   // the plane the next round uses goes straight to s_plane: the seed plane when taken and fitted, else the R-VPF plane
+            const bool seed_wins = taken && mi.n > 0;
+            if (lane == 0) { if (!seed_wins && mv.n > 0) s_plane = mine; s_mn = mv.n; s_refit = mv.n > 0 ? 1 : 0; s_fix = 0; s_taken = taken ? 1 : 0; }
+            if (lane == 16) { if (seed_wins) s_plane = mine; s_mni = mi.n; }
+          } else {
+            if (lane == 0) { s_plane = mine; s_mn = mv.n; s_refit = mv.n > 0 ? 1 : 0; s_fix = 0; s_taken = taken ? 1 : 0; }
+            if (lane == 16) { s_plane2 = mine; s_mni = mi.n; }
+          }
         } else if (w == LOOK_W && rvpf_it == 0) {
           if (nxt.x >= 0) prefetch_patch_l2(sorted + work_item_start(nxt), nxt.y, lane, 32);
         }
@@ -744,11 +756,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       __syncthreads();
       int tot_n = s_mn;
       const bool fixpoint = s_fix != 0;
-      if (s_refit) { pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
+      if (s_refit) { if (!PLS) pl = s_plane; have_plane = true; }   // S:49: an empty set keeps the previous plane
       // ---- state transition (same machine as k_fit_resident) ----
       if (FUSE && fused && s_taken) {   // upright R-VPF plane (S:506 break) + the seed fit of S:513-514 from the same pass
         tot_n = s_mni;
-        if (tot_n > 0) { pl = s_plane2; have_plane = true; }
+        if (tot_n > 0) { if (!PLS) pl = s_plane2; have_plane = true; }
         state = (ap.num_iter > 1) ? ST_GPF : ST_FINAL;
         gpf_it = 0;
       } else

@@ -22,6 +22,8 @@ VARIANTS = [
     {"PWPP_FUSE_SEED": "0", "PWPP_L2_MINB": "4"},
     {"PWPP_FUSE_SEED": "3"},
     {"PWPP_L2_WIDE": "1"},
+    {"PWPP_L2_PLS": "1"},
+    {"PWPP_L2_PLS": "1", "PWPP_L2_MINB": "4"},
     {"PWPP_FRONT": "1", "PWPP_PART_ILP": "1", "PWPP_EMIT_SPLIT": "4", "PWPP_SOLVE_CALL": "1", "PWPP_L2_WIDE": "1"},
 ]
 SWITCHES = sorted({k for v in VARIANTS for k in v})

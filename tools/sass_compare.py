@@ -25,5 +25,9 @@ da = {re.sub(r"\(.*", "", x).replace("void pwpp::", ""): a[n] for n, x in zip(a,
 db = {re.sub(r"\(.*", "", x).replace("void pwpp::", ""): b[n] for n, x in zip(b, names)}
 for k, v in db.items():
     if k in da: continue
-    k2 = re.sub(r", false>$", ">", k)
+    k2 = k
+    while k2 not in da and re.search(r", (false|\d+)>$", k2):   # template parameters appended since the old build (defaults)
+        k2 = re.sub(r", (false|\d+)>$", ">", k2)
+    if k2 == "k_bin_scan<4096>" or k2 not in da:
+        k2 = re.sub(r"<[^<>]*>$", "", k2) if re.sub(r"<[^<>]*>$", "", k2) in da else k2   # a kernel that became a template
     if k2 in da: print("IDENTICAL" if da[k2] == v else "DIFFERENT", len(da[k2]), len(v), k)
