@@ -1110,7 +1110,8 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
 }
 
 // warp_lpr with the loads of both scans batched four at a time (PWPP_PART_ILP): the r01 capture of the L1 kernel (points
-// streamed from L2) shows 12 % of its stall samples on the one-load-per-iteration z reads of these two loops.
+// streamed from L2) shows 12 % of its stall samples on the one-load-per-iteration z reads of these two loops; the exact
+// selection only compares the registers that hold candidates.
 __device__ double warp_lpr_batched(const float4* __restrict__ P, int n, int nit, bool any_removed, const unsigned* __restrict__ alive_w, bool zone0,
                                    double margin_z, int num_lpr, float* sel_buf) {
   const int lane = lane_id();
@@ -1173,10 +1174,11 @@ __device__ double warp_lpr_batched(const float4* __restrict__ P, int n, int nit,
   }
   kmn = __reduce_min_sync(0xffffffffu, kmn);
   kmx = __reduce_max_sync(0xffffffffu, kmx);
+  const int nq = (cc + 31) >> 5;   // registers per lane actually holding candidates (the r01 capture: 7 % of the M kernel's instructions are these compares)
   const unsigned ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
     int cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cnt += ck[q] < cand;
+    for (int q = 0; q < 4; ++q) { if (q >= nq) break; cnt += ck[q] < cand; }
     return __reduce_add_sync(0xffffffffu, cnt);
   });
   double ps = 0.0;
@@ -1277,7 +1279,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
       const bool rvpf_round = rvpf_left > 0;
       const bool fused = fuse_ok && rvpf_round;
       // LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103)
-      const double lpr = (PILP && !STAGE) ? warp_lpr_batched(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf)
+      const double lpr = PILP ? warp_lpr_batched(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf)
                                           : warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
       const double zthr = lpr + (rvpf_round ? ap.th_seeds_v : ap.th_seeds);
       const double zin = lpr + ap.th_seeds;   // inner (R-GPF seed) threshold of a fused round
