@@ -24,12 +24,13 @@ env | grep '^PWPP_' | sort > gpurun_out/chosen_effective.txt
 t0=$SECONDS; timeout 150 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; leg pytest $?
 t0=$SECONDS; timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; leg smoke $?
 t0=$SECONDS; timeout 100 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; leg bench $?
+t0=$SECONDS; timeout 60 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --streaming 64x16 > gpurun_out/bench_streaming.json 2> gpurun_out/bench_streaming.err; leg streaming $?
 t0=$SECONDS; timeout 60 python bench.py --sensor dense1m --frames-per-gpu 32 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_dense1m.json 2> gpurun_out/bench_dense1m.err; leg dense $?
 t0=$SECONDS; timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 33 -c 11 --csv --log-file gpurun_out/launches_1024frames.csv \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; leg ncu-launches $?
 CMD="python bench.py --frames-per-gpu 128 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-# the capture gets what is left of the session's time budget (DEADLINE seconds after start, default 250), minus the export
-left=$(( ${DEADLINE:-250} - SECONDS - 35 ))
+# the capture gets what is left of the session's time budget (DEADLINE seconds after start, default 600), minus the export
+left=$(( ${DEADLINE:-600} - SECONDS - 35 ))
 t0=$SECONDS
 if [ $left -gt 30 ]; then timeout $left ncu --set full --clock-control none --import-source on -k regex:k_ -s 33 -c 11 -f -o gpurun_out/full128 $CMD > gpurun_out/ncu_full.log 2>&1; leg ncu-full $?; else echo "ncu-full skipped (no time left)" | tee -a gpurun_out/legs.txt; fi
 if [ -f gpurun_out/full128.ncu-rep ]; then
