@@ -119,6 +119,7 @@ class SimtTwin(_Base):
         lib.simt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.simt_queue_sizes.argtypes = [C.c_void_p]; lib.simt_queue_sizes.restype = C.c_char_p
         lib.simt_estimate_multi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.simt_set_sched_seed.argtypes = [C.c_ulonglong]
         self._lib = lib
         self.params = params if params is not None else default_params()
         self._h = lib.simt_create(C.byref(self.params), num_streams)
@@ -143,6 +144,10 @@ class SimtTwin(_Base):
     def select(self, f):
         self._lib.simt_select(self._h, f)
         self._n = self._ns[f]
+
+    def set_sched_seed(self, seed: int):
+        """Non-zero: concurrently live CTAs are interleaved at random (per seed) instead of round-robin. Process-wide."""
+        self._lib.simt_set_sched_seed(seed)
 
     def queue_sizes(self):
         return self._lib.simt_queue_sizes(self._h).decode()

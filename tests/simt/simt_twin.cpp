@@ -67,9 +67,23 @@ static unsigned long long total_progress() {
   return p;
 }
 
+// With a non-zero seed a yielding fiber hands over to a RANDOM live fiber of a random live CTA instead of the next one in
+// round-robin order: different seeds give different interleavings of concurrently live CTAs (simt_set_sched_seed).
+static unsigned long long g_sched_state = 0;
+static inline unsigned sched_rand() {
+  g_sched_state = g_sched_state * 6364136223846793005ull + 1442695040888963407ull;
+  return (unsigned) (g_sched_state >> 33);
+}
 // next live fiber after (cta ci, thread ti) in round-robin order over all live CTAs; false if there is none but itself
 static bool next_fiber(int ci, int ti, int& nci, int& nti) {
   const int nc = (int) g_ctas.size();
+  if (g_sched_state != 0 && g_concurrent) {
+    for (int tries = 0; tries < 8; ++tries) {   // a few random probes, then fall back to the round-robin scan
+      const int c = (int) (sched_rand() % (unsigned) nc);
+      const int t = (int) (sched_rand() % (unsigned) g_ctas[c]->nthreads);
+      if (!(c == ci && t == ti) && !g_ctas[c]->fib[t].done) { nci = c; nti = t; return true; }
+    }
+  }
   int c = ci, t = ti;
   for (int steps = 0; steps < nc * MAX_THREADS + MAX_THREADS; ++steps) {
     ++t;
@@ -263,6 +277,7 @@ int simt_set_option(void* h, const char* name, int v) {
   return 0;
 }
 unsigned long long simt_fiber_switches(void) { return simt::g_switches; }
+void simt_set_sched_seed(unsigned long long seed) { simt::g_sched_state = seed; }
 
 // One frame for each of the first nframes streams: the launch sequence of launch_range() (csrc/pwpp_capi.cu).
 void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const int64_t* ns, int cols) {

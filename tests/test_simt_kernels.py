@@ -89,8 +89,14 @@ def test_persistent_front_end_is_identical(kitti):
     a = SimtTwin(num_streams=len(frames)); a.estimate_multi(frames)
     # (W, CTAs, concurrent): sequential CTAs check the list order; concurrent CTAs (all live at once, fibers of all of them
     # interleaved) really wait for each other on the hist_done / scan_done counters
-    for w, nc, conc in ((1, 3, 0), (5, 3, 0), (1, 4, 1), (2, 3, 1), (20, 5, 1)):
-        b = SimtTwin(num_streams=len(frames), front=1, front_w=w, persistent_ctas=nc, front_concurrent=conc); b.estimate_multi(frames)
+    # seed != 0: the fibers of the concurrently live CTAs are interleaved at random instead of round-robin
+    for w, nc, conc, seed in ((1, 3, 0, 0), (5, 3, 0, 0), (1, 4, 1, 0), (2, 3, 1, 0), (20, 5, 1, 0), (1, 5, 1, 7), (3, 2, 1, 8), (2, 6, 1, 9)):
+        b = SimtTwin(num_streams=len(frames), front=1, front_w=w, persistent_ctas=nc, front_concurrent=conc)
+        b.set_sched_seed(seed)
+        try:
+            b.estimate_multi(frames)
+        finally:
+            b.set_sched_seed(0)
         for f in range(len(frames)):
             a.select(f); b.select(f)
             assert np.array_equal(a.bin_ids(), b.bin_ids())
