@@ -104,6 +104,61 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class NvmlSampler:
+    """SM clock and clock-event reasons through NVML every ~5 ms with host timestamps, so that the samples INSIDE the timed
+    region can be told from the ones around it (nvidia-smi's 200 ms loop catches at most one of a 60 ms region).
+    Best effort: any failure leaves `rows` empty and the nvidia-smi sampler's numbers are used."""
+
+    def __init__(self, index):
+        self.rows = []          # (perf_counter, sm_mhz, reasons bit mask)
+        self.max_mhz = None
+        self._stop = False
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def start(self):
+        if self.nv is None:
+            return
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+
+    def _loop(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(get_reasons(self.h)) if get_reasons else 0
+                self.rows.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                return
+            time.sleep(0.005)
+
+    def stop(self, t0, t1):
+        """Summary of the samples taken in [t0, t1] (perf_counter), or None when there is none."""
+        self._stop = True
+        if self._t:
+            self._t.join(timeout=1)
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not inside:
+            return None
+        nv = self.nv
+        sm = sorted(r[1] for r in inside)
+        bits = 0
+        for r in inside:
+            bits |= r[2]
+        names = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": [n for n, b in names if bits & b], "samples": len(inside),
+                "source": "NVML, 5 ms period, samples inside the timed region only"}
+
+
 def measured_peak_gbs():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -239,15 +294,26 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches0 = eng.launch_count()
     clocks = ClockSampler(local)
+    nvml = NvmlSampler(local)
     barrier(); torch.cuda.synchronize()
-    clocks.start()
+    clocks.start(); nvml.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
-    torch.cuda.synchronize(); barrier()
+    torch.cuda.synchronize()
+    t_region1 = time.perf_counter()
+    barrier()
     clk = clocks.stop()
+    try:
+        clk_nvml = nvml.stop(t_region0, t_region1)
+    except Exception:
+        clk_nvml = None
+    if clk_nvml is not None:
+        clk_nvml["nvidia_smi"] = clk      # the 200 ms nvidia-smi loop next to it, for reference
+        clk = clk_nvml
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     # per-kernel device times: the same steps once more with CUDA events around every kernel (the five fit kernels,
