@@ -533,6 +533,8 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     if (env_int("PWPP_X_KERNEL", PWPP_X_KERNEL_DEFAULT, 0, 1)) {
       const int x_nw = env_int("PWPP_X_NW", PWPP_X_NW_DEFAULT, 8, 32), x_minb = env_int("PWPP_X_MINB", PWPP_X_MINB_DEFAULT, 1, 2);
       if (x_nw >= 32) ctx->fit[5] = {fuse_seed ? k_fit_big<32, 1, true> : k_fit_big<32, 1, false>, 0, 1024, 0};
+      else if (x_nw >= 16 && x_minb == 1 && env_int("PWPP_X_FIXPOINT", PWPP_X_FIXPOINT_DEFAULT, 0, 1))   // exact fixpoint exit of the R-GPF passes
+        ctx->fit[5] = {fuse_seed ? k_fit_big<16, 1, true, false, true> : k_fit_big<16, 1, false, false, true>, 0, 512, 0};
       else if (x_nw >= 16 && x_minb == 1) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 1, true> : k_fit_big<16, 1, false>, 0, 512, 0};
       else if (x_nw >= 16) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 2, true> : k_fit_big<16, 2, false>, 0, 512, 0};
       else ctx->fit[5] = {fuse_seed ? k_fit_big<8, 4, true> : k_fit_big<8, 4, false>, 0, 256, 0};

@@ -25,7 +25,10 @@ namespace pwpp {
 constexpr int BIG_CCAP = 512;   // candidate buffer of the LPR selection (16 keys per lane of warp 0)
 constexpr int BIG_U = 4;        // loads in flight per thread
 
-template <int NW, int MINB, bool FUSE, bool NL = false>
+// FIX (PWPP_X_FIXPOINT): every pass records the selected set as ballot words in the patch's (not yet written) output region,
+// an R-GPF pass compares its set with the set its plane was fitted to, and an unchanged set ends the iteration — the exact
+// fixpoint exit of the other fit kernels (on the synthetic frames 1.6 of the 3 R-GPF passes remain), for patches of any size.
+template <int NW, int MINB, bool FUSE, bool NL = false, bool FIX = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g,
                                                             AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq, int* __restrict__ part,
                                                             BinFit* __restrict__ fits) {
@@ -43,6 +46,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
   __shared__ unsigned s_T;
   __shared__ int s_ccount;
   __shared__ int s_n[2];
+  __shared__ int s_chg[FIX ? NW : 1];
   __shared__ Plane s_plane, s_plane2;
   __shared__ int4 s_item;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -220,7 +224,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
     //      MODE 1: {alive, signed distance to `cls` < th_dist}. Leaves the counts in nsel[0..1] and, for non-empty
     //      sets, the fitted planes in s_plane / s_plane2 (valid until the next call). ----
     int nsel[2] = {0, 0};
-    auto fit_pass = [&](int mode, bool fused, double zthr, double zin, const Plane& cls, const double cc[3]) {
+    bool set_changed = true;                                   // FIX: did the last pass select a set different from the recorded one
+    unsigned* mw = reinterpret_cast<unsigned*>(out);           // FIX: ballot words of the recorded set (scratch until the partition)
+    auto fit_pass = [&](int mode, bool fused, double zthr, double zin, const Plane& cls, const double cc[3], bool compare = false) {
       double a[9], b[FUSE ? 9 : 1];
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
@@ -229,13 +235,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
       int na = 0, nb = 0;
       PlaneF pf;
       pf.n0 = (float) cls.normal[0]; pf.n1 = (float) cls.normal[1]; pf.n2 = (float) cls.normal[2]; pf.d = (float) cls.d;
-      for (int i0 = tid; i0 < n; i0 += BIG_U * NT) {
+      int mychg = 0;
+      // FIX: the trip count must be warp-uniform (ballots inside): iterate from the warp's first thread and add the lane
+      for (int i0 = FIX ? tid - lane : tid; i0 < n; i0 += BIG_U * NT) {
         float4 q[BIG_U];
 #pragma unroll
-        for (int u = 0; u < BIG_U; ++u) { const int j = i0 + u * NT; q[u] = P[j < n ? j : n - 1]; }
+        for (int u = 0; u < BIG_U; ++u) { const int j = i0 + (FIX ? lane : 0) + u * NT; q[u] = P[j < n ? j : n - 1]; }
 #pragma unroll
         for (int u = 0; u < BIG_U; ++u) {
-          const int j = i0 + u * NT;
+          const int j = i0 + (FIX ? lane : 0) + u * NT;
           const float4 p = q[u];
           bool in = j < n;
           if (in && rv.n != 0) in = is_alive(rv, ap.th_dist_v, p.x, p.y, p.z);
@@ -244,6 +252,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
             int fl = dist_filter(pf, thf, p.x, p.y, p.z);
             if (fl < 0) fl = (point_plane_distance(cls, p.x, p.y, p.z) < ap.th_dist) ? 1 : 0;   // S:525 / S:529, exact
             in = fl != 0;
+          }
+          if (FIX) {   // record the set the next plane is fitted to (the inner seeds of a fused round)
+            const bool rec = (FUSE && fused) ? (in && ((double) p.z < zin)) : in;
+            const unsigned bal = __ballot_sync(0xffffffffu, rec);
+            const int wb = i0 + u * NT;   // first point of this warp's 32-point group
+            if (lane == 0 && wb < n) {
+              if (compare && mw[wb >> 5] != bal) mychg = 1;
+              mw[wb >> 5] = bal;
+            }
           }
           if (in) {
             const double dx = (double) p.x - cc[0], dy = (double) p.y - cc[1], dz = (double) p.z - cc[2];
@@ -266,6 +283,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
         for (int q = 0; q < (FUSE ? 9 : 1); ++q) b[q] = warp_sum(b[q]);
         nb = __reduce_add_sync(0xffffffffu, nb);
       }
+      if (FIX && lane == 0) s_chg[w] = mychg;
       if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) s_part[w][q] = a[q];
@@ -306,6 +324,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
       __syncthreads();
       nsel[0] = s_n[0];
       nsel[1] = s_n[1];
+      if (FIX) {
+        int ch = 0;
+#pragma unroll
+        for (int q = 0; q < (FIX ? NW : 1); ++q) ch |= s_chg[q];
+        set_changed = ch != 0;
+      }
     };
 
     // 1. R-VPF (S:482-508). For zone != 0 the fitted plane can never be used (see k_fit_stream).
@@ -334,21 +358,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
       fit_pass(0, false, lpr + ap.th_seeds, 0.0, pl, c);
       if (nsel[0] > 0) { pl = s_plane; have_plane = true; }
     }
+    bool fixpoint = false;     // FIX: a pass selected exactly the set its plane was fitted to: every later pass would repeat it
+    Plane cls_fix = pl;
+    int n_ground = 0;
     for (int it = 0; it < ap.num_iter - 1; ++it) {
       if (!have_plane) break;
       const Plane cls = pl;
       const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-      fit_pass(1, false, 0.0, 0.0, cls, cc);
+      fit_pass(1, false, 0.0, 0.0, cls, cc, true);
       if (nsel[0] > 0) pl = s_plane;
+      if (FIX && !set_changed) { fixpoint = true; cls_fix = cls; n_ground = nsel[0]; break; }
     }
     // last iteration (S:528-542): split by the current plane, then refit on the ground part
-    int n_ground = 0;
     if (have_plane) {
-      const Plane cls = pl;
-      const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-      fit_pass(1, false, 0.0, 0.0, cls, cc);
-      n_ground = nsel[0];
-      if (n_ground > 0) pl = s_plane;
+      const Plane cls = fixpoint ? cls_fix : pl;
+      if (!fixpoint) {
+        const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
+        fit_pass(1, false, 0.0, 0.0, cls, cc);
+        n_ground = nsel[0];
+        if (n_ground > 0) pl = s_plane;
+      }
       PlaneF pf;
       pf.n0 = (float) cls.normal[0]; pf.n1 = (float) cls.normal[1]; pf.n2 = (float) cls.normal[2]; pf.d = (float) cls.d;
       int g_run = 0, ng_run = 0, tile = 0;

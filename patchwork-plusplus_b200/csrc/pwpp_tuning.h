@@ -20,5 +20,6 @@
 #define PWPP_PART_ILP_DEFAULT 0     /* 1: four index loads in flight in the final partition of the M/L1/L2/L3 kernels; checked on the SIMT twin, not yet measured */
 #define PWPP_EMIT_SPLIT_DEFAULT 1    /* k_emit: slices per bin (grid.z); > 1 written for dense frames, checked on the SIMT twin, not yet measured */
 #define PWPP_X_KERNEL_DEFAULT 1     /* class X (> 8192 points): 1 = CTA per patch (k_fit_big), 0 = one warp per patch */
+#define PWPP_X_FIXPOINT_DEFAULT 0   /* 1: k_fit_big ends the R-GPF passes at the exact fixpoint (set recorded as ballot words); checked on the SIMT twin, not yet measured */
 #define PWPP_X_NW_DEFAULT 16
 #define PWPP_X_MINB_DEFAULT 1

@@ -227,7 +227,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0;
   std::string last_launches;
 };
 
@@ -272,6 +272,7 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "front_concurrent") t->front_concurrent = v;
   else if (n == "l2_wide") t->l2_wide = v;
   else if (n == "l2_pls") t->l2_pls = v;
+  else if (n == "x_fix") t->x_fix = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -388,6 +389,10 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   simt::launch("k_fit_warp<false,2,2>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2>(FIT_ARGS); });
   simt::launch("k_fit_warp<true,1,1>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2>(FIT_ARGS); });
   simt::launch("k_fit_resident<8,8,0>", pg, FIT_THREADS, 0, [&] { k_fit_resident<8, 8, 0, 2>(FIT_ARGS); });
+  if (t->x_kernel && t->x_fix) {
+    if (t->fuse_seed & 1) simt::launch("k_fit_big<16,1,fuse,fix>", pg, 512, 0, [&] { k_fit_big<16, 1, true, false, true>(FIT_ARGS); });
+    else simt::launch("k_fit_big<16,1,fix>", pg, 512, 0, [&] { k_fit_big<16, 1, false, false, true>(FIT_ARGS); });
+  }
   if (t->x_kernel) {
     if (t->x_nw == 32) { if (t->fuse_seed & 1) simt::launch("k_fit_big<32,1,fuse>", pg, 1024, 0, [&] { k_fit_big<32, 1, true>(FIT_ARGS); }); else simt::launch("k_fit_big<32,1>", pg, 1024, 0, [&] { k_fit_big<32, 1, false>(FIT_ARGS); }); }
     else if (t->x_nw == 8) { if (t->fuse_seed & 1) simt::launch("k_fit_big<8,4,fuse>", pg, 256, 0, [&] { k_fit_big<8, 4, true>(FIT_ARGS); }); else simt::launch("k_fit_big<8,4>", pg, 256, 0, [&] { k_fit_big<8, 4, false>(FIT_ARGS); }); }

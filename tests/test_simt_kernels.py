@@ -127,7 +127,7 @@ def _big_patch_cases():
     }
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(fuse_seed=0), dict(x_nw=8, fuse_seed=3), dict(x_nw=32, emit_split=5), dict(x_kernel=0)])
+@pytest.mark.parametrize("opts", [dict(), dict(fuse_seed=0), dict(x_nw=8, fuse_seed=3), dict(x_nw=32, emit_split=5), dict(x_kernel=0), dict(x_fix=1), dict(x_fix=1, fuse_seed=0)])
 def test_big_patches(opts):
     """Class X (more than 8192 points in one patch): k_fit_big in its CTA shapes and the one-warp fallback, including
     the tie-heavy selections that overflow the candidate buffer and an R-VPF wall removal in zone 0."""
@@ -216,7 +216,7 @@ def test_random_parameter_sets(kitti, seed):
     p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([4, 8, 16, 32, 54, 64], 4)]
     p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 6, 4)]
     opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 3, 8])), solve_call=int(rng.integers(0, 2)),
-                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)), l2_pls=int(rng.integers(0, 2)))
+                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)), l2_pls=int(rng.integers(0, 2)), x_fix=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
     pool = [kitti[0], kitti[4], synth.make_frame(7, 0).numpy()]
     orc, tw = O.Oracle(p, O.ARITH_CANON64), SimtTwin(p, **opts)
