@@ -560,6 +560,12 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       if (fuse_seed && l2_minb == 3 && ctx->fit[3].threads == FIT_THREADS && !ctx->sw_l2_wide) ctx->fit[3].fn = k_fit_cta<4096, 3, 3, 8, true, true>;
       if (fuse_seed && ctx->fit[4].threads == FIT_THREADS) ctx->fit[4].fn = k_fit_cta<8192, 4, 2, 8, true, true>;
     }
+    // PWPP_M_RESIDENT: class M (65..512 points) on the register-resident kernel (one warp x 16 points per lane; 3.4k instructions
+    // against the staged warp kernel's 7.9k, which stalls 27 % on instruction fetch; no incremental moments, no fp32 filter).
+    // PWPP_L1_CTA: class L1 (513..2048 points) on the fused CTA kernel with 24 KB of shared memory per patch (many zone-0
+    // patches are in this class; the warp kernel is not fused and waits on L2 loads for 30 % of its stall samples).
+    if (env_int("PWPP_M_RESIDENT", PWPP_M_RESIDENT_DEFAULT, 0, 1)) ctx->fit[1] = {k_fit_resident<32, 16, 1, 2>, 0, FIT_THREADS, 0};
+    if (env_int("PWPP_L1_CTA", PWPP_L1_CTA_DEFAULT, 0, 1)) ctx->fit[2] = {k_fit_cta<2048, 2, 3, 8, true>, 0, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float)};
     // PWPP_L2_PLS: class L2 with the current plane in shared memory instead of 20 registers per thread (fewer spills at 3 and at
     // 4 CTAs/SM); only for the plain fused 4096-point shape
     if (env_int("PWPP_L2_PLS", PWPP_L2_PLS_DEFAULT, 0, 1) && fuse_seed && !ctx->sw_l2_wide && !part_ilp && ctx->fit[3].threads == FIT_THREADS)

@@ -227,7 +227,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0;
   std::string last_launches;
 };
 
@@ -273,6 +273,8 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "l2_wide") t->l2_wide = v;
   else if (n == "l2_pls") t->l2_pls = v;
   else if (n == "x_fix") t->x_fix = v;
+  else if (n == "m_resident") t->m_resident = v;
+  else if (n == "l1_cta") t->l1_cta = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -362,6 +364,8 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
+  if (t->m_resident) simt::launch("k_fit_resident<32,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<32, 16, 1, 2>(FIT_ARGS); });
+  if (t->l1_cta) simt::launch("k_fit_cta<2048,2,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float), [&] { k_fit_cta<2048, 2, 3, 8, true>(FIT_ARGS); });
   if (t->l2_pls) simt::launch("k_fit_cta<4096,3,4,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8, true, false, true>(FIT_ARGS); });
   if (t->l2_wide) simt::launch("k_fit_cta<5888,3,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * CLS_L2_WIDE_MAX * sizeof(float), [&] { k_fit_cta<CLS_L2_WIDE_MAX, 3, 3, 8, true>(FIT_ARGS); });
   if (t->part_ilp) {   // PWPP_PART_ILP variants of the default shapes drain the queues first
