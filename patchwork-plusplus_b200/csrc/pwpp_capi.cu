@@ -464,7 +464,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
   ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", PWPP_HIST_PIPE_DEFAULT, 0, 2);
   ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", PWPP_SCATTER_V_DEFAULT, 0, 1);
-  ctx->sw_serial_fit = std::getenv("PWPP_SERIAL_FIT") != nullptr;
+  ctx->sw_serial_fit = env_int("PWPP_SERIAL_FIT", PWPP_SERIAL_FIT_DEFAULT, 0, 1) != 0;
   ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", PWPP_EMIT_SPLIT_DEFAULT, 1, 32);
   ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);
   ctx->sw_l2_wide = env_int("PWPP_L2_WIDE", PWPP_L2_WIDE_DEFAULT, 0, 1);

@@ -6,6 +6,7 @@
 #pragma once
 #define PWPP_HIST_PIPE_DEFAULT 2    /* k_bin_hist load pipelining: 0 none, 1 groups of 4, 2 groups of 2 */
 #define PWPP_SCATTER_V_DEFAULT 0    /* 1: software-pipelined k_scatter at 3 CTAs/SM */
+#define PWPP_SERIAL_FIT_DEFAULT 0   /* 1: the fit kernels run one after another on the call's stream instead of forked onto side streams */
 #define PWPP_S_MINB_DEFAULT 2       /* launch-bounds CTAs/SM of the class-S kernel */
 #define PWPP_M_MINB_DEFAULT 2
 #define PWPP_L1_MINB_DEFAULT 2

@@ -124,6 +124,12 @@ if "error" not in base:
             r2 = measure(best[("fuse",)][1], pts, offs_np, F, K, "kitti/fuse-only")
             if "error" not in r2 and r2["sig"] == base["sig"] and r2["ms_per_step"] < base["ms_per_step"]:
                 chosen.update(best[("fuse",)][1])
+    # whole-step switch: the fit kernels one after another instead of forked onto side streams (no per-stage signature)
+    if "error" not in base:
+        cur = measure(dict(chosen), pts, offs_np, F, K, "kitti/chosen") if chosen else base
+        ser = measure({**chosen, "PWPP_SERIAL_FIT": "1"}, pts, offs_np, F, K, "kitti/serial-fit")
+        if "error" not in ser and "error" not in cur and ser["sig"] == base["sig"] and ser["ms_per_step"] < 0.99 * cur["ms_per_step"]:
+            chosen["PWPP_SERIAL_FIT"] = "1"
 del pts
 torch.cuda.empty_cache()
 # ---------------- BASELINE config 5: dense ~1M-point frames (class-X patches) ----------------
