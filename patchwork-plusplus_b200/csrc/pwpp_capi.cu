@@ -98,7 +98,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0, sw_l2_wide = 0;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0, sw_l2_wide = 0, sw_m_half = 0;
   int front_grid = 0;
   DevBuf<FrontItem> d_front_items;
   DevBuf<int> d_front_ctr;
@@ -271,7 +271,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     CU_TRY(cudaMemsetAsync(ctx->d_front_ctr.p, 0, ((size_t) 1 + 2 * nf) * sizeof(int), s));
     k_front_plan<<<(nf + W + 127) / 128, 128, 0, s>>>(ft.chunk_off, nf, W, ctx->d_front_items.p);
     FrontArgs fa{d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->fast_bin ? 1 : 0, ctx->d_bin_ids.p, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits,
-                 ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->sw_l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, ctx->d_front_ctr.p, nf};
+                 ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->sw_l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, ctx->sw_m_half ? CLS_M_HALF_MAX : CLS_M_MAX, ctx->d_front_ctr.p, nf};
     const size_t sm_f = front_smem_bytes(nbp);
     k_front<<<ctx->front_grid, FRONT_THREADS, sm_f, s>>>(fa);
     ctx->launches += 2;
@@ -289,6 +289,11 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     ++ctx->launches;
   }
   STAGE_MARK();
+#define SCAN_ARGS ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits
+  if (ctx->sw_m_half && ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
+  else if (ctx->sw_m_half) k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
+  else
+#undef SCAN_ARGS
   if (ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
   else k_bin_scan<CLS_L2_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
   ++ctx->launches;
@@ -468,6 +473,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", PWPP_EMIT_SPLIT_DEFAULT, 1, 32);
   ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);
   ctx->sw_l2_wide = env_int("PWPP_L2_WIDE", PWPP_L2_WIDE_DEFAULT, 0, 1);
+  ctx->sw_m_half = env_int("PWPP_M_HALF", PWPP_M_HALF_DEFAULT, 0, 1);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -565,6 +571,9 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     // PWPP_L1_CTA: class L1 (513..2048 points) on the fused CTA kernel with 24 KB of shared memory per patch (many zone-0
     // patches are in this class; the warp kernel is not fused and waits on L2 loads for 30 % of its stall samples).
     if (env_int("PWPP_M_RESIDENT", PWPP_M_RESIDENT_DEFAULT, 0, 1)) ctx->fit[1] = {k_fit_resident<32, 16, 1, 2>, 0, FIT_THREADS, 0};
+    // PWPP_M_HALF: class M = 65..256 points on k_fit_resident<16,16> (two patches per warp); 257..512-point patches go to class L1,
+    // whose kernels take any size up to 2048
+    if (ctx->sw_m_half) ctx->fit[1] = {k_fit_resident<16, 16, 1, 2>, 0, FIT_THREADS, 0};
     if (env_int("PWPP_L1_CTA", PWPP_L1_CTA_DEFAULT, 0, 1)) ctx->fit[2] = {k_fit_cta<2048, 2, 3, 8, true>, 0, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float)};
     // PWPP_L2_PLS: class L2 with the current plane in shared memory instead of 20 registers per thread (fewer spills at 3 and at
     // 4 CTAs/SM); only for the plain fused 4096-point shape

@@ -35,6 +35,9 @@ constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 4
 // room for 3 CTAs per SM next to the kernel's static shared memory. r01: an L3 patch (2 CTAs/SM at 96 KB) costs 3x an L2 patch
 // for 1.8x the points, and most L3 patches are below 6k points.
 constexpr int CLS_L2_WIDE_MAX = 5888;
+// PWPP_M_HALF: class M ends here and is served by k_fit_resident<16,16> — two patches per warp, i.e. half the per-round
+// instruction stream (selection, reductions, solve) per patch; patches of 257..512 points join class L1.
+constexpr int CLS_M_HALF_MAX = 256;
 constexpr int NUM_CLASSES = 6;  // S, M, L1, L2, L3, X
 
 // device-side work queues, filled by k_bin_scan. An item describes one patch completely, so that a fit kernel needs
@@ -83,7 +86,7 @@ __device__ __forceinline__ unsigned kth_key(unsigned kmin, unsigned kmax, int ta
 }
 
 // ---- group-wide reductions -------------------------------------------------------------------------
-// G = 8: four independent groups per warp (butterfly inside 8-lane segments); G = 32: one warp.
+// G = 8 / 16: four / two independent groups per warp (butterfly inside 8- / 16-lane segments); G = 32: one warp.
 template <int G>
 struct GroupOps;
 
@@ -103,6 +106,29 @@ struct GroupOps<8> {
   }
   __device__ static __forceinline__ double sum_d(double v, void*) {
     v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+  }
+};
+template <>
+struct GroupOps<16> {   // two independent groups per warp (butterfly inside 16-lane segments)
+  __device__ static __forceinline__ unsigned min_u(unsigned v) {
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 8)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, 2)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+  }
+  __device__ static __forceinline__ unsigned max_u(unsigned v) {
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 8)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 2)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+  }
+  __device__ static __forceinline__ int sum_i(int v, void*) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+  }
+  __device__ static __forceinline__ double sum_d(double v, void*) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
   }
 };
@@ -141,7 +167,7 @@ template <int G, int K, int CLS, int MINB>
 __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_resident(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                  Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                  int* __restrict__ part, BinFit* __restrict__ fits) {
-  static_assert(G == 8 || G == 32, "group is a warp or a quarter warp");
+  static_assert(G == 8 || G == 16 || G == 32, "group is a warp, half a warp or a quarter warp");
   constexpr int NGW = 32 / G;                  // patches per warp
   const int lane = threadIdx.x & 31;
   const int gw = lane / G;                     // group inside the warp
@@ -317,9 +343,9 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_resident(const float4
     // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
     {
       // every lane runs the ballots (lanes of absent patches hold no valid slot); only valid slots store
-      const unsigned seg_shift = (G == 8) ? (unsigned) ((lane >> 3) << 3) : 0u;
-      const unsigned seg_mask = (G == 8) ? 0xffu : 0xffffffffu;
-      const unsigned lt = ((G == 8) ? ((1u << (lane & 7)) - 1u) : lanemask_lt());
+      const unsigned seg_shift = (G < 32) ? (unsigned) ((lane / G) * G) : 0u;
+      const unsigned seg_mask = (G < 32) ? ((1u << (G & 31)) - 1u) : 0xffffffffu;
+      const unsigned lt = ((G < 32) ? ((1u << (lane % G)) - 1u) : lanemask_lt());
       int g_run = 0, ng_run = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) {

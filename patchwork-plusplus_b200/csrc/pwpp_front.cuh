@@ -65,6 +65,7 @@ struct FrontArgs {
   const FrontItem* items;
   int nitems;
   int l2max;        // upper bound of the L2 patch class (CLS_L2_MAX, or CLS_L2_WIDE_MAX with PWPP_L2_WIDE)
+  int mmax;         // upper bound of the M patch class (CLS_M_MAX, or CLS_M_HALF_MAX with PWPP_M_HALF)
   int* ctr;         // [0] next item, [1 .. 1+F) hist_done per frame, [1+F .. 1+2F) scan_done per frame (zeroed per call)
   int nframes;
 };
@@ -153,8 +154,8 @@ __device__ __forceinline__ void front_scan_frame(const FrontArgs& a, int f, int*
       run += v;
     }
   }
-  const int l2max = a.l2max;
-  auto cls_of = [l2max](int n) { return n <= CLS_S_MAX ? 0 : n <= CLS_M_MAX ? 1 : n <= CLS_L1_MAX ? 2 : n <= l2max ? 3 : n <= CLS_L3_MAX ? 4 : 5; };
+  const int l2max = a.l2max, mmax = a.mmax;
+  auto cls_of = [l2max, mmax](int n) { return n <= CLS_S_MAX ? 0 : n <= mmax ? 1 : n <= CLS_L1_MAX ? 2 : n <= l2max ? 3 : n <= CLS_L3_MAX ? 4 : 5; };
   for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
     const int n = s_scan[b + 1] - s_scan[b];
     if (n >= a.ap.num_min_pts && n > 0) atomicAdd(&s_cls_cnt[cls_of(n)], 1);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, 4) k_bin_hist(const float4* __r
 // cbase[chunk][b] = position where chunk's first point of bin b goes.
 // Also sorts the frame's patches into the work queues of the fit kernels by size (S:191: patches below
 // num_min_pts are not fitted) and initialises the BinFit records of the patches that will not be fitted.
-template <int L2MAX>
+template <int L2MAX, int MMAX = CLS_M_MAX>
 __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, const unsigned short* __restrict__ chist, unsigned int* __restrict__ cbase,
                            int* __restrict__ bin_off, WorkQueues wq, BinFit* __restrict__ fits) {
   PW_DYN_SHARED(int, s_scan);  // [nbp + 1]
@@ -135,7 +135,7 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
     }
   }
   // work queues
-  auto cls_of = [](int n) { return n <= CLS_S_MAX ? 0 : n <= CLS_M_MAX ? 1 : n <= CLS_L1_MAX ? 2 : n <= L2MAX ? 3 : n <= CLS_L3_MAX ? 4 : 5; };
+  auto cls_of = [](int n) { return n <= CLS_S_MAX ? 0 : n <= MMAX ? 1 : n <= CLS_L1_MAX ? 2 : n <= L2MAX ? 3 : n <= CLS_L3_MAX ? 4 : 5; };
   for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
     const int n = s_scan[b + 1] - s_scan[b];
     if (n >= num_min_pts && n > 0) atomicAdd(&s_cls_cnt[cls_of(n)], 1);

@@ -18,6 +18,7 @@
 #define PWPP_FRONT_DEFAULT 0        /* 1: binning + scan + scatter as one persistent kernel pipelined through L2 (pwpp_front.cuh); checked on the SIMT twin, not yet measured */
 #define PWPP_L2_WIDE_DEFAULT 0      /* 1: class L2 covers 2049..5888 points (k_fit_cta<5888> still at 3 CTAs/SM), class L3 the rest up to 8192; checked on the SIMT twin, not yet measured */
 #define PWPP_M_RESIDENT_DEFAULT 0   /* 1: class M on the register-resident kernel k_fit_resident<32,16>; checked on the SIMT twin, not yet measured */
+#define PWPP_M_HALF_DEFAULT 0       /* 1: class M = 65..256 points on k_fit_resident<16,16> (two patches per warp), 257..512 joins class L1; checked on the SIMT twin, not yet measured */
 #define PWPP_L1_CTA_DEFAULT 0       /* 1: class L1 on the fused CTA kernel k_fit_cta<2048>; checked on the SIMT twin, not yet measured */
 #define PWPP_L2_PLS_DEFAULT 0       /* 1: class-L2 kernel keeps the current plane in shared memory (fewer spills); checked on the SIMT twin, not yet measured */
 #define PWPP_PART_ILP_DEFAULT 0     /* 1: four index loads in flight in the final partition of the M/L1/L2/L3 kernels; checked on the SIMT twin, not yet measured */

@@ -227,7 +227,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0;
   std::string last_launches;
 };
 
@@ -275,6 +275,7 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "x_fix") t->x_fix = v;
   else if (n == "m_resident") t->m_resident = v;
   else if (n == "l1_cta") t->l1_cta = v;
+  else if (n == "m_half") t->m_half = v;
   else if (n == "x_nw") t->x_nw = v;
   else return -1;
   return 0;
@@ -333,7 +334,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     simt::launch("k_front_plan", (nframes + W + 127) / 128, 128, 0, [&] { k_front_plan(chunk_off.data(), nframes, W, fitems.data()); });
     for (int k = 0; k < nitems; ++k) if (fitems[k].tf < 0) { std::fprintf(stderr, "simt_twin: k_front_plan left item %d unset\n", k); std::abort(); }
     FrontArgs fa{d_pts, ft, states, g, ap, has_intensity, nbp, nb, t->fast ? 1 : 0, bin_ids.data(), chist.data(), cbase.data(), bin_off.data(), wq, fits.data(),
-                 sorted.data(), fitems.data(), nitems, t->l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, fctr.data(), nframes};
+                 sorted.data(), fitems.data(), nitems, t->l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, t->m_half ? CLS_M_HALF_MAX : CLS_M_MAX, fctr.data(), nframes};
     const size_t sm_f = front_smem_bytes(nbp);
     if (t->front_concurrent) simt::launch_concurrent("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });   // CTAs interleave and wait for each other
     else simt::launch("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });
@@ -348,7 +349,11 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     else simt::launch("k_bin_hist<true,2>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 2>(HIST_ARGS); });
 #undef HIST_ARGS
   }
-  if (t->l2_wide) simt::launch("k_bin_scan<5888>", nframes, 512, (nbp + 1) * sizeof(int),
+  if (t->m_half && t->l2_wide) simt::launch("k_bin_scan<5888,256>", nframes, 512, (nbp + 1) * sizeof(int),
+               [&] { k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
+  else if (t->m_half) simt::launch("k_bin_scan<4096,256>", nframes, 512, (nbp + 1) * sizeof(int),
+               [&] { k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
+  else if (t->l2_wide) simt::launch("k_bin_scan<5888>", nframes, 512, (nbp + 1) * sizeof(int),
                [&] { k_bin_scan<CLS_L2_WIDE_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
   else simt::launch("k_bin_scan", nframes, 512, (nbp + 1) * sizeof(int),
                [&] { k_bin_scan<CLS_L2_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
@@ -364,6 +369,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
+  if (t->m_half) simt::launch("k_fit_resident<16,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<16, 16, 1, 2>(FIT_ARGS); });
   if (t->m_resident) simt::launch("k_fit_resident<32,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<32, 16, 1, 2>(FIT_ARGS); });
   if (t->l1_cta) simt::launch("k_fit_cta<2048,2,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float), [&] { k_fit_cta<2048, 2, 3, 8, true>(FIT_ARGS); });
   if (t->l2_pls) simt::launch("k_fit_cta<4096,3,4,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8, true, false, true>(FIT_ARGS); });

@@ -25,6 +25,7 @@ VARIANTS = [
     {"PWPP_X_FIXPOINT": "1"},
     {"PWPP_M_RESIDENT": "1"},
     {"PWPP_L1_CTA": "1"},
+    {"PWPP_M_HALF": "1"},
     {"PWPP_L2_PLS": "1"},
     {"PWPP_L2_PLS": "1", "PWPP_L2_MINB": "4"},
     {"PWPP_FRONT": "1", "PWPP_PART_ILP": "1", "PWPP_EMIT_SPLIT": "4", "PWPP_SOLVE_CALL": "1", "PWPP_L2_WIDE": "1"},
@@ -65,7 +66,7 @@ def test_variant_equals_default(kitti, env):
     for rep in range(2):
         for f in range(len(frames)):
             assert np.array_equal(base[rep][f][0], var[rep][f][0]) and np.array_equal(base[rep][f][1], var[rep][f][1]), f"{env}: index lists differ, call {rep} frame {f}"
-            rounding_only = any(k in env for k in ("PWPP_X_FIXPOINT", "PWPP_M_RESIDENT", "PWPP_L1_CTA"))
+            rounding_only = any(k in env for k in ("PWPP_X_FIXPOINT", "PWPP_M_RESIDENT", "PWPP_L1_CTA", "PWPP_M_HALF"))
             if env.get("PWPP_FUSE_SEED") != "0" and not rounding_only:
                 assert base[rep][f][2] == var[rep][f][2], f"{env}: patch records differ, call {rep} frame {f}"
             if not rounding_only:

@@ -70,7 +70,7 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1), dict(emit_split=8), dict(part_ilp=1), dict(l2_wide=1), dict(l2_pls=1), dict(m_resident=1), dict(l1_cta=1)])
+@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1), dict(emit_split=8), dict(part_ilp=1), dict(l2_wide=1), dict(l2_pls=1), dict(m_resident=1), dict(l1_cta=1), dict(m_half=1), dict(m_half=1, l1_cta=1, l2_wide=1)])
 def test_kernel_variants(kitti, opts):
     """The A/B variants selectable through PWPP_* switches give the same result as the defaults."""
     a = kitti[3]
@@ -216,7 +216,7 @@ def test_random_parameter_sets(kitti, seed):
     p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([4, 8, 16, 32, 54, 64], 4)]
     p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 6, 4)]
     opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 3, 8])), solve_call=int(rng.integers(0, 2)),
-                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)), l2_pls=int(rng.integers(0, 2)), x_fix=int(rng.integers(0, 2)), m_resident=int(rng.integers(0, 2)), l1_cta=int(rng.integers(0, 2)))
+                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)), l2_pls=int(rng.integers(0, 2)), x_fix=int(rng.integers(0, 2)), m_resident=int(rng.integers(0, 2)), l1_cta=int(rng.integers(0, 2)), m_half=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
     pool = [kitti[0], kitti[4], synth.make_frame(7, 0).numpy()]
     orc, tw = O.Oracle(p, O.ARITH_CANON64), SimtTwin(p, **opts)

@@ -12,7 +12,7 @@ leg() { echo "$1 rc=$2 t=$((SECONDS-t0))s" | tee -a gpurun_out/legs.txt; }
 : > gpurun_out/variants_ok.txt
 if [ "${SKIP_VARIANTS:-0}" != "1" ]; then
   t0=$SECONDS
-  for v in "FRONT=1" "PART_ILP=1" "EMIT_SPLIT=8" "SOLVE_CALL=1" "L2_WIDE=1" "X_FIXPOINT=1" "M_RESIDENT=1" "L1_CTA=1" "L2_PLS=1" "L2_PLS=1,L2_MINB=4" "FUSE_SEED=3" "FUSE_SEED=0,L2_MINB=4"; do
+  for v in "FRONT=1" "PART_ILP=1" "EMIT_SPLIT=8" "SOLVE_CALL=1" "L2_WIDE=1" "X_FIXPOINT=1" "M_RESIDENT=1" "L1_CTA=1" "M_HALF=1" "L2_PLS=1" "L2_PLS=1,L2_MINB=4" "FUSE_SEED=3" "FUSE_SEED=0,L2_MINB=4"; do
     if PWPP_TEST_VARIANTS=1 timeout 120 python -m pytest -m gpu -q -p no:cacheprovider "tests/test_gpu_variants.py::test_variant_equals_default[$v]" > gpurun_out/variant_${v//[=,]/_}.log 2>&1 && grep -q "1 passed" gpurun_out/variant_${v//[=,]/_}.log; then echo "$v" >> gpurun_out/variants_ok.txt; fi
   done
   leg variants $?; cat gpurun_out/variants_ok.txt

@@ -18,7 +18,7 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 FD = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 ALL = ["PWPP_HIST_PIPE", "PWPP_SCATTER_V", "PWPP_SERIAL_FIT", "PWPP_S_MINB", "PWPP_M_MINB", "PWPP_L1_MINB", "PWPP_L2_MINB", "PWPP_L2_NW", "PWPP_L3_NW",
-       "PWPP_FUSE_SEED", "PWPP_SOLVE_CALL", "PWPP_PART_ILP", "PWPP_EMIT_SPLIT", "PWPP_FRONT", "PWPP_L2_WIDE", "PWPP_L2_PLS", "PWPP_X_FIXPOINT", "PWPP_M_RESIDENT", "PWPP_L1_CTA", "PWPP_X_KERNEL", "PWPP_X_NW", "PWPP_X_MINB"]
+       "PWPP_FUSE_SEED", "PWPP_SOLVE_CALL", "PWPP_PART_ILP", "PWPP_EMIT_SPLIT", "PWPP_FRONT", "PWPP_L2_WIDE", "PWPP_L2_PLS", "PWPP_X_FIXPOINT", "PWPP_M_RESIDENT", "PWPP_L1_CTA", "PWPP_M_HALF", "PWPP_X_KERNEL", "PWPP_X_NW", "PWPP_X_MINB"]
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
 log = open(os.path.join(REPO, "gpurun_out", "tune.jsonl"), "w")
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream; assert st != 0
@@ -59,7 +59,7 @@ def measure(cfg, pts, offs_np, nf, k, label):
 
 # Switched-off variants are only candidates when tests/test_gpu_variants.py passed for them on this GPU (one line per
 # variant id, e.g. "FRONT=1", written by tools/gpu_round_end.sh); without the file every candidate is tried.
-UNMEASURED = {"PWPP_FRONT", "PWPP_PART_ILP", "PWPP_EMIT_SPLIT", "PWPP_SOLVE_CALL", "PWPP_L2_WIDE", "PWPP_L2_PLS", "PWPP_X_FIXPOINT", "PWPP_M_RESIDENT", "PWPP_L1_CTA"}
+UNMEASURED = {"PWPP_FRONT", "PWPP_PART_ILP", "PWPP_EMIT_SPLIT", "PWPP_SOLVE_CALL", "PWPP_L2_WIDE", "PWPP_L2_PLS", "PWPP_X_FIXPOINT", "PWPP_M_RESIDENT", "PWPP_L1_CTA", "PWPP_M_HALF"}
 _allow_file = os.environ.get("PWPP_TUNE_ALLOW_FILE", "")
 ALLOWED = None
 if _allow_file and os.path.exists(_allow_file):
@@ -91,6 +91,7 @@ candidates = [
     ({"PWPP_L2_WIDE": "1"}, ["fit_L2", "fit_L3"]),
     ({"PWPP_M_RESIDENT": "1"}, ["fit_M"]),
     ({"PWPP_L1_CTA": "1"}, ["fit_L1"]),
+    ({"PWPP_M_HALF": "1"}, ["fit_M", "fit_L1"]), ({"PWPP_M_HALF": "1", "PWPP_L1_CTA": "1"}, ["fit_M", "fit_L1"]),
     ({"PWPP_L2_PLS": "1"}, ["fit_L2"]), ({"PWPP_L2_PLS": "1", "PWPP_L2_MINB": "4"}, ["fit_L2"]),
     ({"PWPP_S_MINB": "3"}, ["fit_S"]), ({"PWPP_S_MINB": "4"}, ["fit_S"]),
     ({"PWPP_M_MINB": "3"}, ["fit_M"]),
