@@ -32,8 +32,12 @@ inline void build_geometry(const pwpp_params& p, Geometry& g, AlgoParams& ap, bo
     g.f_sector_sizes[k] = (float) g.sector_sizes[k];
     g.f_inv_ring[k] = (float) (1.0 / g.ring_sizes[k]);
     g.f_inv_sector[k] = (float) (1.0 / g.sector_sizes[k]);
-    // the fp32 filter of bin_of_point() needs decision cells much wider than the float error
-    if (!(g.ring_sizes[k] >= 0.5) || g.num_sectors[k] > 128) fast = false;
+    // the fp32 filter of bin_of_point() needs decision cells much wider than the float error, and rings of at least
+    // GUARD_R / GUARD_U = 1 m: its range test rejects only points more than GUARD_R (2e-4 m) outside (min_range, max_range]
+    // and leaves the rest to the ring-coordinate guard of GUARD_U (2e-4) RING WIDTHS, so with rings narrower than 1 m a
+    // point 1.9e-4 m inside the rejected side of min_range / max_range was binned instead of dropped (found by the random
+    // parameter sets of tests/test_simt_kernels.py: ring width 0.875 m). Such geometries take the exact double path.
+    if (!(g.ring_sizes[k] >= 1.5) || g.num_sectors[k] > 128) fast = false;
   }
   g.f_max_range = (float) g.max_range;
   g.nbins = g.bin_base[4];

@@ -81,3 +81,30 @@ def test_sequence_runner_matches_the_engine(tmp_path, kitti):
         assert int(tok[2]) == len(kitti[t % 3])
         assert int(tok[4]) == eng.num_ground(0) and int(tok[6]) == eng.num_nonground(0) and int(tok[8]) == eng.num_patches(0)
         assert abs(float(tok[10]) - eng.height(0)) < 1e-4
+
+
+def test_narrow_ring_geometry_takes_the_exact_binning_kernel(kitti):
+    """A concentric-zone layout with rings narrower than 1.5 m (zone 0: 5 rings of 0.875 m) is binned by the exact
+    double-precision kernel (k_bin_hist<false>) instead of the fp32 filter: bin ids bit-exact and index sets identical
+    to the oracle, including points a hair outside min_range / max_range."""
+    import oracle_py as O
+    from pwpp_ctypes import default_params
+    import pwpp_b200
+    p = default_params()
+    p.min_range, p.max_range = 5.0, 40.0
+    p.num_rings_each_zone[:] = [5, 1, 2, 3]
+    p.num_sectors_each_zone[:] = [32, 54, 32, 32]
+    extra = []
+    for r in (5.0, 40.0):
+        for dr in (0.0, 1e-5, -1e-5, 1.9e-4, -1.9e-4, 3e-4, -3e-4):
+            for k in range(0, 54, 2):
+                th = k * (2 * np.pi / 54) + 0.013
+                extra.append([(r + dr) * np.cos(th), (r + dr) * np.sin(th), -1.7, 0.5])
+    a = np.concatenate([kitti[0], np.array(extra, np.float32)])
+    eng = pwpp_b200.Engine(p, device=0)
+    eng.estimate_host([a])
+    orc = O.Oracle(p, O.ARITH_CANON64); orc.estimate(a)
+    assert np.array_equal(orc.bin_ids(), eng.bin_ids(0))
+    if not (orc.bin_min_fit_n() < 3).any():
+        assert np.array_equal(np.sort(orc.getGroundIndices()), np.sort(eng.ground_indices(0)))
+        assert np.array_equal(np.sort(orc.getNongroundIndices()), np.sort(eng.nonground_indices(0)))

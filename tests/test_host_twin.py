@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_py as O
-from helpers import Twin, assert_bins_close, assert_sets_equal, assert_state_close
+from helpers import SimtTwin, Twin, assert_bins_close, assert_sets_equal, assert_state_close
 from param_sets import PARAM_SETS
 
 
@@ -130,3 +130,34 @@ def test_closed_form_eigensolver_against_lapack_and_jacobi():
     assert np.allclose(o2[1, :3], 2) and np.allclose(o2[2, :3], [3, 2, 1]) and np.allclose(np.abs(o2[2, 3:]), [0, 1, 0])
     assert np.isnan(o2[3, :3]).all() and np.isnan(o2[4, :3]).all() and np.array_equal(o2[3, 3:], [0, 0, 1])
     assert np.isfinite(o2[5:]).all() and np.allclose(o2[6, :3] / 1e300, [1.1, 1.0, 0.9])
+
+
+@pytest.mark.parametrize("min_range,max_range,rings", [(5.0, 40.0, [5, 1, 2, 3]), (2.7, 80.0, [2, 4, 4, 4]), (1.0, 30.0, [2, 2, 2, 8]), (0.5, 120.0, [1, 1, 1, 1]),
+                                                       (5.0, 17.0, [1, 1, 1, 4]), (2.0, 26.0, [2, 2, 2, 5])])
+def test_binning_filter_range_limits_for_other_geometries(min_range, max_range, rings):
+    """Points a hair inside / outside min_range and max_range and around every ring boundary, for ring widths from 0.3 m to
+    60 m: the fp32 filter (used only when every ring is at least 1.5 m wide) and the exact path must both agree with the
+    oracle. Regression for a point 1.9e-4 m below min_range that the filter binned with rings 0.875 m wide."""
+    from pwpp_ctypes import default_params
+    p = default_params()
+    p.min_range, p.max_range = min_range, max_range
+    p.num_rings_each_zone[:] = rings
+    p.num_sectors_each_zone[:] = [32, 54, 32, 32]
+    orc, tw = O.Oracle(p, O.ARITH_CANON64), Twin(p)
+    z = [min_range, (7 * min_range + max_range) / 8, (3 * min_range + max_range) / 4, (min_range + max_range) / 2, max_range]
+    radii = list(z)
+    for k in range(4):
+        radii += [z[k] + (z[k + 1] - z[k]) * i / rings[k] for i in range(1, rings[k])]
+    pts = []
+    for r in radii:
+        for dr in (0.0, 1e-7, -1e-7, 1e-5, -1e-5, 1.5e-4, -1.5e-4, 1.9e-4, -1.9e-4, 2.1e-4, -2.1e-4, 2.6e-4, -2.6e-4, 4e-4, -4e-4, 1e-3, -1e-3):
+            for k in range(0, 54, 3):
+                th = k * (2 * np.pi / 54) + 0.013
+                pts.append([(r + dr) * np.cos(th), (r + dr) * np.sin(th), -1.7, 0.5])
+    a = np.array(pts, np.float32)
+    orc.estimate(a); tw.estimate(a)
+    assert np.array_equal(orc.bin_ids(), tw.bin_ids()), f"{int((orc.bin_ids() != tw.bin_ids()).sum())} bin ids differ"
+    assert tw.fast_mismatches() == 0
+    stw = SimtTwin(p)
+    stw.estimate(a)
+    assert np.array_equal(orc.bin_ids(), stw.bin_ids())
