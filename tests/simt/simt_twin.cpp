@@ -372,7 +372,8 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   if (t->m_half) simt::launch("k_fit_resident<16,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<16, 16, 1, 2>(FIT_ARGS); });
   if (t->m_resident) simt::launch("k_fit_resident<32,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<32, 16, 1, 2>(FIT_ARGS); });
   if (t->l1_cta) simt::launch("k_fit_cta<2048,2,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float), [&] { k_fit_cta<2048, 2, 3, 8, true>(FIT_ARGS); });
-  if (t->l2_pls) simt::launch("k_fit_cta<4096,3,4,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8, true, false, true>(FIT_ARGS); });
+  if (t->l2_pls && !t->l2_wide && !t->part_ilp)   // like pwpp_create: only the plain fused 4096-point shape has a PLS variant
+    simt::launch("k_fit_cta<4096,3,4,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8, true, false, true>(FIT_ARGS); });
   if (t->l2_wide) simt::launch("k_fit_cta<5888,3,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * CLS_L2_WIDE_MAX * sizeof(float), [&] { k_fit_cta<CLS_L2_WIDE_MAX, 3, 3, 8, true>(FIT_ARGS); });
   if (t->part_ilp) {   // PWPP_PART_ILP variants of the default shapes drain the queues first
     simt::launch("k_fit_cta<8192,4,2,8,fuse,pilp>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true, true>(FIT_ARGS); });
