@@ -195,7 +195,7 @@ def test_edge_cases():
     assert len(tw.getGroundIndices()) + len(tw.getNongroundIndices()) == len(cases["z_equals_flt_min"]) - 1   # patchworkpp.cpp:591
 
 
-@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18])
 def test_random_parameter_sets(kitti, seed):
     """Random supported parameter sets (bin layouts, num_iter / num_lpr / num_min_pts, thresholds, range, switches on and
     off, N x 3 input) and random kernel-variant switches, a three-frame sequence each: the kernels on the SIMT twin vs
@@ -205,16 +205,16 @@ def test_random_parameter_sets(kitti, seed):
     rng = np.random.default_rng(seed)
     p = default_params()
     p.enable_RNR, p.enable_RVPF, p.enable_TGR = (int(rng.random() < 0.7) for _ in range(3))
-    p.num_iter = int(rng.integers(1, 6)); p.num_lpr = int(rng.choice([1, 5, 20, 32, 33, 64])); p.num_min_pts = int(rng.choice([3, 5, 10, 30]))
+    p.num_iter = int(rng.integers(1, 6)); p.num_lpr = int(rng.choice([1, 5, 20, 32, 33, 64])); p.num_min_pts = int(rng.choice([0, 1, 3, 5, 10, 30, 200]))
     p.num_rings_of_interest = int(rng.integers(0, 5))
     p.max_flatness_storage = int(rng.choice([3, 40, 1000])); p.max_elevation_storage = int(rng.choice([2, 50, 1000]))
     p.sensor_height = float(rng.uniform(1.4, 2.1))
     p.th_seeds = float(rng.choice([0.05, 0.125, 0.3, 0.5])); p.th_seeds_v = float(rng.choice([0.05, 0.25, 0.4]))
     p.th_dist = float(rng.choice([0.05, 0.125, 0.3])); p.th_dist_v = float(rng.choice([0.05, 0.1, 0.9]))
-    p.min_range = float(rng.choice([0.5, 2.7, 5.0])); p.max_range = float(rng.choice([40.0, 80.0, 120.0]))
+    p.min_range = float(rng.choice([0.0, 0.5, 2.7, 5.0])); p.max_range = float(rng.choice([10.0, 40.0, 80.0, 120.0, 250.0, 300.0]))
     p.uprightness_thr = float(rng.choice([0.101, 0.5, 0.707, 0.95]))
-    p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([4, 8, 16, 32, 54, 64], 4)]
-    p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 6, 4)]
+    p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([1, 4, 8, 16, 32, 54, 64, 128, 200], 4)]
+    p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 9, 4)]
     opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 3, 8])), solve_call=int(rng.integers(0, 2)),
                 x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)), l2_pls=int(rng.integers(0, 2)), x_fix=int(rng.integers(0, 2)), m_resident=int(rng.integers(0, 2)), l1_cta=int(rng.integers(0, 2)), m_half=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
