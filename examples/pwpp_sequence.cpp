@@ -103,6 +103,16 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     long long points = 0;
     int done = 0;
+    // releases both slots and joins the reader on every way out of the loop (an exception from estimateGround or a getter
+    // would otherwise destroy a joinable std::thread -> std::terminate, with the reader possibly blocked on cv)
+    struct ReaderGuard {
+      std::thread& th; std::mutex& mu; std::condition_variable& cv; Slot* slot;
+      ~ReaderGuard() {
+        { std::lock_guard<std::mutex> lk(mu); for (int i = 0; i < 2; ++i) if (slot[i].frame != -1) slot[i].frame = -1; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+      }
+    } guard{reader, mu, cv, slot};
     for (int t = 0; t < total; ++t) {
       Slot& s = slot[t & 1];
       { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return s.frame == t || s.frame == -2; }); }

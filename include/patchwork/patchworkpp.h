@@ -103,7 +103,7 @@ class PatchWorkpp {
   ~PatchWorkpp() { if (ctx_) pwpp_destroy(ctx_); }
   PatchWorkpp(const PatchWorkpp&) = delete;
   PatchWorkpp& operator=(const PatchWorkpp&) = delete;
-  PatchWorkpp(PatchWorkpp&& o) noexcept : params_(o.params_), ctx_(o.ctx_), n_(o.n_) { o.ctx_ = nullptr; }
+  PatchWorkpp(PatchWorkpp&& o) noexcept : params_(o.params_), ctx_(o.ctx_), n_(o.n_), ran_(o.ran_) { o.ctx_ = nullptr; }
 
   // reference :152 for raw buffers: element (i,c) of the N x cols cloud is data[i*row_stride + c*col_stride].
   void estimateGround(const float* data, int64_t n, int cols, int64_t row_stride, int64_t col_stride) {
@@ -113,6 +113,7 @@ class PatchWorkpp {
     const int64_t ns[1] = {n};
     check(pwpp_estimate_host(ctx_, 1, ptrs, ns, cols >= 4 ? 4 : 3, row_stride, col_stride));
     n_ = n;
+    ran_ = true;
   }
 
   double getHeight() { return pwpp_height(ctx_, 0); }        // reference :154 (adaptive sensor height)
@@ -146,9 +147,12 @@ class PatchWorkpp {
   patchwork::Params params_;
   pwpp_ctx* ctx_ = nullptr;
   int64_t n_ = 0;
+  bool ran_ = false;
 
   static void check(int rc) { if (rc != PWPP_OK) throw std::runtime_error(std::string("PatchWorkpp: ") + pwpp_last_error()); }
-  static int64_t count(int64_t c) { if (c < 0) throw std::runtime_error(std::string("PatchWorkpp: ") + pwpp_last_error()); return c; }
+  // before the first estimateGround() the reference's getters return empty matrices (its members are empty): a count
+  // of -1 with nothing processed yet is 0 here, any other failure throws
+  int64_t count(int64_t c) const { if (c < 0) { if (!ran_) return 0; throw std::runtime_error(std::string("PatchWorkpp: ") + pwpp_last_error()); } return c; }
 #ifdef PATCHWORKPP_HAVE_EIGEN
   static Eigen::MatrixX3f toEigenCloud(const std::vector<float>& v) {
     Eigen::MatrixX3f m(v.size() / 3, 3);

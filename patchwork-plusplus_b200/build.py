@@ -35,6 +35,7 @@ def build_core(force=False, verbose=False):
                "-I" + os.path.join(REPO, "include"), "-I" + os.path.join(HERE, "csrc"), "-cudart", "static", "-o", out, src]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        cmd[1:1] = os.environ.get("PWPP_EXTRA_NVCC_FLAGS", "").split()
         subprocess.check_call(cmd)
     return out
 
@@ -64,6 +65,11 @@ def build_examples(force=False):
     core = build_core()
     if force or _newer(out, [src, hdr, core]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"), src, "-o", out,
+                               "-L" + LIB, "-lpwpp_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    src2 = os.path.join(REPO, "examples", "pwpp_latency.cpp")
+    out2 = os.path.join(LIB, "pwpp_latency")
+    if force or _newer(out2, [src2, hdr, core]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"), src2, "-o", out2,
                                "-L" + LIB, "-lpwpp_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
     return out
 

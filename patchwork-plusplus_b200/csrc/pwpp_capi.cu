@@ -98,7 +98,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0, sw_l2_wide = 0, sw_m_half = 0;
+  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0, sw_l2_wide = 0, sw_m_half = 0, sw_group = 1;
   int front_grid = 0;
   DevBuf<FrontItem> d_front_items;
   DevBuf<int> d_front_ctr;
@@ -290,7 +290,8 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   }
   STAGE_MARK();
 #define SCAN_ARGS ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits
-  if (ctx->sw_m_half && ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
+  if (ctx->sw_group) k_bin_scan_groups<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
+  else if (ctx->sw_m_half && ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
   else if (ctx->sw_m_half) k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
   else
 #undef SCAN_ARGS
@@ -314,7 +315,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   // left) overlaps the start of the next.
 #define FIT_ARGS ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits
   const bool serial_fit = ctx->sw_serial_fit;   // PWPP_SERIAL_FIT: diagnostic switch
-  auto launch_fit = [&](int c, cudaStream_t st) { const FitLaunch& k = ctx->fit[c]; k.fn<<<k.grid, k.threads, k.smem, st>>>(FIT_ARGS); };
+  auto launch_fit = [&](int c, cudaStream_t st) { const FitLaunch& k = ctx->fit[c]; if (k.fn) { k.fn<<<k.grid, k.threads, k.smem, st>>>(FIT_ARGS); ++ctx->launches; } };
   if (prof || serial_fit) {
     static const int order[NUM_CLASSES] = {0, 4, 3, 2, 1, 5};   // stage slots: S, L3, L2, L1, M, X
     for (int q = 0; q < NUM_CLASSES; ++q) { launch_fit(order[q], s); STAGE_MARK(); }
@@ -322,17 +323,23 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     CU_TRY(cudaEventRecord(ctx->ev_fork, s));
     for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
     // longest classes first
+    if (ctx->sw_group) {   // C (one big patch per CTA) first so that B / A CTAs fill the SMs around them
+      launch_fit(GRP_CLS_C, s);
+      launch_fit(GRP_CLS_B, ctx->side[0]);
+      launch_fit(GRP_CLS_A, ctx->side[1]);
+      launch_fit(5, ctx->side[4]);
+    } else {
     launch_fit(4, s);
     launch_fit(3, ctx->side[0]);
     launch_fit(2, ctx->side[1]);
     launch_fit(1, ctx->side[2]);
     launch_fit(0, ctx->side[3]);
     launch_fit(5, ctx->side[4]);
+    }
     for (int q = 0; q < 5; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
     stage += 6;
   }
 #undef FIT_ARGS
-  ctx->launches += 6;
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
@@ -474,6 +481,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);
   ctx->sw_l2_wide = env_int("PWPP_L2_WIDE", PWPP_L2_WIDE_DEFAULT, 0, 1);
   ctx->sw_m_half = env_int("PWPP_M_HALF", PWPP_M_HALF_DEFAULT, 0, 1);
+  ctx->sw_group = env_int("PWPP_FIT_GROUP", PWPP_FIT_GROUP_DEFAULT, 0, 1);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -579,8 +587,17 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     // 4 CTAs/SM); only for the plain fused 4096-point shape
     if (env_int("PWPP_L2_PLS", PWPP_L2_PLS_DEFAULT, 0, 1) && fuse_seed && !ctx->sw_l2_wide && !part_ilp && ctx->fit[3].threads == FIT_THREADS)
       ctx->fit[3].fn = l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true, false, true> : k_fit_cta<4096, 3, 3, 8, true, false, true>;
+    if (ctx->sw_group && !ctx->sw_front) {
+      // the group fit kernel (pwpp_fit_group.cuh) serves every patch up to GRP_C_PTS points; class X keeps k_fit_big
+      ctx->fit[GRP_CLS_A] = {k_fit_group<GRP_A_PTS, GRP_A_MP, GRP_A_NW, 3, GRP_CLS_A>, 0, GRP_A_NW * 32, (size_t) GRP_A_PTS * sizeof(float4)};
+      ctx->fit[GRP_CLS_B] = {k_fit_patch<GRP_B_NW, 2, GRP_CLS_B>, 0, GRP_B_NW * 32, 0};
+      ctx->fit[GRP_CLS_C] = {k_fit_patch<GRP_C_NW, 1, GRP_CLS_C>, 0, GRP_C_NW * 32, 0};
+      ctx->fit[3] = {nullptr, 0, 0, 0};
+      ctx->fit[4] = {nullptr, 0, 0, 0};
+    } else ctx->sw_group = 0;
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];
+      if (!k.fn) continue;
       if (k.smem > 0) CU_TRY_CTX(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k.smem));
       int per_sm = 1;
       CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.threads, k.smem));
@@ -608,6 +625,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   *out = ctx;
   rc = pwpp_reset_all(ctx);
   if (rc) { pwpp_destroy(ctx); *out = nullptr; return rc; }
+  CU_TRY_CTX(cudaStreamSynchronize(ctx->stream));   // the initial state is in place before any caller stream can read it
   if (max_points_per_frame > 0) {
     const size_t tot = (size_t) max_points_per_frame * num_streams;
     CU_TRY_CTX(ctx->d_bin_ids.reserve(tot));
@@ -703,7 +721,8 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
   const long long total = ctx->pt_off[nframes];
   CU_TRY(ctx->d_in.reserve((size_t) std::max<long long>(total, 1)));
   cudaStream_t s = ctx->stream, s_in = ctx->stream_h2d, s_out = ctx->stream_d2h;
-  // the staging buffers of the previous call must not be in flight any more
+  // the staging buffers of the previous call must not be in flight any more (nor a device-input call on a caller's stream)
+  if (ctx->last_stream && ctx->last_stream != s) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
   CU_TRY(cudaStreamSynchronize(s));
   CU_TRY(cudaStreamSynchronize(s_in));
   CU_TRY(cudaStreamSynchronize(s_out));
@@ -789,6 +808,7 @@ int pwpp_estimate_device(pwpp_ctx* ctx, int nframes, const void* d_pts, const in
   cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
   // work buffers are reused stream-ordered: a call on a different stream than the previous one waits for it
   if (ctx->last_stream && ctx->last_stream != s) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  if (!ctx->last_stream && s != ctx->stream) CU_TRY(cudaStreamSynchronize(ctx->stream));   // resets issued before the first call ran on the ctx's own stream
   rc = run_path(ctx, nframes, (const float4*) d_pts + h_offsets[0], has_intensity, s);
   if (rc) return rc;
   ctx->last_time_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
@@ -971,5 +991,30 @@ int pwpp_copy_bin_ids(pwpp_ctx* ctx, int f, uint16_t* dst) {
   if (n > 0) CU_TRY(cudaMemcpy(dst, ctx->d_bin_ids.p + ctx->pt_off[f], (size_t) n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   return PWPP_OK;
 }
+
+#if defined(PWPP_PHASE_CLOCKS)
+// diagnostic builds only: cycles thread 0 of the k_fit_group CTAs spent per phase, [3 classes][16]; reset = 1 clears them
+int pwpp_debug_phase_clocks(pwpp_ctx* ctx, unsigned long long* out, int reset) {
+  if (!ctx) return PWPP_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(unsigned long long) * 48);
+  if (reset) { static unsigned long long z[48]; cudaMemcpyToSymbol(g_phase_clk, z, sizeof z); }
+  return PWPP_OK;
+}
+int pwpp_debug_events(pwpp_ctx* ctx, unsigned* out, int max_events) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  unsigned n = 0;
+  cudaMemcpyFromSymbol(&n, g_evn, sizeof n);
+  if ((int) n > max_events) n = max_events;
+  if (n > 16384) n = 16384;
+  if (out && n) cudaMemcpyFromSymbol(out, g_ev, (size_t) n * 16);
+  unsigned z = 0;
+  cudaMemcpyToSymbol(g_evn, &z, sizeof z);
+  return (int) n;
+}
+#endif
 
 }  // extern "C"

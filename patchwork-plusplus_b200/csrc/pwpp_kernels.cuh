@@ -24,6 +24,7 @@
 #include "pwpp_fit.cuh"
 #include "pwpp_fit_big.cuh"
 #include "pwpp_fit_group.cuh"
+#include "pwpp_fit_patch.cuh"
 
 namespace pwpp {
 
@@ -162,17 +163,16 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_bin_scan_groups: k_bin_scan for the group fit kernel (pwpp_fit_group.cuh). Same bin offsets and scatter bases; instead
-// of one work item per patch it packs the frame's bins, in bin order, into GROUPS of consecutive bins whose points (a
-// contiguous range of the bin-sorted array) fit the shared memory of one CTA:
-//   queue GRP_CLS_A   <= GRP_A_PTS points, <= GRP_A_MP fitted patches   (the many small patches of the outer zones)
-//   queue GRP_CLS_B   <= GRP_B_PTS points, <= GRP_B_MP fitted patches   (zone-0 / zone-1 patches)
-//   queue GRP_CLS_C   one patch of GRP_B_PTS < n <= GRP_C_PTS points
-//   queue NUM_CLASSES-1 (class X): one patch above GRP_C_PTS points, item format of k_fit_big
-// Bins below num_min_pts (S:191) inside a span only occupy shared memory; leading ones are skipped.
+// k_bin_scan_groups: bin offsets and scatter bases like k_bin_scan; the fit work items are
+//   queue GRP_CLS_A   GROUPS of consecutive small bins (each <= GRP_A_BIN points; <= GRP_A_PTS points and <= GRP_A_MP fitted
+//                     patches per group) for k_fit_group (pwpp_fit_group.cuh): the many small patches of the outer zones
+//   queue GRP_CLS_B   one patch of GRP_A_BIN < n <= GRP_B_PTS points   (k_fit_patch, 8 warps)
+//   queue GRP_CLS_C   one patch of GRP_B_PTS < n <= GRP_C_PTS points   (k_fit_patch, 16 warps)
+//   queue NUM_CLASSES-1 (class X): one patch above GRP_C_PTS points     (k_fit_big)
+// Bins below num_min_pts (S:191) inside a group's span only occupy shared memory; leading ones are skipped.
 constexpr int GRP_CLS_A = 0, GRP_CLS_B = 1, GRP_CLS_C = 2;
-constexpr int GRP_A_PTS = 2048, GRP_A_MP = 32, GRP_B_PTS = 4096, GRP_B_MP = 8, GRP_C_PTS = 8192;
-constexpr int GRP_A_NW = 8, GRP_B_NW = 8, GRP_C_NW = 16;   // warps per CTA of the three instantiations
+constexpr int GRP_A_BIN = 1024, GRP_A_PTS = 2048, GRP_A_MP = 32, GRP_B_PTS = 4096, GRP_C_PTS = 8192;
+constexpr int GRP_A_NW = 8, GRP_B_NW = 8, GRP_C_NW = 16;   // warps per CTA of the three kernels
 __global__ void k_bin_scan_groups(FrameTable ft, int nbp, int nbins, int num_min_pts, const unsigned short* __restrict__ chist, unsigned int* __restrict__ cbase,
                                   int* __restrict__ bin_off, WorkQueues wq, BinFit* __restrict__ fits) {
   PW_DYN_SHARED(int, s_scan);  // [nbp + 1]
@@ -224,7 +224,7 @@ __global__ void k_bin_scan_groups(FrameTable ft, int nbp, int nbins, int num_min
     int gb = 0, gpts = 0, gfit = 0;   // current group: first bin, points, fitted patches
     auto flush = [&](int bend) {
       if (gfit > 0) {
-        const int cls = gpts <= GRP_A_PTS ? GRP_CLS_A : GRP_CLS_B;
+        const int cls = GRP_CLS_A;
         const int pos = atomicAdd(&wq.count[cls], 1);
         wq.items[cls][pos] = make_group_item(f, gb, bend - gb, gpts, p0 + (long long) s_scan[gb]);
       }
@@ -233,18 +233,19 @@ __global__ void k_bin_scan_groups(FrameTable ft, int nbp, int nbins, int num_min
     for (int b = 0; b < nbins; ++b) {
       const int n = s_scan[b + 1] - s_scan[b];
       const bool fit = n >= num_min_pts && n > 0;
-      if (n > GRP_B_PTS) {   // a patch of its own
+      if (n > GRP_A_BIN) {   // a patch of its own
         flush(b);
         if (fit) {
-          if (n > GRP_C_PTS) { const int pos = atomicAdd(&wq.count[NUM_CLASSES - 1], 1); wq.items[NUM_CLASSES - 1][pos] = make_work_item(f, b, n, p0 + (long long) s_scan[b]); }
-          else { const int pos = atomicAdd(&wq.count[GRP_CLS_C], 1); wq.items[GRP_CLS_C][pos] = make_group_item(f, b, 1, n, p0 + (long long) s_scan[b]); }
+          const int cls = n > GRP_C_PTS ? NUM_CLASSES - 1 : (n > GRP_B_PTS ? GRP_CLS_C : GRP_CLS_B);
+          const int pos = atomicAdd(&wq.count[cls], 1);
+          wq.items[cls][pos] = make_work_item(f, b, n, p0 + (long long) s_scan[b]);
         }
         gb = b + 1;
         continue;
       }
       if (gfit == 0 && !fit) { gb = b + 1; gpts = 0; continue; }   // leading unfitted bins stay out
       const int npts = gpts + n, nfit = gfit + (fit ? 1 : 0);
-      const bool ok = npts <= GRP_B_PTS && nfit <= GRP_A_MP && (nfit <= GRP_B_MP || npts <= GRP_A_PTS) && (b - gb) < 1000;
+      const bool ok = npts <= GRP_A_PTS && nfit <= GRP_A_MP && (b - gb) < 1000;
       if (!ok) {
         flush(b);
         if (!fit) { gb = b + 1; continue; }

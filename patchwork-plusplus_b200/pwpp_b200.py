@@ -12,7 +12,7 @@ import numpy as np
 from pwpp_ctypes import PwppBinResult, PwppParams, PwppState, default_params  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpwpp_b200.so")
+LIB_PATH = os.environ.get("PWPP_LIB") or os.path.join(_HERE, "lib", "libpwpp_b200.so")   # PWPP_LIB: a diagnostic build of the same library
 
 _lib = None
 

@@ -227,7 +227,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 1;
   std::string last_launches;
 };
 
@@ -373,8 +373,8 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
   if (t->group) {   // the group fit kernel (pwpp_fit_group.cuh) serves every class but X
-    simt::launch("k_fit_group<C>", pg, GRP_C_NW * 32, (size_t) GRP_C_PTS * 16, [&] { k_fit_group<GRP_C_PTS, GRP_B_MP, GRP_C_NW, 1, GRP_CLS_C>(FIT_ARGS); });
-    simt::launch("k_fit_group<B>", pg, GRP_B_NW * 32, (size_t) GRP_B_PTS * 16, [&] { k_fit_group<GRP_B_PTS, GRP_B_MP, GRP_B_NW, 3, GRP_CLS_B>(FIT_ARGS); });
+    simt::launch("k_fit_patch<C>", pg, GRP_C_NW * 32, 0, [&] { k_fit_patch<GRP_C_NW, 1, GRP_CLS_C>(FIT_ARGS); });
+    simt::launch("k_fit_patch<B>", pg, GRP_B_NW * 32, 0, [&] { k_fit_patch<GRP_B_NW, 2, GRP_CLS_B>(FIT_ARGS); });
     simt::launch("k_fit_group<A>", pg, GRP_A_NW * 32, (size_t) GRP_A_PTS * 16, [&] { k_fit_group<GRP_A_PTS, GRP_A_MP, GRP_A_NW, 3, GRP_CLS_A>(FIT_ARGS); });
   } else {
   if (t->m_half) simt::launch("k_fit_resident<16,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<16, 16, 1, 2>(FIT_ARGS); });

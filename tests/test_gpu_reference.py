@@ -1,0 +1,144 @@
+"""The CUDA path (through the C-ABI) against THE REFERENCE ITSELF — not the CANON64 restatement:
+
+  * the committed golden vectors of all three parameter sets (tests/golden/golden_ref.npz, produced by the reference's
+    own patchworkpp.cpp, tests/golden/make_golden.py), fresh and sequential;
+  * oracle/_ref/libpwref.so (the reference's sources compiled where they lie; the built .so travels to the GPU box) run
+    side by side on >= 256 frames of the benchmark's synthetic config-3 batch and on a dense config-5-shaped frame;
+  * the same on a second device when the box has more than one GPU (BASELINE config 4: no parity claim without it).
+
+The reference computes in fp32, the CUDA path in double: labels are compared exactly and the number of
+differing labels is reported and bounded — on data with points within fp32 rounding of a threshold the two arithmetics can
+legitimately disagree on that point (measured: 1 label in 1.4 M on the synthetic scans); patches whose plane was fitted to
+fewer than 3 points are numerically undefined in the reference too and are excluded (oracle.bin_min_fit_n).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from param_sets import PARAM_SETS
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(params=None, num_streams=1, device=0):
+    import pwpp_b200
+    return pwpp_b200.Engine(params, device=device, num_streams=num_streams)
+
+
+def _mask(golden, key, n):
+    return np.unpackbits(golden[key + "/ground_mask"])[:n].astype(bool)
+
+
+def _degenerate_points(mk, a, floor=0):
+    """Boolean mask of the points that lie in numerically undefined patches (see module docstring)."""
+    orc = O.Oracle(mk(), O.ARITH_CANON64)
+    orc.estimate(a)
+    deg = orc.bin_min_fit_n() < 3
+    if floor:
+        br = orc.bin_results()
+        deg |= np.array([br[b].n < floor for b in range(orc.nbins)])
+    return np.r_[deg, np.zeros(3, bool)][orc.bin_ids()]
+
+
+@pytest.mark.parametrize("pname", ["ros", "no_rvpf_tgr"])
+def test_golden_sets_other_parameter_sets(kitti, golden, pname):
+    """The reference's golden label sets of the ROS launch-file parameters (N x 3 input) and of the no-R-VPF / no-TGR set
+    with another bin layout, fresh instance per scan."""
+    mk, cols = PARAM_SETS[pname]
+    frames = [np.ascontiguousarray(a[:, :cols]) for a in kitti]
+    eng = _engine(mk(), num_streams=6)
+    eng.estimate_host(frames)
+    total_diff = 0
+    for f, a in enumerate(frames):
+        m = np.zeros(a.shape[0], bool); m[eng.ground_indices(f)] = True
+        gm = _mask(golden, f"{pname}/fresh/{f}", a.shape[0])
+        skip = _degenerate_points(mk, a, floor=5 if pname == "ros" else 0)
+        total_diff += int(((m != gm) & ~skip).sum())
+    # test_oracle_golden.py: CANON64 vs the goldens differs in at most one fp32 threshold flip (ros, frame 4)
+    assert total_diff <= (1 if pname == "ros" else 0), f"{pname}: {total_diff} labels differ from the reference golden outside undefined patches"
+
+
+def test_golden_sequence_no_rvpf_tgr(kitti, golden):
+    """One stream over the six scans (temporal state) for the second parameter set, against the reference golden."""
+    mk, cols = PARAM_SETS["no_rvpf_tgr"]
+    eng = _engine(mk())
+    for f, a in enumerate(kitti):
+        a = np.ascontiguousarray(a[:, :cols])
+        eng.estimate_host([a])
+        m = np.zeros(a.shape[0], bool); m[eng.ground_indices(0)] = True
+        gm = _mask(golden, f"no_rvpf_tgr/seq/{f}", a.shape[0])
+        skip = _degenerate_points(mk, a)
+        if skip.any():
+            break   # the states may legitimately diverge after an undefined patch
+        assert np.array_equal(m, gm), f"seq frame {f}: {int((m != gm).sum())} labels differ from the reference golden"
+
+
+def _compare_with_reference(eng, frames, what):
+    """labels of the engine's frames vs libpwref.so run on the same arrays; returns (labels, mismatches)."""
+    labels = mism = 0
+    for f, a in enumerate(frames):
+        ref = O.Reference(stable_sort=False)
+        ref.estimate(a)
+        g_r = ref.getGroundIndices()
+        n_r = ref.getNongroundIndices()
+        ref.close()
+        g_e, n_e = eng.ground_indices(f), eng.nonground_indices(f)
+        assert len(g_e) + len(n_e) == len(g_r) + len(n_r), f"{what}/{f}: emitted {len(g_e) + len(n_e)} vs {len(g_r) + len(n_r)}"
+        mr = np.zeros(a.shape[0], bool); mr[g_r] = True
+        me = np.zeros(a.shape[0], bool); me[g_e] = True
+        d = mr != me
+        if d.any():
+            d &= ~_degenerate_points(_default_params, a)
+        labels += a.shape[0]
+        mism += int(d.sum())
+    return labels, mism
+
+
+def _default_params():
+    from pwpp_ctypes import default_params
+    return default_params()
+
+
+@pytest.mark.skipif(not O.have_reference_build(), reason="oracle/_ref/libpwref.so was not shipped")
+def test_config3_batch_vs_reference_build():
+    """256 frames of the benchmark's batch (config 3: synthetic KITTI-64, fresh state per frame) against the reference's own
+    code on the same arrays."""
+    import synth
+    nf = 256
+    frames = [synth.make_frame(20260922, f).numpy() for f in range(nf)]
+    eng = _engine(num_streams=nf)
+    eng.estimate_host(frames)
+    labels, mism = _compare_with_reference(eng, frames, "config3")
+    print(f"parity_vs_reference: frames={nf} labels={labels} mismatches={mism}")
+    assert mism <= max(4, labels // 1_000_000 * 4), f"{mism} of {labels} labels differ from the reference build"
+
+
+@pytest.mark.skipif(not O.have_reference_build(), reason="oracle/_ref/libpwref.so was not shipped")
+def test_dense_frame_vs_reference_build():
+    """One config-5-shaped frame (~1.2 M points, patches of 20k..40k points: class X) against the reference build."""
+    import synth
+    a = synth.make_frame(20260922, 0, "dense1m").numpy()
+    eng = _engine()
+    eng.estimate_host([a])
+    labels, mism = _compare_with_reference(eng, [a], "dense")
+    print(f"parity_vs_reference (dense): labels={labels} mismatches={mism}")
+    assert mism <= 4, f"{mism} of {labels} labels differ from the reference build"
+
+
+def test_second_device_matches_first(kitti):
+    """BASELINE config 4 shards frames over the GPUs of a box: the same frames on device 1 give bit-identical lists and
+    patch records (skipped on a one-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    import synth
+    frames = [kitti[0], kitti[3], synth.make_frame(20260922, 5).numpy()]
+    e0, e1 = _engine(num_streams=3, device=0), _engine(num_streams=3, device=1)
+    e0.estimate_host(frames); e1.estimate_host(frames)
+    for f in range(3):
+        assert np.array_equal(e0.ground_indices(f), e1.ground_indices(f)) and np.array_equal(e0.nonground_indices(f), e1.nonground_indices(f))
+        assert bytes(e0.bin_results(f)) == bytes(e1.bin_results(f))
+    orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(frames[0])
+    assert np.array_equal(np.sort(e1.ground_indices(0)), np.sort(orc.getGroundIndices()))
