@@ -290,8 +290,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
   }
   STAGE_MARK();
 #define SCAN_ARGS ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits
-  if (ctx->sw_group) k_bin_scan_groups<<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
-  else if (ctx->sw_m_half && ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
+  if (ctx->sw_m_half && ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
   else if (ctx->sw_m_half) k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
   else
 #undef SCAN_ARGS
@@ -323,12 +322,7 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
     CU_TRY(cudaEventRecord(ctx->ev_fork, s));
     for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
     // longest classes first
-    if (ctx->sw_group) {   // C (one big patch per CTA) first so that B / A CTAs fill the SMs around them
-      launch_fit(GRP_CLS_C, s);
-      launch_fit(GRP_CLS_B, ctx->side[0]);
-      launch_fit(GRP_CLS_A, ctx->side[1]);
-      launch_fit(5, ctx->side[4]);
-    } else {
+    {
     launch_fit(4, s);
     launch_fit(3, ctx->side[0]);
     launch_fit(2, ctx->side[1]);
@@ -587,13 +581,11 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     // 4 CTAs/SM); only for the plain fused 4096-point shape
     if (env_int("PWPP_L2_PLS", PWPP_L2_PLS_DEFAULT, 0, 1) && fuse_seed && !ctx->sw_l2_wide && !part_ilp && ctx->fit[3].threads == FIT_THREADS)
       ctx->fit[3].fn = l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true, false, true> : k_fit_cta<4096, 3, 3, 8, true, false, true>;
-    if (ctx->sw_group && !ctx->sw_front) {
-      // the group fit kernel (pwpp_fit_group.cuh) serves every patch up to GRP_C_PTS points; class X keeps k_fit_big
-      ctx->fit[GRP_CLS_A] = {k_fit_group<GRP_A_PTS, GRP_A_MP, GRP_A_NW, 3, GRP_CLS_A>, 0, GRP_A_NW * 32, (size_t) GRP_A_PTS * sizeof(float4)};
-      ctx->fit[GRP_CLS_B] = {k_fit_patch<GRP_B_NW, 2, GRP_CLS_B>, 0, GRP_B_NW * 32, 0};
-      ctx->fit[GRP_CLS_C] = {k_fit_patch<GRP_C_NW, 1, GRP_CLS_C>, 0, GRP_C_NW * 32, 0};
-      ctx->fit[3] = {nullptr, 0, 0, 0};
-      ctx->fit[4] = {nullptr, 0, 0, 0};
+    if (ctx->sw_group && !ctx->sw_front && !ctx->sw_l2_wide && !ctx->sw_m_half) {
+      // patches above 512 points: one patch per CTA held in registers (pwpp_fit_patch.cuh); classes S and M keep their kernels
+      ctx->fit[2] = {k_fit_patch<4, 4, 2>, 0, 4 * 32, (size_t) 4 * FP_STG * sizeof(float4)};
+      ctx->fit[3] = {k_fit_patch<8, 2, 3>, 0, 8 * 32, (size_t) 8 * FP_STG * sizeof(float4)};
+      ctx->fit[4] = {k_fit_patch<16, 1, 4>, 0, 16 * 32, (size_t) 16 * FP_STG * sizeof(float4)};
     } else ctx->sw_group = 0;
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];
@@ -1006,14 +998,10 @@ int pwpp_debug_events(pwpp_ctx* ctx, unsigned* out, int max_events) {
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  unsigned n = 0;
-  cudaMemcpyFromSymbol(&n, g_evn, sizeof n);
-  if ((int) n > max_events) n = max_events;
-  if (n > 16384) n = 16384;
-  if (out && n) cudaMemcpyFromSymbol(out, g_ev, (size_t) n * 16);
-  unsigned z = 0;
-  cudaMemcpyToSymbol(g_evn, &z, sizeof z);
-  return (int) n;
+  if (out && max_events >= 16384) cudaMemcpyFromSymbol(out, g_ev, (size_t) 16384 * 16);
+  static uint4 z[16384];
+  cudaMemcpyToSymbol(g_ev, z, sizeof z);
+  return 16384;
 }
 #endif
 

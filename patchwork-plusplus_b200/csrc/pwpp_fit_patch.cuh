@@ -21,7 +21,8 @@
 
 namespace pwpp {
 
-constexpr int FP_SL = 16;   // points per thread (register slots)
+constexpr int FP_SL = 16;    // points per thread (register slots)
+constexpr int FP_STG = 256;  // staging entries per warp: the participating points of 8 slots
 
 __device__ __forceinline__ float float_ru(double t) {
 #if defined(__CUDA_ARCH__)
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
   static_assert(NW == 8 || NW == 16 || NW == 4, "M_TOP * NW == 32");
   __shared__ double s_part[NW][20];      // per-warp partial moments: [0..9) the set, [9] unused, [10..19) inner set of a fused round
   __shared__ int s_pcnt[NW][4];          // per warp: count, inner count / changes, ground, valid
-  __shared__ unsigned s_top[32];
+  __shared__ unsigned s_min[NT];            // per-thread minimum key of the LPR candidates
+  __shared__ int s_tile[2][FP_SL * NW + 1];   // partition: ground / non-ground count of every (slot, warp) tile, then their exclusive prefix
   __shared__ int s_nv[NW];
   __shared__ unsigned s_cand[GRP_CBUF];
   __shared__ int s_cc;
@@ -82,46 +84,61 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
   __shared__ double s_tot[10];           // running sums of the R-GPF phase + count
   __shared__ int s_ctl[8];               // 0: solved, 1: taken (fused), 2: changes, 3: n of the fitted set
   __shared__ int4 s_item;
+  __shared__ float s_first[2];
+  PW_DYN_SHARED(float4, s_stage);   // [NW][FP_STG] compaction buffers of the accumulation
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt = lanemask_lt();
   const float thf = (float) ap.th_dist;
   const bool fuse_ok = ap.th_seeds <= ap.th_seeds_v;
   const int K = ap.num_lpr;
   const int count = wq.count[CLS];
+  PW_EV_DECL;
 
+  // queue protocol: the first item is claimed synchronously; afterwards the last warp claims one patch AHEAD (atomic +
+  // descriptor load + L2 prefetch of its points while the current patch is processed) and publishes it at the end
+  if (tid == 0) {
+    const int t = atomicAdd(&wq.head[CLS], 1);
+    s_item = t < count ? wq.items[CLS][t] : make_int4(-1, 0, 0, 0);
+  }
   for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      const int t = atomicAdd(&wq.head[CLS], 1);
-      s_item = t < count ? wq.items[CLS][t] : make_int4(-1, 0, 0, 0);
-      s_cc = 0;
-    }
+    if (tid == 0) s_cc = 0;
     if (tid < 10) { s_plane[tid] = 0.0; s_tot[tid] = 0.0; }
     __syncthreads();
+    PW_EV(1);
     const int4 cur = s_item;
     if (cur.x < 0) return;
+    int4 nxt = make_int4(-1, 0, 0, 0);
+    if (tid == NT - 32) {   // lane 0 of the last warp
+      const int t = atomicAdd(&wq.head[CLS], 1);
+      if (t < count) nxt = wq.items[CLS][t];
+    }
     const int f = cur.x >> 12, bin = cur.x & 0xfff, n = cur.y;
     const long long start = work_item_start(cur);
     const float4* P = sorted + start;
     int* out = part + start;
-    const int nrows = (n + 31) >> 5;
-    const int rpw = (nrows + NW - 1) / NW;     // rows per warp (<= FP_SL)
-    const int jbase = ((w * rpw) << 5) + lane;   // this thread's slot k is point jbase + 32 k
+    const int rpw = (n + NT - 1) / NT;           // slots in use (<= FP_SL): slot k of thread tid is point k * NT + tid, so that
+    const int jbase = tid;                         // neighbouring points (similar z within a scan line) land in different threads
 
     // ---- the patch: SL points per thread, loaded once ----
     float px[FP_SL], py[FP_SL], pz[FP_SL];
     unsigned vmask = 0u;
 #pragma unroll
     for (int k = 0; k < FP_SL; ++k) {
-      const int j = jbase + (k << 5);
+      const int j = jbase + k * NT;
       px[k] = 0.f; py[k] = 0.f; pz[k] = 0.f;
       if (k < rpw && j < n) { const float4 q4 = ld_stream_f4(P + j); px[k] = q4.x; py[k] = q4.y; pz[k] = q4.z; vmask |= 1u << k; }
     }
+    if (w == NW - 1) {   // the look-ahead warp pulls the next patch towards L2 while this one is processed
+      nxt.x = __shfl_sync(0xffffffffu, nxt.x, 0); nxt.y = __shfl_sync(0xffffffffu, nxt.y, 0);
+      nxt.z = __shfl_sync(0xffffffffu, nxt.z, 0); nxt.w = __shfl_sync(0xffffffffu, nxt.w, 0);
+      if (nxt.x >= 0) prefetch_patch_l2(sorted + work_item_start(nxt), nxt.y, lane, 32);
+    }
+    PW_EV(2);
     const bool zone0 = bin < g.bin_base[1];
     const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;   // S:90
     const float margin_f = zone0 ? float_ru(margin_z) : -INFINITY;                          // (double) z < margin  <=>  z < margin_f
-    const float4 first = P[0];
-    const double c0 = (double) first.x, c1 = (double) first.y;   // reference point of the moment sums (with the LPR height)
+    if (tid == 0) { s_first[0] = px[0]; s_first[1] = py[0]; }   // point 0: reference point of the moment sums (with the LPR height); read after the first barrier of the seed round
+    double c0 = 0.0, c1 = 0.0;
 
     unsigned amask = vmask, member = 0u;
     int state = (ap.enable_RVPF && zone0) ? ST_RVPF : ST_SEED;
@@ -130,18 +147,65 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
     double c2 = 0.0;
     float pf0 = 0.f, pf1 = 0.f, pf2 = 0.f, pfd = 0.f;   // float copy of the current plane for the distance filter
 
-    // moment sums of the slots in `plus` (added) and `minus` (subtracted), relative to (c0, c1, c2); slot order = summation order
+    // Moment sums of the slots in `plus` (added) and `minus` (subtracted), relative to (c0, c1, c2). A slot usually holds a
+    // point of the set in only some of the 32 lanes, and a double-precision instruction costs the warp ~3 issue cycles
+    // whether 1 or 32 lanes take part (r02 traces: the accumulation was bound by exactly that). So the warp first COMPACTS the
+    // participating points of 8 slots into its staging buffer (ballot prefix: slot-major, lane-minor order) and then
+    // accumulates full rows of 32: ~3x fewer FP64 instructions in seed rounds, ~10x in late R-GPF rounds.
+    float4* stg = s_stage + w * FP_STG;
     auto accumulate = [&](unsigned plus, unsigned minus, double (&acc)[9]) {
       const unsigned any = plus | minus;
 #pragma unroll
-      for (int k = 0; k < FP_SL; ++k) {
-        if ((any >> k) & 1u) {
-          const double wgt = ((minus >> k) & 1u) ? -1.0 : 1.0;
-          const double dx = (double) px[k] - c0, dy = (double) py[k] - c1, dz = (double) pz[k] - c2;
-          const double wx = dx * wgt, wy = dy * wgt, wz = dz * wgt;
-          acc[0] += wx; acc[1] += wy; acc[2] += wz;
-          acc[3] += wx * dx; acc[4] += wx * dy; acc[5] += wx * dz; acc[6] += wy * dy; acc[7] += wy * dz; acc[8] += wz * dz;
+      for (int k0 = 0; k0 < FP_SL; k0 += 8) {
+        if (k0 >= rpw) break;   // uniform
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + u;
+          const bool on = (any >> k) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, on);
+          if (on) stg[cnt + __popc(bal & lt)] = make_float4(px[k], py[k], pz[k], ((minus >> k) & 1u) ? -1.f : 1.f);
+          cnt += __popc(bal);
         }
+        __syncwarp();
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+          const int i = i0 + lane;
+          if (i < cnt) {
+            const float4 q4 = stg[i];
+            const double wgt = (double) q4.w;
+            const double dx = (double) q4.x - c0, dy = (double) q4.y - c1, dz = (double) q4.z - c2;
+            const double wx = dx * wgt, wy = dy * wgt, wz = dz * wgt;
+            acc[0] += wx; acc[1] += wy; acc[2] += wz;
+            acc[3] += wx * dx; acc[4] += wx * dy; acc[5] += wx * dz; acc[6] += wy * dy; acc[7] += wy * dz; acc[8] += wz * dz;
+          }
+        }
+        __syncwarp();
+      }
+    };
+    auto accumulate_plus = [&](unsigned plus, double (&acc)[9]) {
+#pragma unroll
+      for (int k0 = 0; k0 < FP_SL; k0 += 8) {
+        if (k0 >= rpw) break;   // uniform
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + u;
+          const bool on = (plus >> k) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, on);
+          if (on) stg[cnt + __popc(bal & lt)] = make_float4(px[k], py[k], pz[k], 1.f);
+          cnt += __popc(bal);
+        }
+        __syncwarp();
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+          const int i = i0 + lane;
+          if (i < cnt) {
+            const float4 q4 = stg[i];
+            const double dx = (double) q4.x - c0, dy = (double) q4.y - c1, dz = (double) q4.z - c2;
+            acc[0] += dx; acc[1] += dy; acc[2] += dz;
+            acc[3] += dx * dx; acc[4] += dx * dy; acc[5] += dx * dz; acc[6] += dy * dy; acc[7] += dy * dz; acc[8] += dz * dz;
+          }
+        }
+        __syncwarp();
       }
     };
 
@@ -151,6 +215,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
       double a[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
+      PW_EV(10);
       int mn = 0, mx = 0;   // mx: inner count (fused round) or number of membership changes (R-GPF round)
       if (seed_round) {
         // ---- LPR: mean of the K lowest z among the alive points not below the zone-0 margin (S:88-103) ----
@@ -161,18 +226,47 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           if (ok) { smask |= 1u << k; kmin = min(kmin, order_key(pz[k])); }
         }
         int nv = __reduce_add_sync(0xffffffffu, __popc(smask));
-        int rank;
-        warp_kth_of_32(kmin, 1, rank);
-        if (rank < M_TOP) s_top[w * M_TOP + rank] = kmin;
+        s_min[tid] = kmin;
         if (lane == 0) s_nv[w] = nv;
+        PW_EV(11);
         __syncthreads();
+        PW_EV(12);
+        c0 = (double) s_first[0]; c1 = (double) s_first[1];
         int nvalid = 0;
 #pragma unroll
         for (int q = 0; q < NW; ++q) nvalid += s_nv[q];
         const int target = nvalid < K ? nvalid : K;
+        // Bound: lane l's minimum over the NW threads (l, l + 32, ...) covers the points == l (mod 32); the K-th smallest of
+        // these 32 values (ranked with 32 independent shuffles, no bisection) is >= the K-th smallest point, and because the
+        // slot mapping spreads neighbouring points over all lanes only ~1.5 K points lie below it. num_lpr > 32: the
+        // K-th smallest of all NT thread minima by bisection.
         unsigned T = 0xffffffffu;
-        int dummy;
-        if (K <= 32) T = warp_kth_of_32(s_top[lane], K, dummy);   // >= the K-th smallest point; 0xffffffff when the patch has fewer than K candidates
+        {
+          unsigned mk[NW];
+          unsigned lm = 0xffffffffu;
+#pragma unroll
+          for (int q = 0; q < NW; ++q) { mk[q] = s_min[q * 32 + lane]; lm = min(lm, mk[q]); }
+          if (target > 0) {
+            if (K <= 32) { int dummy; T = warp_kth_of_32(lm, target, dummy); }
+            else {
+              int have = 0;
+              unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+              for (int q = 0; q < NW; ++q) if (mk[q] != 0xffffffffu) { ++have; kmn = min(kmn, mk[q]); kmx = max(kmx, mk[q]); }
+              have = __reduce_add_sync(0xffffffffu, have);
+              if (have >= target) {
+                kmn = __reduce_min_sync(0xffffffffu, kmn);
+                kmx = __reduce_max_sync(0xffffffffu, kmx);
+                T = kth_key(kmn, kmx, target, [&](unsigned cand) {
+                  int cnt = 0;
+#pragma unroll
+                  for (int q = 0; q < NW; ++q) cnt += mk[q] < cand;
+                  return __reduce_add_sync(0xffffffffu, cnt);
+                });
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int k = 0; k < FP_SL; ++k) {
           if ((smask >> k) & 1u) {
@@ -180,13 +274,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
             if (key <= T) { const int pos = atomicAdd(&s_cc, 1); if (pos < GRP_CBUF) s_cand[pos] = key; }
           }
         }
+        PW_EV(13);
         __syncthreads();
+        PW_EV(14);
         const int cc = s_cc;
+#if defined(PWPP_SIMT_EMU) && defined(PWPP_DEBUG_FALLBACK)
+        if (tid == 0) std::fprintf(stderr, "sel: n=%d cc=%d target=%d\n", n, cc, target);
+#endif
         double lpr = 0.0;   // S:99-103 with no candidate: lpr_height stays 0
         if (target > 0) {
-          if (K <= 32 && cc <= GRP_CBUF) lpr = grp_rank_mean(s_cand, cc, target);   // every warp, redundantly: no third barrier
+          if (cc <= GRP_CBUF) lpr = grp_rank_mean(s_cand, cc, target);   // every warp, redundantly: no third barrier
           else {
             // rare: num_lpr > 32 or more than GRP_CBUF points tie below the bound: CTA-wide bisection on the order keys
+#if defined(PWPP_SIMT_EMU) && defined(PWPP_DEBUG_FALLBACK)
+            if (tid == 0) std::fprintf(stderr, "fallback: n=%d cc=%d target=%d T=%08x nvalid=%d\n", n, cc, target, T, nvalid);
+#endif
             unsigned ans = 0u;
             for (int bit = 31; bit >= 0; --bit) {
               const unsigned cand = ans | (1u << bit);
@@ -219,6 +321,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           }
         }
         c2 = lpr;
+        PW_EV(15);
         // ---- seeds {alive, z < lpr + th} (S:107-111 / S:144-148); a fused R-VPF round also the inner set of the R-GPF seed fit ----
         const float zthr_f = float_ru(lpr + (state == ST_RVPF ? ap.th_seeds_v : ap.th_seeds)), zin_f = float_ru(lpr + ap.th_seeds);
         unsigned sel = 0u, seli = 0u;
@@ -229,9 +332,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           seli |= ((in && pz[k] < zin_f) ? 1u : 0u) << k;
         }
         member = fused ? seli : sel;
-        accumulate(sel, 0u, a);
-        mn = __popc(sel);
-        if (fused) {   // the inner set in a second sweep over the registers (same summation order as a pass of its own)
+        accumulate_plus(fused ? (sel & ~seli) : sel, a);   // fused: the seeds outside the inner set; the solver adds the inner sums
+        mn = __popc(fused ? (sel & ~seli) : sel);
+        if (fused) {   // the inner set in a second sweep over the registers
           warp_sum9(a, mn, mx);
           if (lane == 0) {
 #pragma unroll
@@ -240,7 +343,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           }
 #pragma unroll
           for (int q = 0; q < 9; ++q) a[q] = 0.0;
-          accumulate(seli, 0u, a);
+          accumulate_plus(seli, a);
           mn = __popc(seli);
           mx = 0;
         }
@@ -266,6 +369,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
         mn = __popc(chg & inm) - __popc(chg & ~inm);
         mx = __popc(chg);
       }
+      PW_EV(20);
       // ---- combine: warp butterfly, then 9 (18) lanes of warp 0 add the NW partials in warp order ----
       warp_sum9(a, mn, mx);
       if (lane == 0) {
@@ -279,7 +383,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           s_pcnt[w][0] = mn; s_pcnt[w][1] = mx;
         }
       }
+      PW_EV(21);
       __syncthreads();
+      PW_EV(22);
       if (w == 0) {
         const int ql = lane & 15;
         const bool hi = lane >= 16;
@@ -288,9 +394,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
         if (ql < 9) {
 #pragma unroll
           for (int ww = 0; ww < NW; ++ww) v += s_part[ww][(hi ? 10 : 0) + ql];
+          if (fused && !hi) {   // all seeds = the seeds outside the inner set + the inner set
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) v += s_part[ww][10 + ql];
+          }
         } else if (ql == 9) {
 #pragma unroll
           for (int ww = 0; ww < NW; ++ww) cn += s_pcnt[ww][hi ? 1 : 0];
+          if (fused && !hi) {
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) cn += s_pcnt[ww][1];
+          }
         }
         // lanes 0..15: the set of this round; lanes 16..31: the inner set (fused) / the change count
         Moments m;
@@ -314,6 +428,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           }
           if (lane == 0) s_ctl[2] = changed;
         }
+        PW_EV(23);
         const int totn = refit ? m.n : (int) s_tot[9];
         if (tid == 0) s_cc = 0;   // (every warp has read the candidate count of this round's selection)
         Plane mine;
@@ -323,6 +438,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           plane_from_moments(m, cc3, mine);
           solved = true;
         }
+        PW_EV(24);
         __syncwarp();   // every lane has read s_tot / s_plane before lanes 0 / 16 rewrite them
         if (fused) {
           // lane 0 holds the R-VPF plane (all seeds), lane 16 the R-GPF seed plane (inner seeds)
@@ -364,7 +480,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
           s_ctl[0] = solved ? 1 : 0; s_ctl[1] = 0; s_ctl[3] = totn;
         }
       }
+      PW_EV(25);
       __syncthreads();
+      PW_EV(26);
       // ---- state transition (same machine as k_fit_cta), every thread ----
       if (s_ctl[0]) have_plane = true;   // S:49: an empty set keeps the previous plane
       const int tot_n = s_ctl[3];
@@ -395,31 +513,48 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
       }
       if (state == ST_DONE) n_ground = have_plane ? tot_n : 0;
     }
+    PW_EV(30);
     const unsigned gmask = have_plane ? member : 0u;
 
     // ---- stable partition: ground indices ascending, then non-ground indices ascending ----
+    // point k * NT + tid: tile (k, w) holds 32 consecutive points; the tiles' counts are scanned in (k, w) order
     {
-      const int gw = __reduce_add_sync(0xffffffffu, __popc(gmask & vmask));
-      const int vw = __reduce_add_sync(0xffffffffu, __popc(vmask));
-      if (lane == 0) { s_pcnt[w][2] = gw; s_pcnt[w][3] = vw; }
       int idxv[FP_SL];
 #pragma unroll
-      for (int k = 0; k < FP_SL; ++k) idxv[k] = ((vmask >> k) & 1u) ? reinterpret_cast<const int*>(P)[4 * (jbase + (k << 5)) + 3] : 0;   // all loads in flight (L2 hits)
-      __syncthreads();
-      int g_run = 0, ng_run = 0;
-      for (int q = 0; q < w; ++q) { g_run += s_pcnt[q][2]; ng_run += s_pcnt[q][3] - s_pcnt[q][2]; }
+      for (int k = 0; k < FP_SL; ++k) idxv[k] = ((vmask >> k) & 1u) ? reinterpret_cast<const int*>(P)[4 * (jbase + k * NT) + 3] : 0;   // all loads in flight (L2 hits)
+      unsigned bgk[FP_SL], bnk[FP_SL];
 #pragma unroll
       for (int k = 0; k < FP_SL; ++k) {
+        bgk[k] = 0u; bnk[k] = 0u;
         if (k < rpw) {   // uniform
           const bool v = (vmask >> k) & 1u, isg = v && ((gmask >> k) & 1u);
-          const unsigned bv = __ballot_sync(0xffffffffu, v), bg = __ballot_sync(0xffffffffu, isg);
-          const unsigned bn = bv & ~bg;
-          if (v) {
-            if (isg) out[g_run + __popc(bg & lt)] = idxv[k];
-            else out[n_ground + ng_run + __popc(bn & lt)] = idxv[k];
-          }
-          g_run += __popc(bg);
-          ng_run += __popc(bn);
+          bgk[k] = __ballot_sync(0xffffffffu, isg);
+          bnk[k] = __ballot_sync(0xffffffffu, v && !isg);
+          if (lane == 0) { s_tile[0][k * NW + w] = __popc(bgk[k]); s_tile[1][k * NW + w] = __popc(bnk[k]); }
+        }
+      }
+      PW_EV(31);
+      __syncthreads();
+      PW_EV(32);
+      if (w < 2) {   // warp 0: ground counts, warp 1: non-ground counts -> exclusive prefix over the rpw * NW tiles
+        const int nt = rpw * NW;
+        int carry = 0;
+        for (int t0 = 0; t0 < nt; t0 += 32) {
+          const int t = t0 + lane;
+          const int v = t < nt ? s_tile[w][t] : 0;
+          int incl = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+          if (t < nt) s_tile[w][t] = carry + incl - v;
+          carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < FP_SL; ++k) {
+        if (k < rpw && ((vmask >> k) & 1u)) {
+          if ((gmask >> k) & 1u) out[s_tile[0][k * NW + w] + __popc(bgk[k] & lt)] = idxv[k];
+          else out[n_ground + s_tile[1][k * NW + w] + __popc(bnk[k] & lt)] = idxv[k];
         }
       }
       if (tid == 0) {
@@ -431,6 +566,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
         r.d = s_plane[9];
       }
     }
+    __syncthreads();   // every thread is done with s_item / the tables of this patch
+    if (tid == NT - 32) s_item = nxt;
   }
 }
 

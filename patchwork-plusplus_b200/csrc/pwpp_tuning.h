@@ -4,7 +4,7 @@
 // classes), L2_MINB=3, X_KERNEL=1, X_MINB=1 and the GPU parity suite passed under it; the per-stage times of that run
 // (profiles/r01_tune.jsonl) show the fused WARP kernels slower than the unfused ones, so fusion is on for the CTA kernels only.
 #pragma once
-#define PWPP_FIT_GROUP_DEFAULT 1   /* 1: the group fit kernel (pwpp_fit_group.cuh) serves every patch up to 8192 points; 0: the size-classed kernels of pwpp_fit.cuh */
+#define PWPP_FIT_GROUP_DEFAULT 0   /* 1: the group fit kernel (pwpp_fit_group.cuh) serves every patch up to 8192 points; 0: the size-classed kernels of pwpp_fit.cuh */
 #define PWPP_HIST_PIPE_DEFAULT 2    /* k_bin_hist load pipelining: 0 none, 1 groups of 4, 2 groups of 2 */
 #define PWPP_SCATTER_V_DEFAULT 0    /* 1: software-pipelined k_scatter at 3 CTAs/SM */
 #define PWPP_SERIAL_FIT_DEFAULT 0   /* 1: the fit kernels run one after another on the call's stream instead of forked onto side streams */

@@ -227,7 +227,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 1;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 0;
   std::string last_launches;
 };
 
@@ -350,9 +350,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     else simt::launch("k_bin_hist<true,2>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 2>(HIST_ARGS); });
 #undef HIST_ARGS
   }
-  if (t->group) simt::launch("k_bin_scan_groups", nframes, 512, (nbp + 1) * sizeof(int),
-               [&] { k_bin_scan_groups(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
-  else if (t->m_half && t->l2_wide) simt::launch("k_bin_scan<5888,256>", nframes, 512, (nbp + 1) * sizeof(int),
+  if (t->m_half && t->l2_wide) simt::launch("k_bin_scan<5888,256>", nframes, 512, (nbp + 1) * sizeof(int),
                [&] { k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
   else if (t->m_half) simt::launch("k_bin_scan<4096,256>", nframes, 512, (nbp + 1) * sizeof(int),
                [&] { k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
@@ -372,10 +370,12 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
-  if (t->group) {   // the group fit kernel (pwpp_fit_group.cuh) serves every class but X
-    simt::launch("k_fit_patch<C>", pg, GRP_C_NW * 32, 0, [&] { k_fit_patch<GRP_C_NW, 1, GRP_CLS_C>(FIT_ARGS); });
-    simt::launch("k_fit_patch<B>", pg, GRP_B_NW * 32, 0, [&] { k_fit_patch<GRP_B_NW, 2, GRP_CLS_B>(FIT_ARGS); });
-    simt::launch("k_fit_group<A>", pg, GRP_A_NW * 32, (size_t) GRP_A_PTS * 16, [&] { k_fit_group<GRP_A_PTS, GRP_A_MP, GRP_A_NW, 3, GRP_CLS_A>(FIT_ARGS); });
+  if (t->group) {   // patches above 512 points: k_fit_patch (pwpp_fit_patch.cuh); classes S, M, X below as always
+    simt::launch("k_fit_patch<16>", pg, 16 * 32, (size_t) 16 * FP_STG * 16, [&] { k_fit_patch<16, 1, 4>(FIT_ARGS); });
+    simt::launch("k_fit_patch<8>", pg, 8 * 32, (size_t) 8 * FP_STG * 16, [&] { k_fit_patch<8, 2, 3>(FIT_ARGS); });
+    simt::launch("k_fit_patch<4>", pg, 4 * 32, (size_t) 4 * FP_STG * 16, [&] { k_fit_patch<4, 4, 2>(FIT_ARGS); });
+    simt::launch("k_fit_warp<true,1,1>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2>(FIT_ARGS); });
+    simt::launch("k_fit_resident<8,8,0>", pg, FIT_THREADS, 0, [&] { k_fit_resident<8, 8, 0, 2>(FIT_ARGS); });
   } else {
   if (t->m_half) simt::launch("k_fit_resident<16,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<16, 16, 1, 2>(FIT_ARGS); });
   if (t->m_resident) simt::launch("k_fit_resident<32,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<32, 16, 1, 2>(FIT_ARGS); });

@@ -31,7 +31,8 @@ ev = (C.c_uint * (4 * 16384))()
 lib.pwpp_debug_events(eng._h, ev, 0)   # clear
 eng.reset(); eng.estimate_device(pts.data_ptr(), offs.numpy(), True, st.cuda_stream)
 torch.cuda.synchronize()
-n = lib.pwpp_debug_events(eng._h, ev, 16384)
-E = np.frombuffer(ev, dtype=np.uint32).reshape(-1, 4)[:n]
+lib.pwpp_debug_events(eng._h, ev, 16384)
+E = np.frombuffer(ev, dtype=np.uint32).reshape(-1, 4)
+E = E[E[:, 3] == 1]
 np.save(os.path.join(REPO, "gpurun_out", "events.npy"), E)
-print("events", n)
+print("events", len(E))
