@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--ref-frames-per-step", type=int, default=0, help="--impl reference: frames per step (0 = 8 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streaming", default="", help="also time streaming mode 'SxT': S sensor streams x T consecutive frames each, T batched calls with the temporal state carried (SURVEY.md 8d config 3), e.g. 64x16; reported under the key 'streaming'")
+    ap.add_argument("--streaming", default="64x16", help="streaming mode 'SxT': S sensor streams x T consecutive frames each, T batched calls with the temporal state carried (SURVEY.md 8d config 3); reported under the key 'streaming' ('' = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records: streaming, dense1m (BASELINE config 5 shape, 32 frames per GPU), latency_us (config 2), parity_vs_reference")
+    ap.add_argument("--dense-frames", type=int, default=32, help="frames per GPU of the dense1m sub-record")
     return ap.parse_args()
 
 
@@ -266,6 +268,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # one process per GPU: pin this process (and the page-locked buffers it allocates from here on) to the GPU's NUMA node
+    numa_node = pwpp_b200.bind_host_to_device(local)
     dist = pwpp_dist.Dist(backend="nccl")   # rendezvous + barriers + max-over-ranks only; no data-path collective
     barrier = dist.barrier
 
@@ -334,11 +338,27 @@ def run_ours(args):
     ng = [eng.num_ground(f) + eng.num_nonground(f) for f in range(0, F, max(1, F // 16))]
     assert all(a == int(offs_np[f + 1] - offs_np[f]) for a, f in zip(ng, range(0, F, max(1, F // 16)))), "partition invariant violated"
 
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline: every kernel against the points IT processes (20 B/point algorithmic) ----
+    # the front end, k_gle and k_emit see every point; a fit kernel only the points of the patches in its size class
+    # (class limits of csrc/pwpp_fit.cuh; patch sizes read back from a sample of frames and scaled to the batch)
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
-    top = max(stage_ms, key=stage_ms.get)
     peak, peak_src = measured_peak_gbs()
-    achieved = ALGO_BYTES_PER_POINT * total_pts / (stage_ms[top] / 1e3) / 1e9
+    sample_f = list(range(0, F, max(1, F // 64)))
+    cls_pts = {"k_fit_S": 0, "k_fit_M": 0, "k_fit_L1": 0, "k_fit_L2": 0, "k_fit_L3": 0, "k_fit_X": 0}
+    samp_pts = 0
+    for f in sample_f:
+        br = np.frombuffer(eng.bin_results(f), dtype=np.dtype([("d", np.float64, 10), ("n", np.int32), ("ng", np.int32), ("verdict", np.int32), ("fitted", np.int32)]))
+        nfit = br["n"][br["fitted"] != 0].astype(np.int64)
+        samp_pts += int(offs_np[f + 1] - offs_np[f])
+        for name, lo, hi in (("k_fit_S", 0, 64), ("k_fit_M", 64, 512), ("k_fit_L1", 512, 2048), ("k_fit_L2", 2048, 4096), ("k_fit_L3", 4096, 8192), ("k_fit_X", 8192, 1 << 30)):
+            cls_pts[name] += int(nfit[(nfit > lo) & (nfit <= hi)].sum())
+    scale = total_pts / max(samp_pts, 1)
+    per_kernel = {}
+    for k, t in stage_ms.items():
+        pts_k = cls_pts[k] * scale if k in cls_pts else float(total_pts)
+        gbs = ALGO_BYTES_PER_POINT * pts_k / max(t, 1e-9) / 1e6
+        per_kernel[k] = {"ms": t, "points": int(pts_k), "achieved_gbs": gbs, "frac": gbs / peak}
+    top = max(stage_ms, key=stage_ms.get)
     traffic = None
     tpath = os.path.join(REPO, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
@@ -348,9 +368,12 @@ def run_ours(args):
                 traffic = tj[top]["dram_bytes"] / tj[top]["frames"] * F
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * total_pts,
-                "stage_ms": stage_ms, "stage_ms_note": "mean over K extra steps with CUDA events around every kernel (fit kernels serialised); the timed region itself runs without them", "whole_path_frac": (ALGO_BYTES_PER_POINT * total_pts / (ms / args.steps / 1e3) / 1e9) / peak}
+    whole = (ALGO_BYTES_PER_POINT * total_pts / (ms / args.steps / 1e3) / 1e9) / peak
+    roofline = {"bound": "hbm", "kernel": top, "achieved": per_kernel[top]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[top]["frac"],
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * per_kernel[top]["points"],
+                "accounting": "achieved = 20 B x the points the kernel's own work queue holds / its mean CUDA-event time; whole_path_frac = 20 B x all points / step time (the primary figure)",
+                "whole_path_frac": whole, "whole_path_achieved_gbs": whole * peak, "per_kernel": per_kernel, "stage_ms": stage_ms,
+                "stage_ms_note": "mean over K extra steps with CUDA events around every kernel (fit kernels serialised); the timed region itself runs without them"}
 
     # ---- end to end through the host entry point of the C-ABI (page-locked host buffers) ----
     e2e = None
@@ -366,8 +389,9 @@ def run_ours(args):
         def e2e_step():
             nonlocal sink
             eng.reset()
-            eng.estimate_host_strided(ptrs, ns, 4, 4, 1)      # H2D of the batch + all kernels
-            sink += int(eng.ground_indices(0)[0]) if eng.num_ground(0) else 0  # first getter pulls ALL frames' index lists D2H
+            eng.estimate_host_strided(ptrs, ns, 4, 4, 1)      # H2D of the batch + all kernels + D2H of every frame's lists into the page-locked result buffer
+            idx, ng, off = eng.host_index_lists()              # zero-copy view of all 2 x F lists (pwpp_host_results)
+            sink += int(idx[0]) + int(ng[F - 1])
         e2e_step()
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -376,13 +400,27 @@ def run_ours(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt = dist.max_over_ranks(dt)
-        e2e = {"value": world * F * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": total_pts * 16 + (F + 1) * 12,
+        # what the per-frame copying getters of the reference surface add on top (2 x F host memcpys out of the result buffer)
+        g_bufs = [np.empty(eng.num_ground(f), np.int32) for f in range(F)]
+        n_bufs = [np.empty(eng.num_nonground(f), np.int32) for f in range(F)]
+        tc = time.perf_counter()
+        for f in range(F):
+            if g_bufs[f].size: eng.lib.pwpp_copy_ground_indices(eng._h, f, g_bufs[f].ctypes.data)
+            if n_bufs[f].size: eng.lib.pwpp_copy_nonground_indices(eng._h, f, n_bufs[f].ctypes.data)
+        copy_ms = 1e3 * (time.perf_counter() - tc)
+        assert sum(b.size for b in g_bufs) + sum(b.size for b in n_bufs) <= total_pts
+        del g_bufs, n_bufs
+        h2d = total_pts * 16 + (F + 1) * 12
+        e2e = {"value": world * F * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": total_pts * 4 + 3 * F * 4, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "api": "pwpp_estimate_host + pwpp_copy_*_indices (C-ABI), page-locked host buffers"}
+               "h2d_gbs_per_rank": h2d / (dt / args.e2e_steps) / 1e9, "numa_node": numa_node,
+               "copying_getters_ms": copy_ms,
+               "api": "pwpp_estimate_host + pwpp_host_results (zero-copy view of all index lists in the page-locked result buffer); copying_getters_ms = the 2 x F pwpp_copy_*_indices calls a caller that wants private copies pays on top (host memcpy, not in value)"}
 
-    # ---- optional: streaming mode, S streams x T consecutive frames (state carried from call to call) ----
-    streaming = None
-    if args.streaming:
+    # ---- extra records (never cost the main line; collectives stay outside the try blocks) ----
+    # streaming mode: S streams x T consecutive frames, state carried from call to call
+    streaming, sms = None, -1.0
+    if args.streaming and not args.no_extras:
         try:
             S, T = (int(x) for x in args.streaming.lower().split("x"))
             assert 1 <= S and 1 <= T and S * T <= F, "needs S*T <= --frames-per-gpu"
@@ -399,20 +437,88 @@ def run_ours(args):
             for _ in range(3):
                 sequence()
             s1.record(); torch.cuda.synchronize()
-            sms = dist.max_over_ranks(s0.elapsed_time(s1) / 3)
-            streaming = {"streams": S, "frames_per_stream": T, "ms_per_sequence": sms, "value": world * S * T / (sms / 1e3), "unit": UNIT,
-                         "ms_per_call": sms / T, "note": "T batched calls of S frames, adaptive state carried between calls"}
+            sms = s0.elapsed_time(s1) / 3
             seng.close()
-        except Exception as ex:   # an extra: never costs the main line
+        except Exception as ex:
             streaming = {"error": repr(ex)[:200]}
+        sms = dist.max_over_ranks(sms)
+        if streaming is None and sms > 0:
+            streaming = {"streams": S, "frames_per_stream": T, "ms_per_sequence": sms, "value": world * S * T / (sms / 1e3), "unit": UNIT,
+                         "ms_per_call": sms / T, "note": "T batched calls of S frames per GPU, adaptive state carried between calls"}
+
+    # dense sensor (BASELINE config 5 shape: ~1.2 M points per frame), --dense-frames frames per GPU, device-resident
+    dense, dms, dstage = None, -1.0, None
+    if args.sensor == "kitti64" and not args.no_extras and args.dense_frames > 0:
+        dmean = 0.0
+        try:
+            DF = args.dense_frames
+            dshard = pwpp_dist.weak_shard(DF, rank, world)
+            dpts, doffs = synth.make_batch(SEED, dshard.start, DF, "dense1m", dev)
+            doffs_np = doffs.numpy()
+            dmean = float(doffs_np[-1]) / DF
+            deng = pwpp_b200.Engine(device=local, num_streams=DF, max_points_per_frame=int(np.diff(doffs_np).max()))
+
+            def dstep():
+                deng.reset(); deng.estimate_device(dpts.data_ptr(), doffs_np, True, stream)
+            for _ in range(3):
+                dstep()
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for _ in range(5):
+                dstep()
+            d1.record(); torch.cuda.synchronize()
+            dms = d0.elapsed_time(d1) / 5
+            deng.set_profiling(True); dstep(); dstage = deng.stage_times_ms(); deng.set_profiling(False)
+            assert deng.num_ground(0) + deng.num_nonground(0) == int(doffs_np[1] - doffs_np[0])
+            deng.close(); del dpts
+        except Exception as ex:
+            dense = {"error": repr(ex)[:200]}
+        dms = dist.max_over_ranks(dms)
+        if dense is None and dms > 0:
+            dense = {"frames_per_gpu": DF, "mean_points": dmean, "ms_per_step": dms, "value": world * DF / (dms / 1e3), "unit": UNIT,
+                     "points_per_s": world * DF * dmean / (dms / 1e3), "whole_path_frac": (ALGO_BYTES_PER_POINT * DF * dmean / (dms / 1e3) / 1e9) / peak,
+                     "stage_ms": dstage, "workload": f"batch={DF} synthetic dense1m frames per GPU (Ouster-128 layout x 16384 azimuth steps), fresh state per frame, device-resident"}
+
+    # single-frame latency of the drop-in C++ class (BASELINE config 2): examples/pwpp_latency.cpp on the first fixture scan
+    latency = None
+    if rank == 0 and not args.no_extras:
+        try:
+            exe = os.path.join(PKG, "lib", "pwpp_latency")
+            gold = os.path.join(REPO, "tests", "golden", "kitti_000000.npz")
+            if os.path.exists(exe) and os.path.exists(gold):
+                import tempfile
+                scan = np.ascontiguousarray(np.load(gold)["xyzi_t"].T)
+                with tempfile.NamedTemporaryFile(suffix=".bin") as tf:
+                    scan.tofile(tf.name)
+                    env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))
+                    out = subprocess.run([exe, tf.name, "300", "30"], capture_output=True, text=True, timeout=120, env=env).stdout
+                latency = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+                latency["what"] = "PatchWorkpp::estimateGround + getGroundIndices + getNongroundIndices on kitti_000000 (124,668 points), host clock around the call sequence, median of 300 calls after 30 warm-up calls; H2D and D2H inside"
+        except Exception as ex:
+            latency = {"error": repr(ex)[:200]}
 
     # ---- CPU baseline on the host cores of this box (rank 0 only) ----
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
         T = os.cpu_count() or 1
         nsample = min(F, max(T * 4, 64))
         frames = [pts[int(offs_np[f]):int(offs_np[f + 1])].cpu().numpy() for f in range(nsample)]
         cpu, _, _ = cpu_reference_throughput(frames, args.cpu_seconds, cycle=True)
+        if not args.no_extras:
+            # labels of the timed result against the reference's own code on the same arrays (first 64 frames of the batch)
+            try:
+                import oracle_py as O
+                labels = mism = 0
+                for f in range(min(64, nsample)):
+                    r = O.Reference(stable_sort=False); r.estimate(frames[f]); g_r = r.getGroundIndices(); r.close()
+                    mr = np.zeros(len(frames[f]), bool); mr[g_r] = True
+                    me = np.zeros(len(frames[f]), bool); me[eng.ground_indices(f)] = True
+                    labels += len(frames[f]); mism += int((mr != me).sum())
+                parity = {"frames": min(64, nsample), "labels": labels, "mismatches": mism,
+                          "note": "ground / non-ground label of every point vs oracle/_ref/libpwref.so (the reference's patchworkpp.cpp, fp32) on the same arrays; the CUDA path computes in double (DESIGN.md section 3)"}
+            except Exception as ex:
+                parity = {"error": repr(ex)[:200]}
 
     if rank == 0:
         out = {
@@ -424,8 +530,9 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {total_pts * 16 / 1e9:.2f} GB of points per step vs 126 MB L2"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
-        if streaming is not None:
-            out["streaming"] = streaming
+        for k, v in (("streaming", streaming), ("dense1m", dense), ("latency_us", latency), ("parity_vs_reference", parity)):
+            if v is not None:
+                out[k] = v
         print(json.dumps(out), flush=True)
     # orderly teardown: release the engine (CUDA buffers, streams) while the CUDA context is still alive
     eng.close()

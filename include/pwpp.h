@@ -167,6 +167,19 @@ double pwpp_time_us(pwpp_ctx* ctx);
  * *d_num_ground -> int32[nframes]. Valid until the next estimate call. */
 int pwpp_device_results(pwpp_ctx* ctx, const int32_t** d_indices, const int32_t** d_num_ground);
 
+/* Host-side zero-copy view of the index lists of the last call (batch consumers: the per-frame getters above copy each
+ * list once more, which for a 1024-frame batch is 0.5 GB of host memcpy): *h_indices -> the page-locked int32 buffer the
+ * device lists were copied into, laid out like pwpp_device_results (frame f's region starts at point offset
+ * *h_offsets[f]: ground list, then nonground list); *h_num_ground -> int32[nframes]. Fetches the lists from the device
+ * if the call was a device-input call. Valid until the next estimate call. */
+int pwpp_host_results(pwpp_ctx* ctx, const int32_t** h_indices, const int32_t** h_num_ground, const int64_t** h_offsets);
+
+/* Placement helper for multi-GPU hosts: binds the CALLING THREAD (and with it the page-locked buffers it allocates
+ * afterwards: first touch) to the CPUs of the NUMA node the device hangs off (sysfs numa_node / cpulist of its PCI
+ * function). Returns the node (>= 0), or -1 if the topology could not be read (nothing changed). Call it before
+ * pwpp_host_alloc / pwpp_create in a one-process-per-GPU launch. */
+int pwpp_bind_host_to_device(int device);
+
 /* ---- per-bin diagnostics for parity tests (not part of the reference surface) ------------ */
 
 /* Per-bin record of the last call, frame f: bin ids in (zone,ring,sector) order. */

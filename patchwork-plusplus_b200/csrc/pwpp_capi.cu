@@ -3,7 +3,10 @@
 // There is no CPU fallback; without a CUDA device pwpp_create() fails with PWPP_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -46,12 +49,15 @@ int fail(int code, const std::string& msg) {
     }                                                                                                        \
   } while (0)
 
+unsigned long long g_alloc_gen = 0;   // bumped whenever a device buffer moves: captured CUDA graphs hold the old pointers
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    ++g_alloc_gen;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -80,6 +86,12 @@ struct PinBuf {
 };
 
 }  // namespace
+
+// N x cols column-major (an Eigen::MatrixXf, reference patchworkpp.h:152) -> packed float4 {x, y, z, intensity | 0}
+__global__ void k_repack_colmajor(const float* __restrict__ src, long long n, int cols, float4* __restrict__ dst) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = make_float4(src[i], src[n + i], src[2 * n + i], cols == 4 ? src[3 * n + i] : 0.f);
+}
 
 typedef void (*FitKernel)(const float4*, FrameTable, const StreamState*, Geometry, AlgoParams, int, const int*, WorkQueues, int*, BinFit*);
 struct FitLaunch {
@@ -118,6 +130,7 @@ struct pwpp_ctx {
 
   // per-call work buffers
   DevBuf<float4> d_in;            // host path only
+  DevBuf<float> d_cm;             // host path: column-major frames as uploaded, repacked on the device
   DevBuf<long long> d_pt_off;     // [F+1]
   DevBuf<int> d_chunk_off;        // [F+1]
   DevBuf<unsigned short> d_bin_ids;
@@ -155,6 +168,13 @@ struct pwpp_ctx {
   bool counts_fetched = false, idx_fetched = false, patches_fetched = false;
   double last_time_us = 0.0;
   cudaStream_t last_stream = nullptr;
+
+  // small calls (the reference's one-frame-per-call pattern): the launch sequence replayed as a CUDA graph
+  struct GraphKey { int nf, has_intensity, chunks; unsigned long long gen; const void* pts; };
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  GraphKey gkey[2] = {};
+  long long glaunches[2] = {0, 0};
+  int sw_graph = 1;
 };
 
 namespace {
@@ -237,9 +257,10 @@ int prepare_call(pwpp_ctx* ctx, int nframes, cudaStream_t s) {
 // Launches the whole path for frames [f0, f0 + nf) of the prepared call on stream s. A frame range is the same
 // launch sequence over per-frame arrays offset by f0 (frame tables hold absolute point / chunk positions), which is
 // what lets pwpp_estimate_host pipeline chunks of frames against their H2D / D2H copies.
-int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_intensity, cudaStream_t s, bool prof) {
+int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_intensity, cudaStream_t s, bool prof, int chunks_override) {
   int max_chunks = 0;
   for (int f = f0; f < f0 + nf; ++f) max_chunks = std::max(max_chunks, ctx->chunk_off[f + 1] - ctx->chunk_off[f]);
+  if (chunks_override > 0) max_chunks = chunks_override;   // graph capture: grids sized for a range of frame sizes (surplus CTAs exit at once)
   const int nb = ctx->g.nbins, nbp = ctx->nbp, nb_all = nb + PW_NUM_PSEUDO;
   const int nframes = nf;
   FrameTable ft{ctx->d_pt_off.p + f0, ctx->d_chunk_off.p + f0};
@@ -353,6 +374,47 @@ int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_int
 #undef STAGE_MARK
   if (prof) ctx->stage_valid = true;
   CU_TRY(cudaGetLastError());
+  ctx->last_pts = d_pts;
+  ctx->last_stream = s;
+  return PWPP_OK;
+}
+
+// Small calls are launch-bound (ten kernels of a few microseconds each plus the fork / join events of the fit kernels): the
+// sequence is captured once per (frames, intensity flag, grid size class, buffer generation) and replayed as one CUDA
+// graph. Only for calls whose input sits in the ctx's own upload buffer (the host entry point), so the captured pointers
+// stay valid; PWPP_GRAPH=0 switches it off.
+constexpr int GRAPH_MAX_FRAMES = 16;
+int launch_range(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int has_intensity, cudaStream_t s, bool prof) {
+  if (prof || !ctx->sw_graph || nf > GRAPH_MAX_FRAMES || f0 != 0 || d_pts != ctx->d_in.p) return launch_range_impl(ctx, f0, nf, d_pts, has_intensity, s, prof, 0);
+  int max_chunks = 0;
+  for (int f = 0; f < nf; ++f) max_chunks = std::max(max_chunks, ctx->chunk_off[f + 1] - ctx->chunk_off[f]);
+  const int capc = std::max(8, (max_chunks + 7) & ~7);
+  const int slot = has_intensity ? 1 : 0;
+  const pwpp_ctx::GraphKey key{nf, has_intensity, capc, g_alloc_gen, (const void*) d_pts};
+  pwpp_ctx::GraphKey& have = ctx->gkey[slot];
+  if (!ctx->gexec[slot] || have.nf != key.nf || have.chunks != key.chunks || have.gen != key.gen || have.pts != key.pts) {
+    if (ctx->gexec[slot]) { cudaGraphExecDestroy(ctx->gexec[slot]); ctx->gexec[slot] = nullptr; }
+    const long long l0 = ctx->launches;
+    CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = launch_range_impl(ctx, 0, nf, d_pts, has_intensity, s, false, capc);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc != PWPP_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->sw_graph = 0;   // capture is not available here: fall back to plain launches for good
+      ctx->launches = l0;
+      return launch_range_impl(ctx, 0, nf, d_pts, has_intensity, s, false, 0);
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&ctx->gexec[slot], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { ctx->gexec[slot] = nullptr; ctx->sw_graph = 0; ctx->launches = l0; cudaGetLastError(); return launch_range_impl(ctx, 0, nf, d_pts, has_intensity, s, false, 0); }
+    ctx->glaunches[slot] = ctx->launches - l0;
+    ctx->launches = l0;
+    have = key;
+  }
+  CU_TRY(cudaGraphLaunch(ctx->gexec[slot], s));
+  ctx->launches += ctx->glaunches[slot];
   ctx->last_pts = d_pts;
   ctx->last_stream = s;
   return PWPP_OK;
@@ -476,6 +538,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_l2_wide = env_int("PWPP_L2_WIDE", PWPP_L2_WIDE_DEFAULT, 0, 1);
   ctx->sw_m_half = env_int("PWPP_M_HALF", PWPP_M_HALF_DEFAULT, 0, 1);
   ctx->sw_group = env_int("PWPP_FIT_GROUP", PWPP_FIT_GROUP_DEFAULT, 0, 1);
+  ctx->sw_graph = env_int("PWPP_GRAPH", 1, 0, 1);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -634,10 +697,11 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  for (int i = 0; i < 2; ++i) if (ctx->gexec[i]) cudaGraphExecDestroy(ctx->gexec[i]);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int i = 0; i < 2; ++i) if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);
   for (int q = 0; q < 5; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
-  ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
+  ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_cm.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
   ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release(); ctx->d_front_items.release(); ctx->d_front_ctr.release();
   for (int c = 0; c < NUM_CLASSES; ++c) ctx->d_wq_items[c].release();
@@ -750,6 +814,16 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
         while (f_last + 1 < f1 && n[f_last + 1] > 0 && pts[f_last + 1] == pts[f_last] + n[f_last] * 4) { ++f_last; run += n[f_last]; }
         CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], pts[f], (size_t) run * sizeof(float4), cudaMemcpyHostToDevice, s_in));
         f = f_last;
+        continue;
+      }
+      if (row_stride == 1 && col_stride == cnt && cnt > 1) {
+        // column-major frame (what the Eigen overload hands over): its cols x n floats are one contiguous block; upload it as
+        // it is and repack on the device instead of gathering 4 strided columns per point on the host
+        if ((size_t) total * 4 > ctx->d_cm.cap) { CU_TRY(cudaStreamSynchronize(s_in)); CU_TRY(ctx->d_cm.reserve((size_t) total * 4)); }
+        float* cm = ctx->d_cm.p + (size_t) ctx->pt_off[f] * 4;
+        CU_TRY(cudaMemcpyAsync(cm, pts[f], (size_t) cnt * cols * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        k_repack_colmajor<<<(unsigned) ((cnt + 255) / 256), 256, 0, s_in>>>(cm, cnt, cols, ctx->d_in.p + ctx->pt_off[f]);
+        ++ctx->launches;
         continue;
       }
       if (!staged_any) { CU_TRY(ctx->h_in.reserve((size_t) std::max<long long>(total, 1))); staged_any = true; }
@@ -962,6 +1036,51 @@ int pwpp_device_results(pwpp_ctx* ctx, const int32_t** d_indices, const int32_t*
   if (d_indices) *d_indices = ctx->d_out_idx.p;
   if (d_num_ground) *d_num_ground = ctx->d_counts.p;
   return PWPP_OK;
+}
+
+int pwpp_host_results(pwpp_ctx* ctx, const int32_t** h_indices, const int32_t** h_num_ground, const int64_t** h_offsets) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  if (ctx->last_nframes <= 0) return fail(PWPP_ERR_INVALID_ARG, "no estimate call yet");
+  int rc = fetch_indices(ctx);
+  if (rc) return rc;
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset table type");
+  if (h_indices) *h_indices = ctx->h_out_idx.p;
+  if (h_num_ground) *h_num_ground = ctx->h_counts.p;
+  if (h_offsets) *h_offsets = reinterpret_cast<const int64_t*>(ctx->pt_off.data());
+  return PWPP_OK;
+}
+
+int pwpp_bind_host_to_device(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* c = bus; *c; ++c) *c = (char) std::tolower((unsigned char) *c);
+  std::string base = std::string("/sys/bus/pci/devices/") + bus;
+  int node = -1;
+  if (FILE* f = std::fopen((base + "/numa_node").c_str(), "r")) { if (std::fscanf(f, "%d", &node) != 1) node = -1; std::fclose(f); }
+  if (node < 0) return -1;
+  std::string list;
+  if (FILE* f = std::fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r")) {
+    char buf[4096] = {0};
+    if (std::fgets(buf, sizeof buf, f)) list = buf;
+    std::fclose(f);
+  }
+  if (list.empty()) return -1;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int ncpu = 0;
+  const char* p = list.c_str();
+  while (*p) {   // "0-31,64-95"
+    char* end = nullptr;
+    long a = std::strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    if (*end == '-') { p = end + 1; b = std::strtol(p, &end, 10); }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int) c, &set); ++ncpu; }
+    p = (*end == ',') ? end + 1 : end;
+    if (*end != ',' ) break;
+  }
+  if (ncpu == 0 || sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+  return node;
 }
 
 int pwpp_copy_bin_results(pwpp_ctx* ctx, int f, pwpp_bin_result* dst) {

@@ -57,8 +57,15 @@ def load_library():
     lib.pwpp_stage_times_ms.argtypes = [vp, C.POINTER(C.c_float)]; lib.pwpp_stage_times_ms.restype = i32
     lib.pwpp_stage_name.argtypes = [i32]; lib.pwpp_stage_name.restype = C.c_char_p
     lib.pwpp_launch_count.argtypes = [vp]; lib.pwpp_launch_count.restype = i64
+    lib.pwpp_host_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]; lib.pwpp_host_results.restype = i32
+    lib.pwpp_bind_host_to_device.argtypes = [i32]; lib.pwpp_bind_host_to_device.restype = i32
     _lib = lib
     return lib
+
+
+def bind_host_to_device(device: int) -> int:
+    """pwpp_bind_host_to_device: pin the calling thread to the CPUs of the GPU's NUMA node (returns the node or -1)."""
+    return int(load_library().pwpp_bind_host_to_device(device))
 
 
 class PwppError(RuntimeError):
@@ -206,6 +213,18 @@ class Engine:
         idx = torch.as_tensor(_View(d_idx, total), device="cuda") if total > 0 else torch.empty(0, dtype=torch.int32, device="cuda")
         ng = torch.as_tensor(_View(d_ng, nf), device="cuda")
         return idx, ng
+
+    def host_index_lists(self):
+        """Zero-copy numpy views of the last call's results in the page-locked result buffer: (indices int32[total],
+        num_ground int32[nframes], offsets int64[nframes + 1]). Frame f: ground = indices[off[f] : off[f] + ng[f]], non-ground
+        follows up to off[f + 1] (minus dropped points). Valid until the next estimate call."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self.lib.pwpp_host_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        total, nf = int(sum(self._n)), len(self._n)
+        idx = np.ctypeslib.as_array((C.c_int32 * max(total, 1)).from_address(a.value))[:total]
+        ng = np.ctypeslib.as_array((C.c_int32 * nf).from_address(b.value))
+        off = np.ctypeslib.as_array((C.c_int64 * (nf + 1)).from_address(c.value))
+        return idx, ng, off
 
     def device_results(self):
         a, b = C.c_void_p(), C.c_void_p()
