@@ -25,6 +25,7 @@
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #if defined(__has_include)
@@ -98,6 +99,7 @@ class PatchWorkpp {
       p.flatness_thr[k] = k < (int) params_.flatness_thr.size() ? params_.flatness_thr[k] : 0.0;
     }
     if (pwpp_create(&p, device, 1, 0, &ctx_) != PWPP_OK) throw std::runtime_error(std::string("PatchWorkpp: ") + pwpp_last_error());
+    pwpp_set_output_order(ctx_, PWPP_ORDER_REFERENCE);   // the drop-in class emits the reference's order (stable per-bin z sort)
     std::cout << "PatchWorkpp::PatchWorkpp() - INITIALIZATION COMPLETE" << std::endl;  // reference :149
   }
   ~PatchWorkpp() { if (ctx_) pwpp_destroy(ctx_); }
@@ -114,6 +116,32 @@ class PatchWorkpp {
     check(pwpp_estimate_host(ctx_, 1, ptrs, ns, cols >= 4 ? 4 : 3, row_stride, col_stride));
     n_ = n;
     ran_ = true;
+  }
+
+  // Device-resident cloud (zero-copy path): packed N x 4 {x,y,z,intensity} or N x 3 rows in device memory.
+  // stream == nullptr: the device is synchronized before and after (any producer / consumer stream is safe); otherwise the
+  // work is enqueued on `stream` and the device results below are valid in stream order.
+  void estimateGroundDevice(const float* d_data, int64_t n, int cols, void* stream = nullptr) {
+    if (cols != 3 && cols != 4) throw std::runtime_error("PatchWorkpp::estimateGroundDevice: packed N x 3 or N x 4 float32 rows expected");
+    if (cols < 4 && params_.enable_RNR) std::cout << "RNR requires intensity information !" << std::endl;  // reference src :380
+    const int64_t offs[2] = {0, n};
+    if (!stream) check(pwpp_device_synchronize(ctx_));
+    check(cols == 4 ? pwpp_estimate_device(ctx_, 1, d_data, offs, 1, stream) : pwpp_estimate_device_xyz(ctx_, 1, d_data, offs, stream));
+    if (!stream) check(pwpp_device_synchronize(ctx_));
+    n_ = n;
+    ran_ = true;
+  }
+  // device views of the last call's index lists (int32, valid until the next estimateGround*): {pointer, count}
+  std::pair<const int32_t*, int64_t> groundIndicesDevice() {
+    const int32_t* idx = nullptr;
+    check(pwpp_device_results(ctx_, &idx, nullptr));
+    return {idx, count(pwpp_num_ground(ctx_, 0))};
+  }
+  std::pair<const int32_t*, int64_t> nongroundIndicesDevice() {
+    const int32_t* idx = nullptr;
+    check(pwpp_device_results(ctx_, &idx, nullptr));
+    const int64_t ng = count(pwpp_num_ground(ctx_, 0));
+    return {idx + ng, count(pwpp_num_nonground(ctx_, 0))};
   }
 
   double getHeight() { return pwpp_height(ctx_, 0); }        // reference :154 (adaptive sensor height)
@@ -140,6 +168,10 @@ class PatchWorkpp {
   Eigen::MatrixX3f getCenters() { return toEigenCloud(getCentersVec()); }
   Eigen::MatrixX3f getNormals() { return toEigenCloud(getNormalsVec()); }
 #endif
+
+  // true (default): index lists in the reference's order inside every bin (ascending z, R-VPF removals first in the
+  // non-ground part); false: ascending point index inside a bin (no sorting pass)
+  void setReferenceOrder(bool on) { check(pwpp_set_output_order(ctx_, on ? PWPP_ORDER_REFERENCE : PWPP_ORDER_BIN)); }
 
   pwpp_ctx* handle() { return ctx_; }
 

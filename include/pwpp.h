@@ -134,6 +134,14 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
  * are ready after pwpp_synchronize() (the copy_* getters synchronize themselves). */
 int pwpp_estimate_device(pwpp_ctx* ctx, int nframes, const void* d_pts,
                          const int64_t* h_offsets, int has_intensity, void* cuda_stream);
+
+/* The same for packed N x 3 rows {x, y, z} resident on the device (no intensity: RNR is skipped like for N x 3 host input,
+ * S:379-382): the rows are padded to the kernels' 16-byte points by a device-side copy into the ctx's input buffer. */
+int pwpp_estimate_device_xyz(pwpp_ctx* ctx, int nframes, const void* d_xyz, const int64_t* h_offsets, void* cuda_stream);
+
+/* cudaDeviceSynchronize() on the ctx's device: what a binding calls before handing device memory produced on an unknown
+ * stream to pwpp_estimate_device (and what makes its results visible to every stream afterwards). */
+int pwpp_device_synchronize(pwpp_ctx* ctx);
 int pwpp_synchronize(pwpp_ctx* ctx);
 
 /* ---- results of the last estimate call, per frame/stream f ------------------------------ */
@@ -166,6 +174,18 @@ double pwpp_time_us(pwpp_ctx* ctx);
  * offset); inside a region the ground list comes first, then the nonground list.
  * *d_num_ground -> int32[nframes]. Valid until the next estimate call. */
 int pwpp_device_results(pwpp_ctx* ctx, const int32_t** d_indices, const int32_t** d_num_ground);
+
+/* Order of the points INSIDE a bin's contribution to the index lists (the order of the bins, of the RNR / out-of-range
+ * prefix and of the TGR-reverted patches is always the reference's, S:264-304):
+ *   PWPP_ORDER_BIN        ascending point index (default of the C-ABI: what the fit kernels produce, no extra work);
+ *   PWPP_ORDER_REFERENCE  the reference's order: ground part in ascending z; non-ground part = R-VPF removals by iteration,
+ *                         each in ascending z, then the final rejects in ascending z (S:199, S:495-504, S:529-541); equal z
+ *                         in ascending point index (= the reference with a stable per-bin sort). One extra kernel (a sort of
+ *                         every fitted patch). The drop-in C++ class and pypatchworkpp select it by default.
+ * Takes effect with the next estimate call. */
+#define PWPP_ORDER_BIN 0
+#define PWPP_ORDER_REFERENCE 1
+int pwpp_set_output_order(pwpp_ctx* ctx, int order);
 
 /* Host-side zero-copy view of the index lists of the last call (batch consumers: the per-frame getters above copy each
  * list once more, which for a 1024-frame batch is 0.5 GB of host memcpy): *h_indices -> the page-locked int32 buffer the

@@ -71,6 +71,11 @@ def build_examples(force=False):
     if force or _newer(out2, [src2, hdr, core]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"), src2, "-o", out2,
                                "-L" + LIB, "-lpwpp_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    src3 = os.path.join(REPO, "tests", "pc2_driver.cpp")   # the PointCloud2 front end against the real engine (GPU test)
+    out3 = os.path.join(LIB, "pc2_driver")
+    if force or _newer(out3, [src3, hdr, os.path.join(REPO, "include", "patchwork", "pointcloud2.hpp"), core]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"), src3, "-o", out3,
+                               "-L" + LIB, "-lpwpp_b200", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

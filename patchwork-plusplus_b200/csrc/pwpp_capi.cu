@@ -93,6 +93,12 @@ __global__ void k_repack_colmajor(const float* __restrict__ src, long long n, in
   if (i < n) dst[i] = make_float4(src[i], src[n + i], src[2 * n + i], cols == 4 ? src[3 * n + i] : 0.f);
 }
 
+// packed N x 3 rows on the device (the ROS node's conversion, reference ros/src/Utils.hpp:158-172) -> float4 {x, y, z, 0}
+__global__ void k_pad_xyz(const float* __restrict__ src, long long n, float4* __restrict__ dst) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+
 typedef void (*FitKernel)(const float4*, FrameTable, const StreamState*, Geometry, AlgoParams, int, const int*, WorkQueues, int*, BinFit*);
 struct FitLaunch {
   FitKernel fn = nullptr;
@@ -142,9 +148,11 @@ struct pwpp_ctx {
   DevBuf<BinFit> d_fits;          // [F][nbins]
   DevBuf<BinSeg> d_segs;          // [F][nbins+3]
   DevBuf<int4> d_wq_items[NUM_CLASSES];  // fit work queues
-  DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES]: counts, heads
+  DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES + 1]: counts, heads, k_order's head
+  DevBuf<unsigned char> d_labels; // reference-order output only: what became of every point of a fitted patch
+  int order_mode = 0;             // PWPP_ORDER_*
   FitLaunch fit[NUM_CLASSES];   // persistent fit kernel of every patch-size class (variant chosen in pwpp_create)
-  int max_sectors = 0;
+  int max_sectors = 0, order_grid = 0;
   DevBuf<int> d_out_idx;
   DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
   DevBuf<float> d_centers, d_normals;  // [F][nbins][3]
@@ -237,6 +245,7 @@ int prepare_call(pwpp_ctx* ctx, int nframes, cudaStream_t s) {
   CU_TRY(ctx->d_bin_off.reserve((size_t) nframes * (nbp + 1)));
   CU_TRY(ctx->d_sorted.reserve((size_t) total));
   CU_TRY(ctx->d_part.reserve((size_t) total));
+  if (ctx->order_mode) CU_TRY(ctx->d_labels.reserve((size_t) total));
   CU_TRY(ctx->d_fits.reserve((size_t) nframes * nb));
   CU_TRY(ctx->d_segs.reserve((size_t) nframes * nb_all));
   for (int c = 0; c < NUM_CLASSES; ++c) CU_TRY(ctx->d_wq_items[c].reserve((size_t) nframes * nb));
@@ -271,7 +280,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   BinSeg* segs = ctx->d_segs.p + (size_t) f0 * nb_all;
   float* centers = ctx->d_centers.p + (size_t) f0 * nb * 3;
   float* normals = ctx->d_normals.p + (size_t) f0 * nb * 3;
-  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, 2 * NUM_CLASSES * sizeof(int), s));
+  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, (2 * NUM_CLASSES + 1) * sizeof(int), s));
   int stage = 0;
 #define STAGE_MARK() do { if (prof) CU_TRY(cudaEventRecord(ctx->stage_ev[stage], s)); ++stage; } while (0)
   STAGE_MARK();
@@ -279,6 +288,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = ctx->d_wq_items[c].p;
   wq.count = ctx->d_wq_ctr.p;
   wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
+  wq.labels = ctx->order_mode ? ctx->d_labels.p : nullptr;
   if (ctx->sw_front) {
     // PWPP_FRONT: binning, scan and scatter as one persistent kernel pipelined through L2 (pwpp_front.cuh)
     const int total_chunks = ctx->chunk_off[f0 + nf] - ctx->chunk_off[f0];
@@ -355,6 +365,10 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     stage += 6;
   }
 #undef FIT_ARGS
+  if (ctx->order_mode) {   // reference emission order inside every fitted patch (pwpp_order.cuh)
+    k_order<<<ctx->order_grid, ORD_THREADS, ORD_CAP * sizeof(unsigned long long), s>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
+    ++ctx->launches;
+  }
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
@@ -575,7 +589,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   }
   CU_TRY_CTX(ctx->d_hist.reserve((size_t) num_streams * 2 * 4 * ctx->hcap));
   CU_TRY_CTX(ctx->d_counts.reserve((size_t) 3 * num_streams));
-  CU_TRY_CTX(ctx->d_wq_ctr.reserve(2 * NUM_CLASSES));
+  CU_TRY_CTX(ctx->d_wq_ctr.reserve(2 * NUM_CLASSES + 1));
   {
     cudaDeviceProp prop;
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
@@ -658,6 +672,12 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.threads, k.smem));
       k.grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
+    {
+      CU_TRY_CTX(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (ORD_CAP * sizeof(unsigned long long))));
+      int per_sm = 1;
+      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_order, ORD_THREADS, ORD_CAP * sizeof(unsigned long long)));
+      ctx->order_grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
     const size_t gle_smem = (size_t) 6 * max_sectors * sizeof(double) + (size_t) 2 * max_sectors * sizeof(int);
     if (gle_smem > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_gle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gle_smem));
   }
@@ -703,7 +723,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int q = 0; q < 5; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_cm.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
-  ctx->d_part.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release(); ctx->d_front_items.release(); ctx->d_front_ctr.release();
+  ctx->d_part.release(); ctx->d_labels.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release(); ctx->d_front_items.release(); ctx->d_front_ctr.release();
   for (int c = 0; c < NUM_CLASSES; ++c) ctx->d_wq_items[c].release();
   ctx->d_out_idx.release(); ctx->d_counts.release();
   ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();
@@ -881,6 +901,34 @@ int pwpp_estimate_device(pwpp_ctx* ctx, int nframes, const void* d_pts, const in
   return PWPP_OK;
 }
 
+int pwpp_estimate_device_xyz(pwpp_ctx* ctx, int nframes, const void* d_xyz, const int64_t* h_offsets, void* cuda_stream) {
+  if (!ctx || !h_offsets) return fail(PWPP_ERR_INVALID_ARG, "NULL argument");
+  if (nframes < 1 || nframes > ctx->num_streams) return fail(PWPP_ERR_INVALID_ARG, "nframes must be in [1, num_streams]");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  const long long total = h_offsets[nframes] - h_offsets[0];
+  if (total < 0 || (total > 0 && !d_xyz)) return fail(PWPP_ERR_INVALID_ARG, "bad offsets / d_xyz is NULL");
+  cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : ctx->stream;
+  if (ctx->last_stream && ctx->last_stream != s) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
+  if (!ctx->last_stream && s != ctx->stream) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx->d_in.reserve((size_t) std::max<long long>(total, 1)));
+  if (total > 0) {
+    k_pad_xyz<<<(unsigned) ((total + 255) / 256), 256, 0, s>>>((const float*) d_xyz + 3 * h_offsets[0], total, ctx->d_in.p);
+    ++ctx->launches;
+  }
+  std::vector<int64_t> offs(h_offsets, h_offsets + nframes + 1);
+  for (auto& o : offs) o -= h_offsets[0];
+  return pwpp_estimate_device(ctx, nframes, ctx->d_in.p, offs.data(), 0, s);
+}
+
+int pwpp_device_synchronize(pwpp_ctx* ctx) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  CU_TRY(cudaDeviceSynchronize());
+  return PWPP_OK;
+}
+
 int pwpp_synchronize(pwpp_ctx* ctx) {
   if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
   int rc = bind_device(ctx);
@@ -1035,6 +1083,14 @@ int pwpp_device_results(pwpp_ctx* ctx, const int32_t** d_indices, const int32_t*
   if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
   if (d_indices) *d_indices = ctx->d_out_idx.p;
   if (d_num_ground) *d_num_ground = ctx->d_counts.p;
+  return PWPP_OK;
+}
+
+int pwpp_set_output_order(pwpp_ctx* ctx, int order) {
+  if (!ctx) return fail(PWPP_ERR_INVALID_ARG, "ctx is NULL");
+  if (order != PWPP_ORDER_BIN && order != PWPP_ORDER_REFERENCE) return fail(PWPP_ERR_INVALID_ARG, "order must be PWPP_ORDER_BIN or PWPP_ORDER_REFERENCE");
+  if (order != ctx->order_mode) ++g_alloc_gen;   // captured graphs were recorded with the other launch sequence
+  ctx->order_mode = order;
   return PWPP_OK;
 }
 

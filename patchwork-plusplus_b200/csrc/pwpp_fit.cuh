@@ -48,7 +48,13 @@ struct WorkQueues {
   int4* items[NUM_CLASSES];
   int* count;                // [NUM_CLASSES]  number of items
   int* head;                 // [NUM_CLASSES]  next item to hand out (persistent kernels)
+  // Reference-order output (pwpp_set_output_order): when non-null, every fit kernel records for each point of a fitted patch,
+  // at its position in the bin-sorted array, what became of it: PW_LABEL_GROUND, PW_LABEL_REJECT (non-ground by the final
+  // distance test, S:529-541) or 1..num_iter = the R-VPF iteration that removed it (S:495-504). k_order sorts by it.
+  unsigned char* labels;
 };
+#define PW_LABEL_GROUND 255
+#define PW_LABEL_REJECT 0
 __device__ __forceinline__ int4 make_work_item(int frame, int bin, int n, long long start) {
   return make_int4((frame << 12) | bin, n, (int) (unsigned) (start & 0xffffffffll), (int) (start >> 32));
 }
@@ -319,7 +325,10 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_resident(const float4
         if (have_plane && pl.normal[2] < ap.uprightness_thr) {  // S:489: remove the vertical structure, iterate
 #pragma unroll
           for (int k = 0; k < K; ++k)
-            if (((amask >> k) & 1u) && fabs(point_plane_distance(pl, px[k], py[k], pz[k])) < ap.th_dist_v) amask &= ~(1u << k);  // S:499
+            if (((amask >> k) & 1u) && fabs(point_plane_distance(pl, px[k], py[k], pz[k])) < ap.th_dist_v) {   // S:499
+              amask &= ~(1u << k);
+              if (wq.labels) wq.labels[(P - sorted) + k * G + gl] = (unsigned char) (rvpf_it + 1);
+            }
           ++rvpf_it;
           if (rvpf_it >= ap.num_iter) state = ST_SEED;
         } else state = ST_SEED;  // S:506 break
@@ -358,6 +367,7 @@ __global__ void __launch_bounds__(FIT_THREADS, MINB) k_fit_resident(const float4
           const int idx = __float_as_int(P[j].w);
           if (isg) out[g_run + __popc(bg & lt)] = idx;
           else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+          if (wq.labels && (isg || ((amask >> k) & 1u))) wq.labels[(P - sorted) + j] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
         }
         g_run += __popc(bg);
         ng_run += __popc(bn);
@@ -795,7 +805,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
           for (int it = 0; it < nit; ++it) {
             if (!((amask >> it) & 1u)) continue;
             const int j = jbase + it * 32;
-            if (fabs(point_plane_distance(pl, sx[j], sy[j], sz[j])) < ap.th_dist_v) amask &= ~(1u << it);   // S:499
+            if (fabs(point_plane_distance(pl, sx[j], sy[j], sz[j])) < ap.th_dist_v) {   // S:499
+              amask &= ~(1u << it);
+              if (wq.labels) wq.labels[start + j] = (unsigned char) (rvpf_it + 1);
+            }
           }
           ++rvpf_it;
           if (rvpf_it >= ap.num_iter) state = ST_SEED;
@@ -842,6 +855,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
             if (v) {
               if (isg) out[g_run + __popc(bg & lt)] = idxv[u];
               else out[n_ground + ng_run + __popc(bn & lt)] = idxv[u];
+              if (wq.labels && (isg || ((amask >> it) & 1u))) wq.labels[start + jbase + it * 32] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
             }
             g_run += __popc(bg);
             ng_run += __popc(bn);
@@ -856,6 +870,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
           const int idx = __float_as_int(P[jbase + it * 32].w);
           if (isg) out[g_run + __popc(bg & lt)] = idx;
           else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+          if (wq.labels && (isg || ((amask >> it) & 1u))) wq.labels[start + jbase + it * 32] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
         }
         g_run += __popc(bg);
         ng_run += __popc(bn);
@@ -1400,7 +1415,9 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
           bool keep = j < n;
           const float4 p = P[j < n ? j : n - 1];
           if (any_removed) keep = keep && ((alive_w[it] >> lane) & 1u);
+          const bool was_alive = keep;
           keep = keep && !(fabs(point_plane_distance(pl, p.x, p.y, p.z)) < ap.th_dist_v);   // S:499
+          if (wq.labels && was_alive && !keep) wq.labels[start + j] = (unsigned char) (ap.num_iter - rvpf_left + 1);
           const unsigned bal = __ballot_sync(0xffffffffu, keep);
           if (lane == 0) alive_w[it] = bal;
         }
@@ -1485,6 +1502,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
             if (v) {
               if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idxv[u];
               else out[n_ground + ng_run + __popc(bn & lt)] = idxv[u];
+              if (wq.labels) { const bool isg = (bg >> lane) & 1u; if (isg || !any_removed || ((alive_w[it] >> lane) & 1u)) wq.labels[start + j] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT; }
             }
             g_run += __popc(bg);
             ng_run += __popc(bn);
@@ -1501,6 +1519,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
           const int idx = __float_as_int(P[j].w);
           if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idx;
           else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+          if (wq.labels) { const bool isg = (bg >> lane) & 1u; if (isg || !any_removed || ((alive_w[it] >> lane) & 1u)) wq.labels[start + j] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT; }
         }
         g_run += __popc(bg);
         ng_run += __popc(bn);

@@ -388,12 +388,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
           p = P[i];
-          const bool alive = (rv.n == 0) || is_alive(rv, ap.th_dist_v, p.x, p.y, p.z);
-          if (alive) {
+          int rmk = 0;   // the R-VPF iteration that removed the point (S:495-504), 0 = still alive
+          for (int k = 0; k < rv.n; ++k) if (rmk == 0 && fabs(point_plane_distance(rv.pl[k], p.x, p.y, p.z)) < ap.th_dist_v) rmk = k + 1;   // S:499
+          if (rmk == 0) {
             int fl = dist_filter(pf, thf, p.x, p.y, p.z);
             if (fl < 0) fl = (point_plane_distance(cls, p.x, p.y, p.z) < ap.th_dist) ? 1 : 0;
             is_g = fl != 0;
           }
+          if (wq.labels) wq.labels[start + i] = is_g ? PW_LABEL_GROUND : (unsigned char) rmk;   // (PW_LABEL_REJECT == 0)
         }
         const unsigned bg = __ballot_sync(0xffffffffu, valid && is_g);
         const unsigned bn = __ballot_sync(0xffffffffu, valid && !is_g);
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
         ng_run += tn;
       }
     } else {
-      for (int i = tid; i < n; i += NT) out[i] = __float_as_int(P[i].w);
+      for (int i = tid; i < n; i += NT) { out[i] = __float_as_int(P[i].w); if (wq.labels) wq.labels[start + i] = PW_LABEL_REJECT; }
     }
     if (tid == 0) {
       BinFit& r = fits[(size_t) f * g.nbins + bin];

@@ -509,7 +509,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
         rp.d = s_plane[9];
 #pragma unroll
         for (int k = 0; k < FP_SL; ++k)
-          if (((amask >> k) & 1u) && fabs(point_plane_distance(rp, px[k], py[k], pz[k])) < ap.th_dist_v) amask &= ~(1u << k);   // S:499
+          if (((amask >> k) & 1u) && fabs(point_plane_distance(rp, px[k], py[k], pz[k])) < ap.th_dist_v) {   // S:499
+            amask &= ~(1u << k);
+            if (wq.labels) wq.labels[start + jbase + k * NT] = (unsigned char) rvpf_it;   // (rvpf_it was incremented above: 1-based)
+          }
       }
       if (state == ST_DONE) n_ground = have_plane ? tot_n : 0;
     }
@@ -553,8 +556,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
 #pragma unroll
       for (int k = 0; k < FP_SL; ++k) {
         if (k < rpw && ((vmask >> k) & 1u)) {
-          if ((gmask >> k) & 1u) out[s_tile[0][k * NW + w] + __popc(bgk[k] & lt)] = idxv[k];
+          const bool isg = (gmask >> k) & 1u;
+          if (isg) out[s_tile[0][k * NW + w] + __popc(bgk[k] & lt)] = idxv[k];
           else out[n_ground + s_tile[1][k * NW + w] + __popc(bnk[k] & lt)] = idxv[k];
+          if (wq.labels && (isg || ((amask >> k) & 1u))) wq.labels[start + jbase + k * NT] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
         }
       }
       if (tid == 0) {

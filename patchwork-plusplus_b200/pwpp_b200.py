@@ -57,6 +57,7 @@ def load_library():
     lib.pwpp_stage_times_ms.argtypes = [vp, C.POINTER(C.c_float)]; lib.pwpp_stage_times_ms.restype = i32
     lib.pwpp_stage_name.argtypes = [i32]; lib.pwpp_stage_name.restype = C.c_char_p
     lib.pwpp_launch_count.argtypes = [vp]; lib.pwpp_launch_count.restype = i64
+    lib.pwpp_set_output_order.argtypes = [vp, i32]; lib.pwpp_set_output_order.restype = i32
     lib.pwpp_host_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]; lib.pwpp_host_results.restype = i32
     lib.pwpp_bind_host_to_device.argtypes = [i32]; lib.pwpp_bind_host_to_device.restype = i32
     _lib = lib
@@ -230,6 +231,12 @@ class Engine:
         a, b = C.c_void_p(), C.c_void_p()
         _check(self.lib.pwpp_device_results(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    ORDER_BIN, ORDER_REFERENCE = 0, 1
+
+    def set_output_order(self, order: int):
+        """ORDER_BIN (default): ascending point index inside a bin; ORDER_REFERENCE: the reference's z order (pwpp.h)."""
+        _check(self.lib.pwpp_set_output_order(self._h, order))
 
     NUM_STAGES = 11
 

@@ -24,6 +24,11 @@ int main(int argc, char** argv) {
   };
   patchwork::Params params;
   params.verbose = false;
+  if (argc > 2 && std::strcmp(argv[2], "ros") == 0) {   // reference ros/launch/patchworkpp.launch.py:50-64 + GroundSegmentationServer.cpp:47
+    params.sensor_height = 1.88; params.num_iter = 3; params.num_lpr = 20; params.num_min_pts = 0; params.th_seeds = 0.3; params.th_dist = 0.125;
+    params.th_seeds_v = 0.25; params.th_dist_v = 0.9; params.max_range = 80.0; params.min_range = 1.0; params.uprightness_thr = 0.101;
+    params.enable_RNR = false;
+  }
   for (const Layout& L : layouts) {
     std::vector<uint8_t> msg((size_t) n * L.step + 8, 0xAB);
     for (size_t i = 0; i < n; ++i) {
@@ -36,7 +41,9 @@ int main(int argc, char** argv) {
     v.data = msg.data(); v.num_points = (int64_t) n; v.point_step = L.step; v.off_x = L.ox; v.off_y = L.oy; v.off_z = L.oz; v.off_intensity = L.oi;
     const bool zc = patchwork::estimateGround(pw, v);
     const patchwork::PointCloud2Payload g = patchwork::makeCloudPayload(pw, true), ng = patchwork::makeCloudPayload(pw, false);
-    std::printf("%s %d %u %u %zu\n", L.name, zc ? 1 : 0, g.width, ng.width, g.data.size() + ng.data.size());
+    long long chk = 0;   // order-independent checksum of the ground index set
+    for (int v : pw.getGroundIndicesVec()) chk += (long long) v * (long long) (v % 97 + 1);
+    std::printf("%s %d %u %u %zu %lld\n", L.name, zc ? 1 : 0, g.width, ng.width, g.data.size() + ng.data.size(), chk);
   }
   return 0;
 }

@@ -227,7 +227,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 0;
+  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 0, order = 0;
   std::string last_launches;
 };
 
@@ -278,6 +278,7 @@ int simt_set_option(void* h, const char* name, int v) {
   else if (n == "m_half") t->m_half = v;
   else if (n == "x_nw") t->x_nw = v;
   else if (n == "group") t->group = v;
+  else if (n == "order") t->order = v;
   else return -1;
   return 0;
 }
@@ -317,7 +318,8 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   std::vector<BinSeg> segs((size_t) nframes * nb_all);
   std::vector<int4> items[NUM_CLASSES];
   for (auto& v : items) v.resize((size_t) nframes * nb + 1);
-  std::vector<int> ctr(2 * NUM_CLASSES, 0);
+  std::vector<int> ctr(2 * NUM_CLASSES + 1, 0);
+  std::vector<unsigned char> labels((size_t) total + 1, 0);
   std::vector<int> counts((size_t) 3 * nframes, 0);
   std::vector<float> centers((size_t) nframes * nb * 3), normals((size_t) nframes * nb * 3);
 
@@ -328,6 +330,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   for (int c = 0; c < NUM_CLASSES; ++c) wq.items[c] = items[c].data();
   wq.count = ctr.data();
   wq.head = ctr.data() + NUM_CLASSES;
+  wq.labels = t->order ? labels.data() : nullptr;
   if (t->front) {   // PWPP_FRONT: the three front-end kernels as one persistent, L2-pipelined kernel
     const int nitems = 2 * total_chunks + nframes, W = std::max(1, std::min(nframes, t->front_w));
     std::vector<FrontItem> fitems((size_t) nitems + 1, FrontItem{-1, -1});
@@ -427,6 +430,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     std::snprintf(buf, sizeof buf, "S=%d M=%d L1=%d L2=%d L3=%d X=%d", ctr[0], ctr[1], ctr[2], ctr[3], ctr[4], ctr[5]);
     t->last_launches = buf;
   }
+  if (t->order) simt::launch("k_order", pg, ORD_THREADS, ORD_CAP * sizeof(unsigned long long), [&] { k_order(sorted.data(), wq, ctr.data() + 2 * NUM_CLASSES, part.data()); });
   int* d_ng = counts.data();
   int* d_np = counts.data() + nframes;
   int* d_nd = counts.data() + 2 * nframes;

@@ -30,3 +30,8 @@ int pwpp_copy_centers(pwpp_ctx* c, int f, float* d) { (void) c; (void) f; memset
 int pwpp_copy_normals(pwpp_ctx* c, int f, float* d) { (void) c; (void) f; memset(d, 0, 24); return 0; }
 double pwpp_height(pwpp_ctx* c, int f) { (void) f; return c->h; }
 double pwpp_time_us(pwpp_ctx* c) { (void) c; return 1000.0; }
+int pwpp_set_output_order(pwpp_ctx* c, int order) { (void) c; (void) order; return 0; }
+int pwpp_device_synchronize(pwpp_ctx* c) { (void) c; return 0; }
+int pwpp_estimate_device(pwpp_ctx* c, int nf, const void* d, const int64_t* o, int hi, void* s) { (void) c; (void) nf; (void) d; (void) o; (void) hi; (void) s; return -1; }
+int pwpp_estimate_device_xyz(pwpp_ctx* c, int nf, const void* d, const int64_t* o, void* s) { (void) c; (void) nf; (void) d; (void) o; (void) s; return -1; }
+int pwpp_device_results(pwpp_ctx* c, const int32_t** a, const int32_t** b) { (void) c; if (a) *a = 0; if (b) *b = 0; return 0; }

@@ -77,7 +77,7 @@ def test_pointcloud2_adaptor_with_stub(tmp_path, kitti):
     rows = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.stdout.splitlines() if l.split() and l.split()[0] in names}
     ng = int((a[:, 2] < -1.5).sum())
     assert set(rows) == names
-    for name, (zero_copy, g, n, payload) in rows.items():
+    for name, (zero_copy, g, n, payload, _chk) in rows.items():
         assert (g, n) == (ng, len(a) - ng), name
         assert payload == 12 * len(a), name
         assert zero_copy == (0 if name in ("pcl_xyzi32", "velodyne22") else 1), name

@@ -1,5 +1,7 @@
 """Stream-level features next to the hot path: state checkpoint / migration and zero-copy device results.
 Runs after tests/test_gpu_parity.py (the parity gate) in the same `-m gpu` session."""
+import os
+
 import numpy as np
 import pytest
 
@@ -108,3 +110,71 @@ def test_narrow_ring_geometry_takes_the_exact_binning_kernel(kitti):
     if not (orc.bin_min_fit_n() < 3).any():
         assert np.array_equal(np.sort(orc.getGroundIndices()), np.sort(eng.ground_indices(0)))
         assert np.array_equal(np.sort(orc.getNongroundIndices()), np.sort(eng.nonground_indices(0)))
+
+
+def test_pointcloud2_front_end_drives_the_real_engine(kitti, tmp_path):
+    """include/patchwork/pointcloud2.hpp (the ROS 2 node's message handling, reference ros/src/GroundSegmentationServer.cpp:74-95,
+    ros/src/Utils.hpp:158-195) against the REAL engine: PointCloud2-shaped buffers with point_step 12 / 16 / 32 / 22 / 48, with
+    and without an intensity field, under the ROS launch-file parameters (ros/launch/patchworkpp.launch.py:50-64): every layout
+    gives the same ground set as the engine fed with the packed N x 3 points."""
+    import subprocess
+    import pwpp_b200
+    from param_sets import PARAM_SETS
+    exe = os.path.join(os.path.dirname(pwpp_b200.LIB_PATH), "pc2_driver")
+    assert os.path.exists(exe), "lib/pc2_driver was not built (patchwork-plusplus_b200/build.py)"
+    a = np.ascontiguousarray(kitti[2][:60000])
+    a.tofile(tmp_path / "scan.bin")
+    out = subprocess.run([exe, str(tmp_path / "scan.bin"), "ros"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    names = {"xyz12", "xyzi16", "pcl_xyzi32", "velodyne22", "ouster48_noint"}
+    rows = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.stdout.splitlines() if l.split() and l.split()[0] in names}
+    assert set(rows) == names
+    mk, _ = PARAM_SETS["ros"]
+    eng = pwpp_b200.Engine(mk(), device=0)
+    eng.estimate_host([np.ascontiguousarray(a[:, :3])])
+    g = eng.ground_indices(0).astype(np.int64)
+    chk = int((g * (g % 97 + 1)).sum())
+    for name, (zero_copy, ng, nn, payload, c) in rows.items():
+        assert (ng, nn) == (len(g), len(a) - len(g)), name     # RNR is off in the launch file: intensity changes nothing
+        assert c == chk, f"{name}: ground set differs from the engine's"
+        assert payload == 12 * len(a), name
+        assert zero_copy == (0 if name in ("pcl_xyzi32", "velodyne22") else 1), name
+
+
+def test_pybind_device_tensors(kitti):
+    """pypatchworkpp.estimateGround on CUDA tensors (__cuda_array_interface__ and DLPack, N x 4 and N x 3) and the device index
+    views: identical to the numpy path, no host copy of the cloud."""
+    import torch
+    import pypatchworkpp as m
+    a = kitti[1]
+    P = m.Parameters(); P.verbose = False
+    ref = m.patchworkpp(P); ref.estimateGround(a)
+    g_ref, n_ref = ref.getGroundIndices(), ref.getNongroundIndices()
+    t4 = torch.from_numpy(a).cuda()
+    pw = m.patchworkpp(P)
+    pw.estimateGround(t4)                                   # __cuda_array_interface__
+    assert np.array_equal(pw.getGroundIndices(), g_ref) and np.array_equal(pw.getNongroundIndices(), n_ref)
+    gd = torch.as_tensor(pw.getGroundIndicesDevice(), device="cuda")
+    nd = torch.as_tensor(pw.getNongroundIndicesDevice(), device="cuda")
+    assert gd.dtype == torch.int32 and np.array_equal(gd.cpu().numpy(), g_ref) and np.array_equal(nd.cpu().numpy(), n_ref)
+
+    class OnlyDLPack:   # an object that offers DLPack but no __cuda_array_interface__
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, stream=None): return self.t.__dlpack__()
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+    pw2 = m.patchworkpp(P)
+    pw2.estimateGround(OnlyDLPack(t4))
+    assert np.array_equal(pw2.getGroundIndices(), g_ref)
+    # N x 3 on the device (the ROS node's input) vs N x 3 on the host
+    P3 = m.Parameters(); P3.verbose = False; P3.enable_RNR = False
+    h3, d3 = m.patchworkpp(P3), m.patchworkpp(P3)
+    h3.estimateGround(np.ascontiguousarray(a[:, :3]))
+    d3.estimateGround(torch.from_numpy(np.ascontiguousarray(a[:, :3])).cuda())
+    assert np.array_equal(h3.getGroundIndices(), d3.getGroundIndices())
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        t = torch.from_numpy(a).cuda()
+        pw.estimateGround(t, stream=s.cuda_stream)          # enqueued on the producer's stream
+        gd2 = torch.as_tensor(pw.getGroundIndicesDevice(), device="cuda").clone()
+    s.synchronize()
+    assert np.array_equal(gd2.cpu().numpy(), g_ref)

@@ -1,0 +1,58 @@
+"""Reference emission order (pwpp_set_output_order(PWPP_ORDER_REFERENCE), csrc/pwpp_order.cuh): the index LISTS — not just the
+sets — equal those of the reference's own code with a stable per-bin sort (oracle/_ref/libpwref_stable.so: ties in z keep
+ascending point index; with std::sort their order is unspecified in the reference itself). Kernels on the SIMT twin here,
+on the GPU in tests/test_gpu_reference.py."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import SimtTwin
+from param_sets import PARAM_SETS
+
+pytestmark = pytest.mark.skipif(not O.have_reference_build(), reason="needs oracle/_ref/libpwref_stable.so")
+
+
+def _lists_equal(ref, tw, what):
+    for name in ("getGroundIndices", "getNongroundIndices"):
+        a, b = getattr(ref, name)(), getattr(tw, name)()
+        assert a.shape == b.shape and np.array_equal(a, b), f"{what}: {name} differs (first at {np.nonzero(a[:len(b)] != b[:len(a)])[0][:3]})"
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_fixture_lists_in_reference_order(kitti, group):
+    for f in (0, 3):
+        ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1, group=group)
+        ref.estimate(kitti[f]); tw.estimate(kitti[f])
+        _lists_equal(ref, tw, f"fixture {f}")
+
+
+def test_rvpf_removals_come_first_in_iteration_order():
+    """A wall inside a zone-0 bin: R-VPF removes points in several iterations; the reference appends them to the non-ground
+    list iteration by iteration, each in ascending z, before the final rejects (patchworkpp.cpp:495-504, :529-541)."""
+    rng = np.random.default_rng(11)
+    wall = np.r_[np.c_[4 + rng.random(6000) * 0.05, rng.random(6000) * 0.6, -1.7 + rng.random(6000) * 2.0, rng.random(6000)],
+                 np.c_[3 + rng.random(6000) * 4, rng.random(6000) * 0.6, -1.7 + rng.normal(0, 0.02, 6000), rng.random(6000)]].astype(np.float32)
+    for group in (0, 1):
+        ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1, group=group)
+        ref.estimate(wall); tw.estimate(wall)
+        _lists_equal(ref, tw, f"wall/group={group}")
+
+
+def test_other_parameter_set_and_synthetic_and_ties():
+    import synth
+    mk, cols = PARAM_SETS["no_rvpf_tgr"]
+    a = np.ascontiguousarray(conftest_kitti(1)[:, :cols])
+    ref, tw = O.Reference(mk(), stable_sort=True), SimtTwin(mk(), order=1)
+    ref.estimate(a); tw.estimate(a)
+    _lists_equal(ref, tw, "no_rvpf_tgr")
+    b = synth.make_frame(20260922, 1).numpy()
+    b[:, 2] = np.round(b[:, 2] / 0.01) * 0.01   # centimetre-quantised z: thousands of exact ties per bin
+    ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1)
+    ref.estimate(b); tw.estimate(b)
+    if np.array_equal(np.sort(ref.getGroundIndices()), np.sort(tw.getGroundIndices())):   # (lattice data can flip labels between fp32 and double)
+        _lists_equal(ref, tw, "ties")
+
+
+def conftest_kitti(f):
+    import conftest
+    return conftest.load_kitti(f)
