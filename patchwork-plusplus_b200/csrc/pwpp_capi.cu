@@ -16,7 +16,6 @@
 
 #include "pwpp.h"
 #include "pwpp_kernels.cuh"
-#include "pwpp_front.cuh"
 #include "pwpp_tuning.h"
 #include "pwpp_host.hpp"
 
@@ -116,10 +115,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_hist_pipe = 2, sw_scatter_pipe = 0, sw_emit_split = 1, sw_front = 0, sw_l2_wide = 0, sw_m_half = 0, sw_group = 1;
-  int front_grid = 0;
-  DevBuf<FrontItem> d_front_items;
-  DevBuf<int> d_front_ctr;
+  int sw_emit_split = 1, sw_front = 1, sw_patch = 0;
   bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -290,56 +286,40 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
   wq.labels = ctx->order_mode ? ctx->d_labels.p : nullptr;
   if (ctx->sw_front) {
-    // PWPP_FRONT: binning, scan and scatter as one persistent kernel pipelined through L2 (pwpp_front.cuh)
-    const int total_chunks = ctx->chunk_off[f0 + nf] - ctx->chunk_off[f0];
-    const int nitems = 2 * total_chunks + nf;
-    const long long pts_in_range = ctx->pt_off[f0 + nf] - ctx->pt_off[f0];
-    const long long per_frame = std::max(1LL, pts_in_range / nf) * 16;
-    static const long long window_mb = env_int("PWPP_FRONT_WINDOW_MB", 32, 1, 96);   // how far (MB of points) the scatter trails the binning pass: must stay L2-resident
-    const int W = (int) std::max(1LL, std::min((long long) nf, (window_mb << 20) / per_frame));
-    CU_TRY(ctx->d_front_items.reserve((size_t) nitems + 1));
-    CU_TRY(ctx->d_front_ctr.reserve((size_t) 1 + 2 * nf));
-    CU_TRY(cudaMemsetAsync(ctx->d_front_ctr.p, 0, ((size_t) 1 + 2 * nf) * sizeof(int), s));
-    k_front_plan<<<(nf + W + 127) / 128, 128, 0, s>>>(ft.chunk_off, nf, W, ctx->d_front_items.p);
-    FrontArgs fa{d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->fast_bin ? 1 : 0, ctx->d_bin_ids.p, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits,
-                 ctx->d_sorted.p, ctx->d_front_items.p, nitems, ctx->sw_l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, ctx->sw_m_half ? CLS_M_HALF_MAX : CLS_M_MAX, ctx->d_front_ctr.p, nf};
-    const size_t sm_f = front_smem_bytes(nbp);
-    k_front<<<ctx->front_grid, FRONT_THREADS, sm_f, s>>>(fa);
-    ctx->launches += 2;
+    // one thread-block cluster per frame: binning, scan and stable scatter in one kernel (pwpp_front.cuh)
+    if (nframes > 0) {
+      const size_t sm_f = front_cluster_smem_bytes(nbp);
+      dim3 grid(FC_CS, nframes);
+#define FC_ARGS d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->d_bin_ids.p, bin_off, wq, fits, ctx->d_sorted.p
+      if (ctx->fast_bin) k_front_cluster<true, CLS_L2_MAX><<<grid, FC_THREADS, sm_f, s>>>(FC_ARGS);
+      else k_front_cluster<false, CLS_L2_MAX><<<grid, FC_THREADS, sm_f, s>>>(FC_ARGS);
+#undef FC_ARGS
+      ++ctx->launches;
+    }
     STAGE_MARK(); STAGE_MARK(); STAGE_MARK();
   } else {
-  if (max_chunks > 0) {
-    dim3 grid(max_chunks, nframes);
-    const int hist_pipe = ctx->sw_hist_pipe;
+    // the three stand-alone kernels (PWPP_FRONT=0)
+    if (max_chunks > 0) {
+      dim3 grid(max_chunks, nframes);
+      const size_t sm_h = nbp * sizeof(unsigned int);
 #define HIST_ARGS d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, ctx->d_bin_ids.p, ctx->d_chist.p
-    const size_t sm_h = nbp * sizeof(unsigned int);
-    if (!ctx->fast_bin) k_bin_hist<false, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
-    else if (hist_pipe == 0) k_bin_hist<true, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
-    else k_bin_hist<true, 2><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
+      if (!ctx->fast_bin) k_bin_hist<false, 0><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
+      else k_bin_hist<true, 2><<<grid, CHUNK_THREADS, sm_h, s>>>(HIST_ARGS);
 #undef HIST_ARGS
+      ++ctx->launches;
+    }
+    STAGE_MARK();
+    k_bin_scan<CLS_L2_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
     ++ctx->launches;
+    STAGE_MARK();
+    if (max_chunks > 0) {
+      dim3 grid(max_chunks, nframes);
+      const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
+      k_scatter<false, 4><<<grid, CHUNK_THREADS, sm_sc, s>>>(d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p);
+      ++ctx->launches;
+    }
+    STAGE_MARK();
   }
-  STAGE_MARK();
-#define SCAN_ARGS ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits
-  if (ctx->sw_m_half && ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
-  else if (ctx->sw_m_half) k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(SCAN_ARGS);
-  else
-#undef SCAN_ARGS
-  if (ctx->sw_l2_wide) k_bin_scan<CLS_L2_WIDE_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
-  else k_bin_scan<CLS_L2_MAX><<<nframes, 512, (nbp + 1) * sizeof(int), s>>>(ft, nbp, nb, ctx->ap.num_min_pts, ctx->d_chist.p, ctx->d_cbase.p, bin_off, wq, fits);
-  ++ctx->launches;
-  STAGE_MARK();
-  if (max_chunks > 0) {
-    dim3 grid(max_chunks, nframes);
-    const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
-#define SC_ARGS d_pts, ft, nbp, ctx->d_bin_ids.p, ctx->d_cbase.p, ctx->d_sorted.p
-    if (ctx->sw_scatter_pipe) k_scatter<true, 3><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS);   // PWPP_SCATTER_V=1
-    else k_scatter<false, 4><<<grid, CHUNK_THREADS, sm_sc, s>>>(SC_ARGS);
-#undef SC_ARGS
-    ++ctx->launches;
-  }
-  STAGE_MARK();
-  }   // !sw_front
   // persistent fit kernels, one per patch-size class (queues were filled by k_bin_scan). The classes are independent:
   // unless per-stage timing is requested they run on side streams so that the tail of one class (few long patches
   // left) overlaps the start of the next.
@@ -354,7 +334,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
     // longest classes first
     {
-    launch_fit(4, s);
+    launch_fit(4, s);   // longest patches first
     launch_fit(3, ctx->side[0]);
     launch_fit(2, ctx->side[1]);
     launch_fit(1, ctx->side[2]);
@@ -379,8 +359,12 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   }
   STAGE_MARK();
   if (max_chunks > 0) {
-    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, ctx->sw_emit_split);
-    if (ctx->sw_emit_split > 1) k_emit<true><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    // a bin is copied by `split` warps: 1 for KITTI-sized frames (bins of a few thousand points), 16 for dense sensors whose
+    // 20k..40k-point bins would otherwise be left to one warp each (r02: dense k_emit 1.15 -> 0.14 ms; KITTI 0.33 -> 0.94 ms at 16)
+    const long long mean_pts = (ctx->pt_off[f0 + nf] - ctx->pt_off[f0]) / std::max(nf, 1);
+    const int split = ctx->sw_emit_split > 0 ? ctx->sw_emit_split : (mean_pts > 400000 ? 16 : 1);
+    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, split);
+    if (split > 1) k_emit<true><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     else k_emit<false><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
@@ -544,14 +528,10 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->device = device;
   ctx->num_streams = num_streams;
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
-  ctx->sw_hist_pipe = env_int("PWPP_HIST_PIPE", PWPP_HIST_PIPE_DEFAULT, 0, 2);
-  ctx->sw_scatter_pipe = env_int("PWPP_SCATTER_V", PWPP_SCATTER_V_DEFAULT, 0, 1);
-  ctx->sw_serial_fit = env_int("PWPP_SERIAL_FIT", PWPP_SERIAL_FIT_DEFAULT, 0, 1) != 0;
-  ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", PWPP_EMIT_SPLIT_DEFAULT, 1, 32);
-  ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);
-  ctx->sw_l2_wide = env_int("PWPP_L2_WIDE", PWPP_L2_WIDE_DEFAULT, 0, 1);
-  ctx->sw_m_half = env_int("PWPP_M_HALF", PWPP_M_HALF_DEFAULT, 0, 1);
-  ctx->sw_group = env_int("PWPP_FIT_GROUP", PWPP_FIT_GROUP_DEFAULT, 0, 1);
+  ctx->sw_serial_fit = env_int("PWPP_SERIAL_FIT", 0, 0, 1) != 0;       // diagnostic: the fit kernels one after another on the call's stream
+  ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", 0, 0, 32);             // 0 = chosen from the frame size
+  ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);        // 1: cluster-per-frame front end, 0: k_bin_hist + k_bin_scan + k_scatter
+  ctx->sw_patch = env_int("PWPP_FIT_PATCH", PWPP_FIT_PATCH_DEFAULT, 0, 1);   // 1: patches above 512 points on k_fit_patch
   ctx->sw_graph = env_int("PWPP_GRAPH", 1, 0, 1);
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
@@ -593,80 +573,27 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   {
     cudaDeviceProp prop;
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
-    // Fit kernel of every class. The *_MINB switches pick the launch-bounds variant (CTAs per SM the register
-    // allocation is sized for): these kernels are latency-bound, so more resident warps can pay for a few spills.
-    const int s_minb = env_int("PWPP_S_MINB", PWPP_S_MINB_DEFAULT, 2, 4), m_minb = env_int("PWPP_M_MINB", PWPP_M_MINB_DEFAULT, 2, 3);
-    const int l1_minb = env_int("PWPP_L1_MINB", PWPP_L1_MINB_DEFAULT, 2, 4), l2_minb = env_int("PWPP_L2_MINB", PWPP_L2_MINB_DEFAULT, 3, 4);   // measured: 4 CTAs/SM on the 4096 class: 1.31 -> 1.23 ms
+    // Fit kernel of every patch-size class (launch shapes from the r01 / r02 measurements, profiles/):
+    //   S  <= 64      k_fit_resident: 8 lanes x 8 register slots per patch
+    //   M  <= 512     k_fit_warp, patch staged in shared memory
+    //   L1 <= 2048    k_fit_warp streaming from L2            | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
+    //   L2 <= 4096    k_fit_cta, plane in shared memory, 3/SM |                   4 / 8 / 16 warps
+    //   L3 <= 8192    k_fit_cta, 2 CTAs/SM                    |
+    //   X  >  8192    k_fit_big (dense sensors)
     const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
-    ctx->fit[0] = {s_minb == 4 ? k_fit_resident<8, 8, 0, 4> : s_minb == 3 ? k_fit_resident<8, 8, 0, 3> : k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
-    ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3> : k_fit_warp<true, 1, 1, 2, 2>, 0, FITW_WARPS * 32, sm_m};
-    ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3> : k_fit_warp<false, 2, 2, FITW_U, 2>, 0, FITW_WARPS * 32, 0};
-    ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8> : k_fit_cta<4096, 3, 3, 8>, 0, FIT_THREADS, sm_l2};
-    if (env_int("PWPP_L2_NW", PWPP_L2_NW_DEFAULT, 8, 16) == 16) ctx->fit[3] = {k_fit_cta<4096, 3, 2, 16>, 0, 512, sm_l2};
-    ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8>, 0, FIT_THREADS, sm_l3};
-    if (env_int("PWPP_L3_NW", PWPP_L3_NW_DEFAULT, 8, 16) == 16) ctx->fit[4] = {k_fit_cta<8192, 4, 2, 16>, 0, 512, sm_l3};
-    ctx->fit[5] = {k_fit_stream, 0, 128, 0};
-    const int part_ilp = env_int("PWPP_PART_ILP", PWPP_PART_ILP_DEFAULT, 0, 1);   // batched index loads in the final partition (default shapes only)
-    // class X (> 8192 points, dense sensors): one CTA per patch streaming from L2 (pwpp_fit_big.cuh); PWPP_X_KERNEL=0 selects
-    // the one-warp-per-patch fallback, PWPP_X_NW / PWPP_X_MINB the CTA shape (A/B switches)
-    // PWPP_FUSE_SEED is a bit mask: 1 = the CTA kernels (classes L2, L3, X), 2 = the warp kernels (classes M, L1).
-    // r01 measurement (profiles/r01_tune.jsonl): fused CTA kernels gain 5-10 %, fused warp kernels lose 3-10 % (their
-    // code grows by a quarter and they already stall on instruction fetch), hence the default 1.
-    const int fuse_mask = env_int("PWPP_FUSE_SEED", PWPP_FUSE_SEED_DEFAULT, 0, 3);
-    const int fuse_seed = fuse_mask & 1, fuse_warp = fuse_mask & 2;
-    const int solve_call = env_int("PWPP_SOLVE_CALL", PWPP_SOLVE_CALL_DEFAULT, 0, 1);   // 1: warp kernels call one out-of-line plane solver
-    if (env_int("PWPP_X_KERNEL", PWPP_X_KERNEL_DEFAULT, 0, 1)) {
-      const int x_nw = env_int("PWPP_X_NW", PWPP_X_NW_DEFAULT, 8, 32), x_minb = env_int("PWPP_X_MINB", PWPP_X_MINB_DEFAULT, 1, 2);
-      if (x_nw >= 32) ctx->fit[5] = {fuse_seed ? k_fit_big<32, 1, true> : k_fit_big<32, 1, false>, 0, 1024, 0};
-      else if (x_nw >= 16 && x_minb == 1 && env_int("PWPP_X_FIXPOINT", PWPP_X_FIXPOINT_DEFAULT, 0, 1))   // exact fixpoint exit of the R-GPF passes
-        ctx->fit[5] = {fuse_seed ? k_fit_big<16, 1, true, false, true> : k_fit_big<16, 1, false, false, true>, 0, 512, 0};
-      else if (x_nw >= 16 && x_minb == 1) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 1, true> : k_fit_big<16, 1, false>, 0, 512, 0};
-      else if (x_nw >= 16) ctx->fit[5] = {fuse_seed ? k_fit_big<16, 2, true> : k_fit_big<16, 2, false>, 0, 512, 0};
-      else ctx->fit[5] = {fuse_seed ? k_fit_big<8, 4, true> : k_fit_big<8, 4, false>, 0, 256, 0};
-    }
-    // PWPP_FUSE_SEED: zone-0 patches fit the R-VPF plane and the R-GPF seed plane from one selection + one pass (pwpp_fit.cuh)
-    if (fuse_warp) {
-      ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3, true> : k_fit_warp<true, 1, 1, 2, 2, true>, 0, FITW_WARPS * 32, sm_m};
-      ctx->fit[2] = {l1_minb == 4 ? k_fit_warp<false, 2, 2, FITW_U, 4, true> : l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3, true> : k_fit_warp<false, 2, 2, FITW_U, 2, true>, 0, FITW_WARPS * 32, 0};
-    } else if (solve_call) {
-      ctx->fit[1] = {m_minb == 3 ? k_fit_warp<true, 1, 1, 2, 3, false, true> : k_fit_warp<true, 1, 1, 2, 2, false, true>, 0, FITW_WARPS * 32, sm_m};
-      ctx->fit[2] = {l1_minb == 3 ? k_fit_warp<false, 2, 2, FITW_U, 3, false, true> : k_fit_warp<false, 2, 2, FITW_U, 2, false, true>, 0, FITW_WARPS * 32, 0};
-    }
-    if (fuse_seed) {
-      ctx->fit[3] = {l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true> : k_fit_cta<4096, 3, 3, 8, true>, 0, FIT_THREADS, sm_l2};
-      ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
-    }
-    if (ctx->sw_l2_wide && fuse_seed && ctx->fit[3].threads == FIT_THREADS) {   // PWPP_L2_WIDE: class L2 = 2049..5888 points at 3 CTAs/SM
-      ctx->fit[3] = {k_fit_cta<CLS_L2_WIDE_MAX, 3, 3, 8, true>, 0, FIT_THREADS, (size_t) 3 * CLS_L2_WIDE_MAX * sizeof(float)};
-    } else ctx->sw_l2_wide = 0;   // (only with the fused 8-warp CTA kernel)
-    if (part_ilp) {
-      if (!fuse_warp && !solve_call && m_minb == 2) ctx->fit[1].fn = k_fit_warp<true, 1, 1, 2, 2, false, false, true>;
-      if (!fuse_warp && !solve_call && l1_minb == 2) ctx->fit[2].fn = k_fit_warp<false, 2, 2, FITW_U, 2, false, false, true>;
-      if (fuse_seed && l2_minb == 3 && ctx->fit[3].threads == FIT_THREADS && !ctx->sw_l2_wide) ctx->fit[3].fn = k_fit_cta<4096, 3, 3, 8, true, true>;
-      if (fuse_seed && ctx->fit[4].threads == FIT_THREADS) ctx->fit[4].fn = k_fit_cta<8192, 4, 2, 8, true, true>;
-    }
-    // PWPP_M_RESIDENT: class M (65..512 points) on the register-resident kernel (one warp x 16 points per lane; 3.4k instructions
-    // against the staged warp kernel's 7.9k, which stalls 27 % on instruction fetch; no incremental moments, no fp32 filter).
-    // PWPP_L1_CTA: class L1 (513..2048 points) on the fused CTA kernel with 24 KB of shared memory per patch (many zone-0
-    // patches are in this class; the warp kernel is not fused and waits on L2 loads for 30 % of its stall samples).
-    if (env_int("PWPP_M_RESIDENT", PWPP_M_RESIDENT_DEFAULT, 0, 1)) ctx->fit[1] = {k_fit_resident<32, 16, 1, 2>, 0, FIT_THREADS, 0};
-    // PWPP_M_HALF: class M = 65..256 points on k_fit_resident<16,16> (two patches per warp); 257..512-point patches go to class L1,
-    // whose kernels take any size up to 2048
-    if (ctx->sw_m_half) ctx->fit[1] = {k_fit_resident<16, 16, 1, 2>, 0, FIT_THREADS, 0};
-    if (env_int("PWPP_L1_CTA", PWPP_L1_CTA_DEFAULT, 0, 1)) ctx->fit[2] = {k_fit_cta<2048, 2, 3, 8, true>, 0, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float)};
-    // PWPP_L2_PLS: class L2 with the current plane in shared memory instead of 20 registers per thread (fewer spills at 3 and at
-    // 4 CTAs/SM); only for the plain fused 4096-point shape
-    if (env_int("PWPP_L2_PLS", PWPP_L2_PLS_DEFAULT, 0, 1) && fuse_seed && !ctx->sw_l2_wide && !part_ilp && ctx->fit[3].threads == FIT_THREADS)
-      ctx->fit[3].fn = l2_minb == 4 ? k_fit_cta<4096, 3, 4, 8, true, false, true> : k_fit_cta<4096, 3, 3, 8, true, false, true>;
-    if (ctx->sw_group && !ctx->sw_front && !ctx->sw_l2_wide && !ctx->sw_m_half) {
-      // patches above 512 points: one patch per CTA held in registers (pwpp_fit_patch.cuh); classes S and M keep their kernels
+    ctx->fit[0] = {k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
+    ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 2>, 0, FITW_WARPS * 32, sm_m};
+    ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 2>, 0, FITW_WARPS * 32, 0};
+    ctx->fit[3] = {k_fit_cta<4096, 3, 3, 8, true, true>, 0, FIT_THREADS, sm_l2};
+    ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
+    ctx->fit[5] = {k_fit_big<16, 1, true>, 0, 512, 0};
+    if (ctx->sw_patch) {
       ctx->fit[2] = {k_fit_patch<4, 4, 2>, 0, 4 * 32, (size_t) 4 * FP_STG * sizeof(float4)};
       ctx->fit[3] = {k_fit_patch<8, 2, 3>, 0, 8 * 32, (size_t) 8 * FP_STG * sizeof(float4)};
       ctx->fit[4] = {k_fit_patch<16, 1, 4>, 0, 16 * 32, (size_t) 16 * FP_STG * sizeof(float4)};
-    } else ctx->sw_group = 0;
+    }
     for (int c = 0; c < NUM_CLASSES; ++c) {
       FitLaunch& k = ctx->fit[c];
-      if (!k.fn) continue;
       if (k.smem > 0) CU_TRY_CTX(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k.smem));
       int per_sm = 1;
       CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.threads, k.smem));
@@ -683,18 +610,12 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   }
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
+    if (scat > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+    const size_t sm_f = front_cluster_smem_bytes(ctx->nbp);
+    if (sm_f > 220 * 1024) ctx->sw_front = 0;   // (thousands of bins: the per-warp count tables no longer fit next to the tiles)
     if (ctx->sw_front) {
-      const size_t sm_f = front_smem_bytes(ctx->nbp);
-      if (sm_f > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
-      cudaDeviceProp prop;
-      CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
-      int per_sm = 1;
-      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, sm_f));
-      ctx->front_grid = std::max(1, per_sm) * prop.multiProcessorCount;
-    }
-    if (scat > 48 * 1024) {
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
-      CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<true, CLS_L2_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<false, CLS_L2_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
     }
   }
   *out = ctx;
@@ -723,7 +644,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int q = 0; q < 5; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_cm.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
-  ctx->d_part.release(); ctx->d_labels.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release(); ctx->d_front_items.release(); ctx->d_front_ctr.release();
+  ctx->d_part.release(); ctx->d_labels.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release();
   for (int c = 0; c < NUM_CLASSES; ++c) ctx->d_wq_items[c].release();
   ctx->d_out_idx.release(); ctx->d_counts.release();
   ctx->d_centers.release(); ctx->d_normals.release(); ctx->d_xyz.release();

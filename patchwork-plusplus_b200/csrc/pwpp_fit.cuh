@@ -31,13 +31,6 @@ namespace pwpp {
 
 constexpr int FIT_THREADS = 256;
 constexpr int CLS_S_MAX = 64, CLS_M_MAX = 512, CLS_L1_MAX = 2048, CLS_L2_MAX = 4096, CLS_L3_MAX = 8192;
-// PWPP_L2_WIDE: the L2 class reaches up to this many points — the largest patch whose SoA coordinates (12 B/point) still leave
-// room for 3 CTAs per SM next to the kernel's static shared memory. r01: an L3 patch (2 CTAs/SM at 96 KB) costs 3x an L2 patch
-// for 1.8x the points, and most L3 patches are below 6k points.
-constexpr int CLS_L2_WIDE_MAX = 5888;
-// PWPP_M_HALF: class M ends here and is served by k_fit_resident<16,16> — two patches per warp, i.e. half the per-round
-// instruction stream (selection, reductions, solve) per patch; patches of 257..512 points join class L1.
-constexpr int CLS_M_HALF_MAX = 256;
 constexpr int NUM_CLASSES = 6;  // S, M, L1, L2, L3, X
 
 // device-side work queues, filled by k_bin_scan. An item describes one patch completely, so that a fit kernel needs
@@ -150,19 +143,6 @@ struct GroupOps<32> {
   }
 };
 enum FitState { ST_RVPF = 0, ST_SEED = 1, ST_GPF = 2, ST_FINAL = 3, ST_DONE = 4 };
-
-// The plane solve (estimate_plane, S:47-75, from moment sums) is ~1.5k SASS instructions. Inlined at every call site it
-// makes the warp kernels 8-10k instructions (126-160 KB) and k_fit_big 20k: the r01 ncu capture shows 27 % of the class-M
-// kernel's stall samples as "no instruction" (instruction-cache misses). NL = true calls ONE out-of-line copy instead.
-__device__ __noinline__ void plane_from_moments_call(const Moments& m, const double* c, Plane& pl) {
-  const double cc[3] = {c[0], c[1], c[2]};
-  plane_from_moments(m, cc, pl);
-}
-template <bool NL>
-__device__ __forceinline__ void solve_plane(const Moments& m, const double* c, Plane& pl) {
-  if (NL) plane_from_moments_call(m, c, pl);
-  else plane_from_moments(m, c, pl);
-}
 
 // The register-resident fit kernel (classes S and M). G lanes cooperate on one patch, K points per lane; a warp
 // holds 32/G patches and is completely independent of the other warps of its CTA (no block barriers): it pulls its
@@ -407,7 +387,7 @@ __device__ __forceinline__ int dist_filter(const PlaneF& pf, float th, float x, 
 // PLS (PWPP_L2_PLS): the current plane lives in shared memory (s_plane) instead of 20 registers per thread — warp 0 rewrites it
 // in place between the two barriers of a round, when no other warp reads it — so that the fused kernel fits the 64-register
 // budget of 4 CTAs per SM with far fewer spills.
-template <int CAP, int CLS, int MINB, int NW, bool FUSE = false, bool PILP = false, bool PLS = false>
+template <int CAP, int CLS, int MINB, int NW, bool FUSE = false, bool PLS = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                                 Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                                 int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -835,33 +815,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       int g_run = 0, ng_run = 0;
       for (int q = 0; q < w; ++q) { g_run += s_cnt[q][0]; ng_run += s_cnt[q][1]; }
       const unsigned lt = lanemask_lt();
-      if (PILP) {
-        // PWPP_PART_ILP: the point indices of four slots are requested before the first one is stored (the r01 capture
-        // shows 7-9 % of this kernel's stall samples on the index load that feeds each store)
-        for (int it0 = 0; it0 < nit; it0 += 4) {
-          int idxv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = it0 + u;
-            idxv[u] = (it < nit && ((vmask >> it) & 1u)) ? __float_as_int(P[jbase + it * 32].w) : 0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = it0 + u;
-            if (it >= nit) break;   // uniform
-            const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
-            const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
-            const unsigned bn = __ballot_sync(0xffffffffu, v && !isg);
-            if (v) {
-              if (isg) out[g_run + __popc(bg & lt)] = idxv[u];
-              else out[n_ground + ng_run + __popc(bn & lt)] = idxv[u];
-              if (wq.labels && (isg || ((amask >> it) & 1u))) wq.labels[start + jbase + it * 32] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
-            }
-            g_run += __popc(bg);
-            ng_run += __popc(bn);
-          }
-        }
-      } else
       for (int it = 0; it < nit; ++it) {
         const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
         const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
@@ -948,8 +901,6 @@ struct LprSelector {
   }
 };
 
-// extract_initial_seeds (S:77-149) over the currently alive points of the bin: returns lpr_height.
-// alive(p) = not removed by an earlier R-VPF iteration.
 struct RvpfPlanes {
   Plane pl[MAX_RVPF];
   int n;
@@ -960,70 +911,6 @@ __device__ __forceinline__ bool is_alive(const RvpfPlanes& rv, double th_dist_v,
   for (int k = 0; k < rv.n; ++k) alive = alive && !(fabs(point_plane_distance(rv.pl[k], x, y, z)) < th_dist_v);  // S:499
   return alive;
 }
-
-__device__ double select_lpr(const float4* __restrict__ P, int n, bool zone0, double margin_z, int num_lpr, const RvpfPlanes& rv, double th_dist_v,
-                             float* sel_buf) {
-  LprSelector sel;
-  sel.init(sel_buf, num_lpr);
-  const int lane = lane_id();
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    bool valid = false;
-    float z = 0.f;
-    if (i < n) {
-      const float4 p = P[i];
-      z = p.z;
-      valid = (rv.n == 0) || is_alive(rv, th_dist_v, p.x, p.y, p.z);
-      if (zone0 && ((double) z < margin_z)) valid = false;  // S:88-96: the sorted prefix below the margin is skipped
-    }
-    sel.push(valid, z);
-  }
-  sel.prune();
-  // S:99-103: double sum of the (<= num_lpr) lowest z in ascending order
-  double lpr = 0.0;
-  if (lane == 0) {
-    double sum = 0.0;
-    const int cnt = sel.m;
-    for (int i = 0; i < cnt; ++i) sum += (double) sel_buf[i];
-    lpr = cnt != 0 ? sum / cnt : 0.0;
-  }
-  __syncwarp();
-  return __shfl_sync(0xffffffffu, lpr, 0);
-}
-
-// Moment sums over {alive && pred}, pred = (z < z_thr) for seeds or (dist(plane) < th) for R-GPF.
-// MODE 0: seeds (z < zthr); MODE 1: signed distance to `pl` below th_dist.
-template <int MODE>
-__device__ __forceinline__ Moments accumulate(const float4* __restrict__ P, int n, const RvpfPlanes& rv, double th_dist_v, double zthr, const Plane& pl,
-                                              double th_dist, const double c[3]) {
-  Moments m;
-  m.n = 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) m.s1[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) m.s2[k] = 0.0;
-  const int lane = lane_id();
-  for (int i = lane; i < n; i += 32) {
-    const float4 p = P[i];
-    bool in = (rv.n == 0) || is_alive(rv, th_dist_v, p.x, p.y, p.z);
-    if (MODE == 0) in = in && ((double) p.z < zthr);                        // S:108 / S:145
-    else in = in && (point_plane_distance(pl, p.x, p.y, p.z) < th_dist);     // S:525 / S:529
-    if (in) {
-      const double dx = (double) p.x - c[0], dy = (double) p.y - c[1], dz = (double) p.z - c[2];
-      m.s1[0] += dx; m.s1[1] += dy; m.s1[2] += dz;
-      m.s2[0] += dx * dx; m.s2[1] += dx * dy; m.s2[2] += dx * dz;
-      m.s2[3] += dy * dy; m.s2[4] += dy * dz; m.s2[5] += dz * dz;
-      m.n += 1;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) m.s1[k] = warp_sum(m.s1[k]);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) m.s2[k] = warp_sum(m.s2[k]);
-  m.n = warp_sum_i(m.n);
-  return m;
-}
-
 
 // ---------------------------------------------------------------------------------------------------
 // k_fit_warp: one warp per patch, no block-level synchronisation at all.
@@ -1150,90 +1037,7 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-// warp_lpr with the loads of both scans batched four at a time (PWPP_PART_ILP): the r01 capture of the L1 kernel (points
-// streamed from L2) shows 12 % of its stall samples on the one-load-per-iteration z reads of these two loops; the exact
-// selection only compares the registers that hold candidates.
-__device__ double warp_lpr_batched(const float4* __restrict__ P, int n, int nit, bool any_removed, const unsigned* __restrict__ alive_w, bool zone0,
-                                   double margin_z, int num_lpr, float* sel_buf) {
-  const int lane = lane_id();
-  const unsigned lt = lanemask_lt();
-  unsigned* cbuf = reinterpret_cast<unsigned*>(sel_buf);
-  if (num_lpr > 32) return warp_lpr_fallback(P, n, nit, any_removed, alive_w, zone0, margin_z, num_lpr, sel_buf);
-  unsigned kminL = 0xffffffffu;
-  int nv = 0;
-  for (int it0 = 0; it0 < nit; it0 += 4) {
-    float zv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int j = (it0 + u) * 32 + lane; zv[u] = P[j < n ? j : n - 1].z; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int it = it0 + u, j = it * 32 + lane;
-      bool valid = j < n;
-      if (any_removed && it < nit) valid = valid && ((alive_w[it] >> lane) & 1u);
-      if (zone0 && ((double) zv[u] < margin_z)) valid = false;
-      if (valid) { kminL = min(kminL, order_key(zv[u])); ++nv; }
-    }
-  }
-  const int nvalid = __reduce_add_sync(0xffffffffu, nv);
-  const int target = nvalid < num_lpr ? nvalid : num_lpr;
-  if (target == 0) return 0.0;
-  const int have = __reduce_add_sync(0xffffffffu, kminL != 0xffffffffu ? 1 : 0);
-  unsigned T = 0xffffffffu;
-  if (have >= target) {
-    const unsigned gmn = __reduce_min_sync(0xffffffffu, kminL);
-    const unsigned gmx = __reduce_max_sync(0xffffffffu, kminL != 0xffffffffu ? kminL : 0u);
-    T = kth_key(gmn, gmx, target, [&](unsigned cand) { return __reduce_add_sync(0xffffffffu, kminL < cand ? 1 : 0); });
-  }
-  int cc = 0;
-  for (int it0 = 0; it0 < nit; it0 += 4) {
-    float zv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int j = (it0 + u) * 32 + lane; zv[u] = P[j < n ? j : n - 1].z; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int it = it0 + u, j = it * 32 + lane;
-      if (it >= nit) break;   // uniform
-      bool valid = j < n;
-      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
-      if (zone0 && ((double) zv[u] < margin_z)) valid = false;
-      const unsigned key = order_key(zv[u]);
-      const bool c = valid && key <= T;
-      const unsigned bal = __ballot_sync(0xffffffffu, c);
-      if (c) { const int pos = cc + __popc(bal & lt); if (pos < 128) cbuf[pos] = key; }
-      cc += __popc(bal);
-    }
-  }
-  __syncwarp();
-  if (cc > 128) return warp_lpr_fallback(P, n, nit, any_removed, alive_w, zone0, margin_z, num_lpr, sel_buf);
-  unsigned ck[4];
-  unsigned kmn = 0xffffffffu, kmx = 0u;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int i = lane + 32 * q;
-    ck[q] = i < cc ? cbuf[i] : 0xffffffffu;
-    if (i < cc) { kmn = min(kmn, ck[q]); kmx = max(kmx, ck[q]); }
-  }
-  kmn = __reduce_min_sync(0xffffffffu, kmn);
-  kmx = __reduce_max_sync(0xffffffffu, kmx);
-  const int nq = (cc + 31) >> 5;   // registers per lane actually holding candidates (the r01 capture: 7 % of the M kernel's instructions are these compares)
-  const unsigned ans = kth_key(kmn, kmx, target, [&](unsigned cand) {
-    int cnt = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { if (q >= nq) break; cnt += ck[q] < cand; }
-    return __reduce_add_sync(0xffffffffu, cnt);
-  });
-  double ps = 0.0;
-  int c_lt = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) if (ck[q] < ans) { ps += (double) key_to_float(ck[q]); ++c_lt; }
-  ps = warp_sum(ps);
-  c_lt = __reduce_add_sync(0xffffffffu, c_lt);
-  const double lpr = (ps + (double) (target - c_lt) * (double) key_to_float(ans)) / (double) target;
-  __syncwarp();
-  return lpr;
-}
-
-template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false, bool NL = false, bool PILP = false>
+template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false>
 __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -1320,8 +1124,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
       const bool rvpf_round = rvpf_left > 0;
       const bool fused = fuse_ok && rvpf_round;
       // LPR: mean of the num_lpr lowest z among the alive points not below the zone-0 margin (S:88-103)
-      const double lpr = PILP ? warp_lpr_batched(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf)
-                                          : warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
+      const double lpr = warp_lpr(P, n, nit, any_removed, alive_w, zone0, margin_z, ap.num_lpr, sel_buf);
       const double zthr = lpr + (rvpf_round ? ap.th_seeds_v : ap.th_seeds);
       const double zin = lpr + ap.th_seeds;   // inner (R-GPF seed) threshold of a fused round
       c[2] = lpr;
@@ -1390,7 +1193,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
 #pragma unroll
         for (int q = 0; q < 6; ++q) ms.s2[q] = hi ? mi.s2[q] : m.s2[q];
         Plane mine = pl;
-        if (ms.n > 0) solve_plane<NL>(ms, c, mine);
+        if (ms.n > 0) plane_from_moments(ms, c, mine);
         auto bcast = [&](int src) {
           Plane t;
 #pragma unroll
@@ -1405,7 +1208,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
           break;
         }
       } else {
-        if (m.n > 0) { solve_plane<NL>(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
+        if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
         tot = m;
         if (!rvpf_round) break;
       }
@@ -1477,7 +1280,7 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
 #pragma unroll
       for (int q = 0; q < 6; ++q) tot.s2[q] += warp_sum(dm.s2[q]);
       tot.n += warp_sum_i(dm.n);
-      if (tot.n > 0) solve_plane<NL>(tot, c, pl);   // S:49 otherwise
+      if (tot.n > 0) plane_from_moments(tot, c, pl);   // S:49 otherwise
       __syncwarp();
     }
     const int n_ground = have_plane ? tot.n : 0;
@@ -1485,30 +1288,6 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
     // stable partition: ground indices ascending, then non-ground indices ascending
     {
       int g_run = 0, ng_run = 0;
-      if (PILP) {   // PWPP_PART_ILP: four index loads in flight per lane (see k_fit_cta)
-        for (int it0 = 0; it0 < nit; it0 += 4) {
-          int idxv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { const int j = (it0 + u) * 32 + lane; idxv[u] = j < n ? __float_as_int(P[j].w) : 0; }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = it0 + u;
-            if (it >= nit) break;   // uniform
-            const int j = it * 32 + lane;
-            const bool v = j < n;
-            const unsigned bg = have_plane ? member_w[it] : 0u;
-            const unsigned bv = __ballot_sync(0xffffffffu, v);
-            const unsigned bn = bv & ~bg;
-            if (v) {
-              if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idxv[u];
-              else out[n_ground + ng_run + __popc(bn & lt)] = idxv[u];
-              if (wq.labels) { const bool isg = (bg >> lane) & 1u; if (isg || !any_removed || ((alive_w[it] >> lane) & 1u)) wq.labels[start + j] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT; }
-            }
-            g_run += __popc(bg);
-            ng_run += __popc(bn);
-          }
-        }
-      } else
       for (int it = 0; it < nit; ++it) {
         const int j = it * 32 + lane;
         const bool v = j < n;
@@ -1540,103 +1319,6 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
       if (cls >= cls_last) cnt = wq.count[cls];
       claim_sync();
     }
-  }
-}
-
-__global__ void __launch_bounds__(128) k_fit_stream(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
-                                                    int nbp, const int* __restrict__ bin_off, WorkQueues wq, int* __restrict__ part, BinFit* __restrict__ fits) {
-  __shared__ float s_sel[4][128];
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  float* sel_buf = s_sel[warp];
-  for (;;) {
-    int it0 = 0;
-    if (lane == 0) it0 = atomicAdd(&wq.head[NUM_CLASSES - 1], 1);
-    it0 = __shfl_sync(0xffffffffu, it0, 0);
-    if (it0 >= wq.count[NUM_CLASSES - 1]) return;
-    const int4 wi = wq.items[NUM_CLASSES - 1][it0];
-    const int f = wi.x >> 12, bin = wi.x & 0xfff, n = wi.y;
-    const long long start = work_item_start(wi);
-    const float4* P = sorted + start;
-    int* out = part + start;
-    const int zone = (bin >= g.bin_base[3]) ? 3 : (bin >= g.bin_base[2]) ? 2 : (bin >= g.bin_base[1]) ? 1 : 0;
-    const bool zone0 = (zone == 0);
-    const double margin_z = ap.adaptive_seed_selection_margin * states[f].sensor_height;  // S:90
-
-    RvpfPlanes rv;
-    rv.n = 0;
-    Plane pl;  // the "member" plane: normal_, pc_mean_, singular_values_, d_
-    pl.d = 0.0;
-    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
-    bool have_plane = false;
-    const float4 first = P[0];
-    double c[3] = {(double) first.x, (double) first.y, 0.0};
-
-    // 1. R-VPF (S:482-508). For zone != 0 the fitted plane can never be used (the loop breaks at once and the
-    //    R-GPF seed fit overwrites it: its seed set is non-empty because pwpp_create enforces th_seeds > 0).
-    if (ap.enable_RVPF && zone0) {
-      for (int it = 0; it < ap.num_iter; ++it) {
-        const double lpr = select_lpr(P, n, true, margin_z, ap.num_lpr, rv, ap.th_dist_v, sel_buf);
-        c[2] = lpr;
-        const Moments m = accumulate<0>(P, n, rv, ap.th_dist_v, lpr + ap.th_seeds_v, pl, 0.0, c);
-        if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
-        if (have_plane && pl.normal[2] < ap.uprightness_thr) {  // S:489
-          if (rv.n < MAX_RVPF) rv.pl[rv.n++] = pl;
-        } else break;
-      }
-    }
-    // 2. R-GPF (S:513-543)
-    {
-      const double lpr = select_lpr(P, n, zone0, margin_z, ap.num_lpr, rv, ap.th_dist_v, sel_buf);
-      c[2] = lpr;
-      const Moments m = accumulate<0>(P, n, rv, ap.th_dist_v, lpr + ap.th_seeds, pl, 0.0, c);
-      if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }
-    }
-    for (int it = 0; it < ap.num_iter - 1; ++it) {
-      if (!have_plane) break;
-      const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-      const Moments m = accumulate<1>(P, n, rv, ap.th_dist_v, 0.0, pl, ap.th_dist, cc);
-      if (m.n > 0) plane_from_moments(m, cc, pl);
-    }
-    // last iteration (S:528-542): split by the current plane, then refit on the ground part
-    int n_ground = 0;
-    if (have_plane) {
-      const Plane cls = pl;
-      const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-      const Moments m = accumulate<1>(P, n, rv, ap.th_dist_v, 0.0, cls, ap.th_dist, cc);
-      n_ground = m.n;
-      if (m.n > 0) plane_from_moments(m, cc, pl);
-      int g_run = 0, ng_run = 0;
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < n;
-        bool is_g = false;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          p = P[i];
-          const bool alive = (rv.n == 0) || is_alive(rv, ap.th_dist_v, p.x, p.y, p.z);
-          is_g = alive && (point_plane_distance(cls, p.x, p.y, p.z) < ap.th_dist);
-        }
-        const unsigned bg = __ballot_sync(0xffffffffu, valid && is_g);
-        const unsigned bn = __ballot_sync(0xffffffffu, valid && !is_g);
-        if (valid) {
-          const int idx = __float_as_int(p.w);
-          if (is_g) out[g_run + __popc(bg & lanemask_lt())] = idx;
-          else out[n_ground + ng_run + __popc(bn & lanemask_lt())] = idx;
-        }
-        g_run += __popc(bg);
-        ng_run += __popc(bn);
-      }
-    } else {
-      for (int i = lane; i < n; i += 32) out[i] = __float_as_int(P[i].w);
-    }
-    if (lane == 0) {
-      BinFit& r = fits[(size_t) f * g.nbins + bin];
-      r.n = n; r.n_ground = n_ground; r.fitted = 1;
-      r.verdict = have_plane ? 0 : PW_FIT_NO_PLANE;
-      for (int k = 0; k < 3; ++k) { r.mean[k] = pl.mean[k]; r.normal[k] = pl.normal[k]; r.sv[k] = pl.sv[k]; }
-      r.d = pl.d;
-    }
-    __syncwarp();
   }
 }
 

@@ -2,7 +2,7 @@
 //
 // Same per-patch algorithm and citations as pwpp_fit.cuh (reference cpp/patchworkpp/src/patchworkpp.cpp "S:":
 // extract_piecewiseground 467-549, extract_initial_seeds 77-149, estimate_plane 47-75). A patch of this size does not
-// fit the register / shared-memory resident kernels, and one warp per patch (k_fit_stream) leaves a 1M-point frame's
+// fit the register / shared-memory resident kernels, and one warp per patch would leave a 1M-point frame's
 // thirty-odd 20k..40k-point patches on thirty-odd warps. Here one CTA owns a patch: every pass streams the patch from
 // L2 (it was written by k_scatter just before and is re-read 5..7 times; 16 B x 40k points = 640 KB stays L2-resident)
 // with NT-strided, fully coalesced float4 loads, four in flight per thread; per-pass state is recomputed instead of
@@ -25,10 +25,7 @@ namespace pwpp {
 constexpr int BIG_CCAP = 512;   // candidate buffer of the LPR selection (16 keys per lane of warp 0)
 constexpr int BIG_U = 4;        // loads in flight per thread
 
-// FIX (PWPP_X_FIXPOINT): every pass records the selected set as ballot words in the patch's (not yet written) output region,
-// an R-GPF pass compares its set with the set its plane was fitted to, and an unchanged set ends the iteration — the exact
-// fixpoint exit of the other fit kernels (on the synthetic frames 1.6 of the 3 R-GPF passes remain), for patches of any size.
-template <int NW, int MINB, bool FUSE, bool NL = false, bool FIX = false>
+template <int NW, int MINB, bool FUSE>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states, Geometry g,
                                                             AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq, int* __restrict__ part,
                                                             BinFit* __restrict__ fits) {
@@ -46,7 +43,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
   __shared__ unsigned s_T;
   __shared__ int s_ccount;
   __shared__ int s_n[2];
-  __shared__ int s_chg[FIX ? NW : 1];
   __shared__ Plane s_plane, s_plane2;
   __shared__ int4 s_item;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -224,9 +220,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
     //      MODE 1: {alive, signed distance to `cls` < th_dist}. Leaves the counts in nsel[0..1] and, for non-empty
     //      sets, the fitted planes in s_plane / s_plane2 (valid until the next call). ----
     int nsel[2] = {0, 0};
-    bool set_changed = true;                                   // FIX: did the last pass select a set different from the recorded one
-    unsigned* mw = reinterpret_cast<unsigned*>(out);           // FIX: ballot words of the recorded set (scratch until the partition)
-    auto fit_pass = [&](int mode, bool fused, double zthr, double zin, const Plane& cls, const double cc[3], bool compare = false) {
+    auto fit_pass = [&](int mode, bool fused, double zthr, double zin, const Plane& cls, const double cc[3]) {
       double a[9], b[FUSE ? 9 : 1];
 #pragma unroll
       for (int q = 0; q < 9; ++q) a[q] = 0.0;
@@ -235,15 +229,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
       int na = 0, nb = 0;
       PlaneF pf;
       pf.n0 = (float) cls.normal[0]; pf.n1 = (float) cls.normal[1]; pf.n2 = (float) cls.normal[2]; pf.d = (float) cls.d;
-      int mychg = 0;
-      // FIX: the trip count must be warp-uniform (ballots inside): iterate from the warp's first thread and add the lane
-      for (int i0 = FIX ? tid - lane : tid; i0 < n; i0 += BIG_U * NT) {
+      for (int i0 = tid; i0 < n; i0 += BIG_U * NT) {
         float4 q[BIG_U];
 #pragma unroll
-        for (int u = 0; u < BIG_U; ++u) { const int j = i0 + (FIX ? lane : 0) + u * NT; q[u] = P[j < n ? j : n - 1]; }
+        for (int u = 0; u < BIG_U; ++u) { const int j = i0 + u * NT; q[u] = P[j < n ? j : n - 1]; }
 #pragma unroll
         for (int u = 0; u < BIG_U; ++u) {
-          const int j = i0 + (FIX ? lane : 0) + u * NT;
+          const int j = i0 + u * NT;
           const float4 p = q[u];
           bool in = j < n;
           if (in && rv.n != 0) in = is_alive(rv, ap.th_dist_v, p.x, p.y, p.z);
@@ -252,15 +244,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
             int fl = dist_filter(pf, thf, p.x, p.y, p.z);
             if (fl < 0) fl = (point_plane_distance(cls, p.x, p.y, p.z) < ap.th_dist) ? 1 : 0;   // S:525 / S:529, exact
             in = fl != 0;
-          }
-          if (FIX) {   // record the set the next plane is fitted to (the inner seeds of a fused round)
-            const bool rec = (FUSE && fused) ? (in && ((double) p.z < zin)) : in;
-            const unsigned bal = __ballot_sync(0xffffffffu, rec);
-            const int wb = i0 + u * NT;   // first point of this warp's 32-point group
-            if (lane == 0 && wb < n) {
-              if (compare && mw[wb >> 5] != bal) mychg = 1;
-              mw[wb >> 5] = bal;
-            }
           }
           if (in) {
             const double dx = (double) p.x - cc[0], dy = (double) p.y - cc[1], dz = (double) p.z - cc[2];
@@ -283,7 +266,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
         for (int q = 0; q < (FUSE ? 9 : 1); ++q) b[q] = warp_sum(b[q]);
         nb = __reduce_add_sync(0xffffffffu, nb);
       }
-      if (FIX && lane == 0) s_chg[w] = mychg;
       if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) s_part[w][q] = a[q];
@@ -317,19 +299,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
         for (int q = 0; q < 6; ++q) ms.s2[q] = __shfl_sync(0xffffffffu, v, half + 3 + q);
         ms.n = __shfl_sync(0xffffffffu, cn, half + 9);
         Plane mine = pl;
-        if (ms.n > 0) solve_plane<NL>(ms, cc, mine);
+        if (ms.n > 0) plane_from_moments(ms, cc, mine);
         if (lane == 0) { s_plane = mine; s_n[0] = ms.n; }
         if (lane == 16) { s_plane2 = mine; s_n[1] = (FUSE && fused) ? ms.n : 0; }
       }
       __syncthreads();
       nsel[0] = s_n[0];
       nsel[1] = s_n[1];
-      if (FIX) {
-        int ch = 0;
-#pragma unroll
-        for (int q = 0; q < (FIX ? NW : 1); ++q) ch |= s_chg[q];
-        set_changed = ch != 0;
-      }
     };
 
     // 1. R-VPF (S:482-508). For zone != 0 the fitted plane can never be used (see k_fit_stream).
@@ -358,21 +334,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_big(const float4* __restr
       fit_pass(0, false, lpr + ap.th_seeds, 0.0, pl, c);
       if (nsel[0] > 0) { pl = s_plane; have_plane = true; }
     }
-    bool fixpoint = false;     // FIX: a pass selected exactly the set its plane was fitted to: every later pass would repeat it
-    Plane cls_fix = pl;
     int n_ground = 0;
     for (int it = 0; it < ap.num_iter - 1; ++it) {
       if (!have_plane) break;
       const Plane cls = pl;
       const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
-      fit_pass(1, false, 0.0, 0.0, cls, cc, true);
+      fit_pass(1, false, 0.0, 0.0, cls, cc);
       if (nsel[0] > 0) pl = s_plane;
-      if (FIX && !set_changed) { fixpoint = true; cls_fix = cls; n_ground = nsel[0]; break; }
     }
     // last iteration (S:528-542): split by the current plane, then refit on the ground part
     if (have_plane) {
-      const Plane cls = fixpoint ? cls_fix : pl;
-      if (!fixpoint) {
+      const Plane cls = pl;
+      {
         const double cc[3] = {pl.mean[0], pl.mean[1], pl.mean[2]};
         fit_pass(1, false, 0.0, 0.0, cls, cc);
         n_ground = nsel[0];

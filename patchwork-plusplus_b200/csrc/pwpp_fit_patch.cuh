@@ -17,9 +17,45 @@
 //   * the 9 moment sums are reduced by an interleaved butterfly (all 9 chains in flight), partials are combined by 9 lanes
 //     of warp 0 in warp order (bit-reproducible), the 3x3 problem is solved once (two planes side by side in fused rounds).
 #pragma once
-#include "pwpp_fit_group.cuh"
+#include "pwpp_fit.cuh"
+#include "pwpp_trace.cuh"
 
 namespace pwpp {
+
+constexpr int GRP_CBUF = 128;   // candidates the exact LPR selection handles (4 keys per lane)
+
+// exact selection among cc (<= GRP_CBUF) candidate keys in cbuf: mean of the `target` smallest (S:99-103) by RANKING: a
+// candidate's rank = number of candidates before it in (key, position) order; all compares are independent (no serial
+// bisection). The sum of <= 32 floats in double is exact, so the result does not depend on the candidates' order. Uniform.
+__device__ __forceinline__ double grp_rank_mean(const unsigned* cbuf, int cc, int target) {
+  const int lane = lane_id();
+  unsigned ck[GRP_CBUF / 32];
+  int rank[GRP_CBUF / 32];
+  const int nq = (cc + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < GRP_CBUF / 32; ++q) { const int i = lane + 32 * q; ck[q] = i < cc ? cbuf[i] : 0xffffffffu; rank[q] = 0; }
+  // candidates are broadcast 8 at a time (independent shared-memory reads in flight); entries past cc hold 0xffffffff (or
+  // stale keys) and are masked by the position test
+  for (int j0 = 0; j0 < cc; j0 += 8) {
+    unsigned v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = cbuf[(j0 + u) < GRP_CBUF ? (j0 + u) : (GRP_CBUF - 1)];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u;
+      if (j < cc) {   // uniform
+#pragma unroll
+        for (int q = 0; q < GRP_CBUF / 32; ++q) { if (q >= nq) break; rank[q] += (v[u] < ck[q] || (v[u] == ck[q] && j < lane + 32 * q)) ? 1 : 0; }
+      }
+    }
+  }
+  double ps = 0.0;
+#pragma unroll
+  for (int q = 0; q < GRP_CBUF / 32; ++q) if (lane + 32 * q < cc && rank[q] < target) ps += (double) key_to_float(ck[q]);
+  ps = warp_sum(ps);
+  return ps / (double) target;
+}
+
 
 constexpr int FP_SL = 16;    // points per thread (register slots)
 constexpr int FP_STG = 256;  // staging entries per warp: the participating points of 8 slots

@@ -23,9 +23,9 @@
 #include "pwpp_common.cuh"
 #include "pwpp_fit.cuh"
 #include "pwpp_fit_big.cuh"
-#include "pwpp_fit_group.cuh"
 #include "pwpp_fit_patch.cuh"
 #include "pwpp_order.cuh"
+#include "pwpp_front.cuh"
 
 namespace pwpp {
 
@@ -160,100 +160,6 @@ __global__ void k_bin_scan(FrameTable ft, int nbp, int nbins, int num_min_pts, c
       const int c = cls_of(n);
       wq.items[c][s_cls_base[c] + atomicAdd(&s_cls_pos[c], 1)] = make_work_item(f, b, n, ft.pt_off[f] + (long long) s_scan[b]);
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_bin_scan_groups: bin offsets and scatter bases like k_bin_scan; the fit work items are
-//   queue GRP_CLS_A   GROUPS of consecutive small bins (each <= GRP_A_BIN points; <= GRP_A_PTS points and <= GRP_A_MP fitted
-//                     patches per group) for k_fit_group (pwpp_fit_group.cuh): the many small patches of the outer zones
-//   queue GRP_CLS_B   one patch of GRP_A_BIN < n <= GRP_B_PTS points   (k_fit_patch, 8 warps)
-//   queue GRP_CLS_C   one patch of GRP_B_PTS < n <= GRP_C_PTS points   (k_fit_patch, 16 warps)
-//   queue NUM_CLASSES-1 (class X): one patch above GRP_C_PTS points     (k_fit_big)
-// Bins below num_min_pts (S:191) inside a group's span only occupy shared memory; leading ones are skipped.
-constexpr int GRP_CLS_A = 0, GRP_CLS_B = 1, GRP_CLS_C = 2;
-constexpr int GRP_A_BIN = 1024, GRP_A_PTS = 2048, GRP_A_MP = 32, GRP_B_PTS = 4096, GRP_C_PTS = 8192;
-constexpr int GRP_A_NW = 8, GRP_B_NW = 8, GRP_C_NW = 16;   // warps per CTA of the three kernels
-__global__ void k_bin_scan_groups(FrameTable ft, int nbp, int nbins, int num_min_pts, const unsigned short* __restrict__ chist, unsigned int* __restrict__ cbase,
-                                  int* __restrict__ bin_off, WorkQueues wq, BinFit* __restrict__ fits) {
-  PW_DYN_SHARED(int, s_scan);  // [nbp + 1]
-  const int f = blockIdx.x;
-  const int c0 = ft.chunk_off[f], c1 = ft.chunk_off[f + 1];
-  for (int b = threadIdx.x; b < nbp; b += blockDim.x) {
-    int tot = 0;
-    for (int c = c0; c < c1; ++c) tot += chist[(size_t) c * nbp + b];
-    s_scan[b] = tot;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    int carry = 0;
-    for (int b0 = 0; b0 < nbp; b0 += 32) {
-      const int b = b0 + threadIdx.x;
-      int v = b < nbp ? s_scan[b] : 0;
-      int incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int) threadIdx.x >= o) incl += t; }
-      if (b < nbp) s_scan[b] = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (threadIdx.x == 0) s_scan[nbp] = carry;
-  }
-  __syncthreads();
-  int* bo = bin_off + (size_t) f * (nbp + 1);
-  for (int b = threadIdx.x; b <= nbp; b += blockDim.x) bo[b] = s_scan[b];
-  for (int b = threadIdx.x; b < nbp; b += blockDim.x) {
-    unsigned int run = (unsigned int) s_scan[b];
-    for (int c = c0; c < c1; ++c) {
-      const unsigned int v = chist[(size_t) c * nbp + b];
-      cbase[(size_t) c * nbp + b] = run;
-      run += v;
-    }
-  }
-  for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
-    const int n = s_scan[b + 1] - s_scan[b];
-    if (!(n >= num_min_pts && n > 0)) {
-      BinFit& r = fits[(size_t) f * nbins + b];
-      r.n = n; r.n_ground = 0; r.d = 0.0;
-      for (int k = 0; k < 3; ++k) { r.mean[k] = 0.0; r.normal[k] = 0.0; r.sv[k] = 0.0; }
-      r.fitted = (n >= num_min_pts) ? 1 : 0;   // an EMPTY patch with num_min_pts <= 0 is "fitted" with the previous patch's plane (S:49)
-      r.verdict = r.fitted ? PW_FIT_NO_PLANE : 0;
-    }
-  }
-  // greedy packing in bin order (sequential: ~nbins short steps per frame)
-  if (threadIdx.x == 0) {
-    const long long p0 = ft.pt_off[f];
-    int gb = 0, gpts = 0, gfit = 0;   // current group: first bin, points, fitted patches
-    auto flush = [&](int bend) {
-      if (gfit > 0) {
-        const int cls = GRP_CLS_A;
-        const int pos = atomicAdd(&wq.count[cls], 1);
-        wq.items[cls][pos] = make_group_item(f, gb, bend - gb, gpts, p0 + (long long) s_scan[gb]);
-      }
-      gb = bend; gpts = 0; gfit = 0;
-    };
-    for (int b = 0; b < nbins; ++b) {
-      const int n = s_scan[b + 1] - s_scan[b];
-      const bool fit = n >= num_min_pts && n > 0;
-      if (n > GRP_A_BIN) {   // a patch of its own
-        flush(b);
-        if (fit) {
-          const int cls = n > GRP_C_PTS ? NUM_CLASSES - 1 : (n > GRP_B_PTS ? GRP_CLS_C : GRP_CLS_B);
-          const int pos = atomicAdd(&wq.count[cls], 1);
-          wq.items[cls][pos] = make_work_item(f, b, n, p0 + (long long) s_scan[b]);
-        }
-        gb = b + 1;
-        continue;
-      }
-      if (gfit == 0 && !fit) { gb = b + 1; gpts = 0; continue; }   // leading unfitted bins stay out
-      const int npts = gpts + n, nfit = gfit + (fit ? 1 : 0);
-      const bool ok = npts <= GRP_A_PTS && nfit <= GRP_A_MP && (b - gb) < 1000;
-      if (!ok) {
-        flush(b);
-        if (!fit) { gb = b + 1; continue; }
-        gpts = n; gfit = 1;
-      } else { gpts = npts; gfit = nfit; }
-    }
-    flush(nbins);
   }
 }
 

@@ -103,7 +103,9 @@ extern "C" void simt_switch(void** save_sp, void* load_sp);
 void yield_();
 [[noreturn]] void deadlock(const char* what);
 void launch_impl(const char* name, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
-void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem, const std::function<void()>& body);
+void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem, const std::function<void()>& body, unsigned block_y = 0);
+void cluster_sync_();                       // barrier over all threads of all live CTAs (a cluster = the CTAs of one concurrent launch)
+void* cluster_map_(void* p, int rank);      // the same dynamic-shared-memory location in CTA `rank`
 
 }  // namespace simt
 
@@ -290,5 +292,5 @@ namespace simt {
 template <typename F>
 static inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, F&& f) { launch_impl(name, grid, block, smem, std::function<void()>(f)); }
 template <typename F>
-static inline void launch_concurrent(const char* name, int nctas, dim3 block, size_t smem, F&& f) { launch_concurrent_impl(name, nctas, block, smem, std::function<void()>(f)); }
+static inline void launch_concurrent(const char* name, int nctas, dim3 block, size_t smem, F&& f, unsigned block_y = 0) { launch_concurrent_impl(name, nctas, block, smem, std::function<void()>(f), block_y); }
 }

@@ -13,7 +13,6 @@
 #include "pwpp.h"
 #include "pwpp_host.hpp"
 #include "pwpp_kernels.cuh"
-#include "pwpp_front.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // runtime of the stand-in
@@ -187,7 +186,27 @@ void launch_impl(const char* name, dim3 grid, dim3 block, size_t smem, const std
 
 // All CTAs of a 1-D grid live at once (a kernel whose CTAs wait for each other). The kernel must not use static
 // __shared__ variables (they would be shared by all CTAs here).
-void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem, const std::function<void()>& body) {
+// cluster barrier: every thread of every live CTA (threads that returned no longer count)
+static int g_cl_arrived = 0;
+static unsigned long long g_cl_gen = 0;
+void cluster_sync_() {
+  auto alive = [] { int a = 0; for (Cta* c : g_ctas) a += c->alive; return a; };
+  ++g_cta.progress;
+  const unsigned long long gen = g_cl_gen;
+  if (++g_cl_arrived >= alive()) { g_cl_arrived = 0; ++g_cl_gen; return; }
+  while (g_cl_gen == gen) {
+    yield_();
+    if (g_cl_gen == gen && g_cl_arrived >= alive()) { g_cl_arrived = 0; ++g_cl_gen; }
+  }
+}
+void* cluster_map_(void* p, int rank) {
+  char* base = g_cta.dyn_smem.data();
+  const size_t off = (size_t) (static_cast<char*>(p) - base);
+  if (off >= g_cta.dyn_smem.size() || rank < 0 || rank >= (int) g_ctas.size()) { std::fprintf(stderr, "simt: cluster_map of a pointer outside dynamic shared memory\n"); std::abort(); }
+  return g_ctas[rank]->dyn_smem.data() + off;
+}
+
+void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem, const std::function<void()>& body, unsigned block_y) {
   const int nt = (int) (block.x * block.y * block.z);
   if (nt <= 0 || nt > MAX_THREADS || nctas < 1 || nctas > 16) { std::fprintf(stderr, "simt: bad concurrent launch (%d CTAs x %d threads)\n", nctas, nt); std::abort(); }
   blockDim = block; gridDim = dim3(nctas, 1, 1);
@@ -195,7 +214,8 @@ void launch_concurrent_impl(const char* name, int nctas, dim3 block, size_t smem
   static std::vector<Cta*> pool;
   while ((int) pool.size() < nctas) pool.push_back(new Cta());
   g_ctas.assign(pool.begin(), pool.begin() + nctas);
-  for (int c = 0; c < nctas; ++c) { uint3 bid; bid.x = c; bid.y = 0; bid.z = 0; init_cta(*g_ctas[c], name, nt, smem, body, bid); }
+  for (int c = 0; c < nctas; ++c) { uint3 bid; bid.x = c; bid.y = block_y; bid.z = 0; init_cta(*g_ctas[c], name, nt, smem, body, bid); }
+  g_cl_arrived = 0;
   g_concurrent = true;
   run_live_ctas();
   g_concurrent = false;
@@ -226,8 +246,8 @@ struct SimtTwin {
   std::vector<double> hist;
   std::vector<FrameOut> out;
   int sel = 0;
-  // kernel-variant switches (the PWPP_* environment switches of pwpp_create)
-  int hist_pipe = 2, scatter_pipe = 0, l2_nw = 8, l3_nw = 8, persistent_ctas = 2, fuse_seed = 1, solve_call = 0, x_kernel = 1, x_nw = 16, emit_split = 1, part_ilp = 0, front = 0, front_w = 2, front_concurrent = 0, l2_wide = 0, l2_pls = 0, x_fix = 0, m_resident = 0, l1_cta = 0, m_half = 0, group = 0, order = 0;
+  // switches (the PWPP_* environment switches of pwpp_create)
+  int persistent_ctas = 2, emit_split = 1, front = 1, patch = 0, order = 0;
   std::string last_launches;
 };
 
@@ -257,27 +277,10 @@ void simt_select(void* h, int f) { ((SimtTwin*) h)->sel = f; }
 int simt_set_option(void* h, const char* name, int v) {
   SimtTwin* t = (SimtTwin*) h;
   const std::string n(name);
-  if (n == "hist_pipe") t->hist_pipe = v;
-  else if (n == "scatter_pipe") t->scatter_pipe = v;
-  else if (n == "l2_nw") t->l2_nw = v;
-  else if (n == "l3_nw") t->l3_nw = v;
-  else if (n == "persistent_ctas") t->persistent_ctas = v;
-  else if (n == "fuse_seed") t->fuse_seed = v;
-  else if (n == "solve_call") t->solve_call = v;
-  else if (n == "x_kernel") t->x_kernel = v;
+  if (n == "persistent_ctas") t->persistent_ctas = v;
   else if (n == "emit_split") t->emit_split = v;
-  else if (n == "part_ilp") t->part_ilp = v;
   else if (n == "front") t->front = v;
-  else if (n == "front_w") t->front_w = v;
-  else if (n == "front_concurrent") t->front_concurrent = v;
-  else if (n == "l2_wide") t->l2_wide = v;
-  else if (n == "l2_pls") t->l2_pls = v;
-  else if (n == "x_fix") t->x_fix = v;
-  else if (n == "m_resident") t->m_resident = v;
-  else if (n == "l1_cta") t->l1_cta = v;
-  else if (n == "m_half") t->m_half = v;
-  else if (n == "x_nw") t->x_nw = v;
-  else if (n == "group") t->group = v;
+  else if (n == "patch") t->patch = v;
   else if (n == "order") t->order = v;
   else return -1;
   return 0;
@@ -331,97 +334,46 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   wq.count = ctr.data();
   wq.head = ctr.data() + NUM_CLASSES;
   wq.labels = t->order ? labels.data() : nullptr;
-  if (t->front) {   // PWPP_FRONT: the three front-end kernels as one persistent, L2-pipelined kernel
-    const int nitems = 2 * total_chunks + nframes, W = std::max(1, std::min(nframes, t->front_w));
-    std::vector<FrontItem> fitems((size_t) nitems + 1, FrontItem{-1, -1});
-    std::vector<int> fctr(1 + 2 * nframes, 0);
-    simt::launch("k_front_plan", (nframes + W + 127) / 128, 128, 0, [&] { k_front_plan(chunk_off.data(), nframes, W, fitems.data()); });
-    for (int k = 0; k < nitems; ++k) if (fitems[k].tf < 0) { std::fprintf(stderr, "simt_twin: k_front_plan left item %d unset\n", k); std::abort(); }
-    FrontArgs fa{d_pts, ft, states, g, ap, has_intensity, nbp, nb, t->fast ? 1 : 0, bin_ids.data(), chist.data(), cbase.data(), bin_off.data(), wq, fits.data(),
-                 sorted.data(), fitems.data(), nitems, t->l2_wide ? CLS_L2_WIDE_MAX : CLS_L2_MAX, t->m_half ? CLS_M_HALF_MAX : CLS_M_MAX, fctr.data(), nframes};
-    const size_t sm_f = front_smem_bytes(nbp);
-    if (t->front_concurrent) simt::launch_concurrent("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });   // CTAs interleave and wait for each other
-    else simt::launch("k_front", t->persistent_ctas, FRONT_THREADS, sm_f, [&] { k_front(fa); });
-    if (fctr[0] < nitems) { std::fprintf(stderr, "simt_twin: k_front stopped at item %d of %d\n", fctr[0], nitems); std::abort(); }
+  if (t->front) {   // one cluster per frame (pwpp_front.cuh): the CTAs of a cluster run concurrently, frames one after another
+    const size_t sm_f = front_cluster_smem_bytes(nbp);
+    for (int f = 0; f < nframes; ++f) {
+#define FC_ARGS d_pts, ft, states, g, ap, has_intensity, nbp, nb, bin_ids.data(), bin_off.data(), wq, fits.data(), sorted.data()
+      if (t->fast) simt::launch_concurrent("k_front_cluster<fast>", FC_CS, FC_THREADS, sm_f, [&] { k_front_cluster<true, CLS_L2_MAX>(FC_ARGS); }, (unsigned) f);
+      else simt::launch_concurrent("k_front_cluster<exact>", FC_CS, FC_THREADS, sm_f, [&] { k_front_cluster<false, CLS_L2_MAX>(FC_ARGS); }, (unsigned) f);
+#undef FC_ARGS
+    }
   } else {
-  if (max_chunks > 0) {
-    dim3 grid(max_chunks, nframes);
-    const size_t sm_h = nbp * sizeof(unsigned int);
+    if (max_chunks > 0) {
+      dim3 grid(max_chunks, nframes);
+      const size_t sm_h = nbp * sizeof(unsigned int);
 #define HIST_ARGS d_pts, ft, states, g, ap, has_intensity, nbp, bin_ids.data(), chist.data()
-    if (!t->fast) simt::launch("k_bin_hist<false,0>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<false, 0>(HIST_ARGS); });
-    else if (t->hist_pipe == 0) simt::launch("k_bin_hist<true,0>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 0>(HIST_ARGS); });
-    else simt::launch("k_bin_hist<true,2>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 2>(HIST_ARGS); });
+      if (!t->fast) simt::launch("k_bin_hist<false,0>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<false, 0>(HIST_ARGS); });
+      else simt::launch("k_bin_hist<true,2>", grid, CHUNK_THREADS, sm_h, [&] { k_bin_hist<true, 2>(HIST_ARGS); });
 #undef HIST_ARGS
+    }
+    simt::launch("k_bin_scan", nframes, 512, (nbp + 1) * sizeof(int),
+                 [&] { k_bin_scan<CLS_L2_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
+    if (max_chunks > 0) {
+      dim3 grid(max_chunks, nframes);
+      const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
+      simt::launch("k_scatter<false,4>", grid, CHUNK_THREADS, sm_sc, [&] { k_scatter<false, 4>(d_pts, ft, nbp, bin_ids.data(), cbase.data(), sorted.data()); });
+    }
   }
-  if (t->m_half && t->l2_wide) simt::launch("k_bin_scan<5888,256>", nframes, 512, (nbp + 1) * sizeof(int),
-               [&] { k_bin_scan<CLS_L2_WIDE_MAX, CLS_M_HALF_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
-  else if (t->m_half) simt::launch("k_bin_scan<4096,256>", nframes, 512, (nbp + 1) * sizeof(int),
-               [&] { k_bin_scan<CLS_L2_MAX, CLS_M_HALF_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
-  else if (t->l2_wide) simt::launch("k_bin_scan<5888>", nframes, 512, (nbp + 1) * sizeof(int),
-               [&] { k_bin_scan<CLS_L2_WIDE_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
-  else simt::launch("k_bin_scan", nframes, 512, (nbp + 1) * sizeof(int),
-               [&] { k_bin_scan<CLS_L2_MAX>(ft, nbp, nb, ap.num_min_pts, chist.data(), cbase.data(), bin_off.data(), wq, fits.data()); });
-  if (max_chunks > 0) {
-    dim3 grid(max_chunks, nframes);
-    const size_t sm_sc = (size_t) (CHUNK_THREADS / 32) * nbp * sizeof(unsigned int);
-#define SC_ARGS d_pts, ft, nbp, bin_ids.data(), cbase.data(), sorted.data()
-    if (t->scatter_pipe) simt::launch("k_scatter<true,3>", grid, CHUNK_THREADS, sm_sc, [&] { k_scatter<true, 3>(SC_ARGS); });
-    else simt::launch("k_scatter<false,4>", grid, CHUNK_THREADS, sm_sc, [&] { k_scatter<false, 4>(SC_ARGS); });
-#undef SC_ARGS
-  }
-  }   // !front
 #define FIT_ARGS sorted.data(), ft, states, g, ap, nbp, bin_off.data(), wq, part.data(), fits.data()
   const int pg = t->persistent_ctas;
   const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
-  if (t->group) {   // patches above 512 points: k_fit_patch (pwpp_fit_patch.cuh); classes S, M, X below as always
+  if (t->patch) {   // PWPP_FIT_PATCH: patches above 512 points on k_fit_patch
     simt::launch("k_fit_patch<16>", pg, 16 * 32, (size_t) 16 * FP_STG * 16, [&] { k_fit_patch<16, 1, 4>(FIT_ARGS); });
     simt::launch("k_fit_patch<8>", pg, 8 * 32, (size_t) 8 * FP_STG * 16, [&] { k_fit_patch<8, 2, 3>(FIT_ARGS); });
     simt::launch("k_fit_patch<4>", pg, 4 * 32, (size_t) 4 * FP_STG * 16, [&] { k_fit_patch<4, 4, 2>(FIT_ARGS); });
-    simt::launch("k_fit_warp<true,1,1>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2>(FIT_ARGS); });
-    simt::launch("k_fit_resident<8,8,0>", pg, FIT_THREADS, 0, [&] { k_fit_resident<8, 8, 0, 2>(FIT_ARGS); });
   } else {
-  if (t->m_half) simt::launch("k_fit_resident<16,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<16, 16, 1, 2>(FIT_ARGS); });
-  if (t->m_resident) simt::launch("k_fit_resident<32,16,1>", pg, FIT_THREADS, 0, [&] { k_fit_resident<32, 16, 1, 2>(FIT_ARGS); });
-  if (t->l1_cta) simt::launch("k_fit_cta<2048,2,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * 2048 * sizeof(float), [&] { k_fit_cta<2048, 2, 3, 8, true>(FIT_ARGS); });
-  if (t->l2_pls && !t->l2_wide && !t->part_ilp)   // like pwpp_create: only the plain fused 4096-point shape has a PLS variant
-    simt::launch("k_fit_cta<4096,3,4,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8, true, false, true>(FIT_ARGS); });
-  if (t->l2_wide) simt::launch("k_fit_cta<5888,3,3,8,fuse>", pg, FIT_THREADS, (size_t) 3 * CLS_L2_WIDE_MAX * sizeof(float), [&] { k_fit_cta<CLS_L2_WIDE_MAX, 3, 3, 8, true>(FIT_ARGS); });
-  if (t->part_ilp) {   // PWPP_PART_ILP variants of the default shapes drain the queues first
-    simt::launch("k_fit_cta<8192,4,2,8,fuse,pilp>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true, true>(FIT_ARGS); });
-    simt::launch("k_fit_cta<4096,3,3,8,fuse,pilp>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true, true>(FIT_ARGS); });
-    simt::launch("k_fit_warp<false,2,2,pilp>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2, false, false, true>(FIT_ARGS); });
-    simt::launch("k_fit_warp<true,1,1,pilp>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2, false, false, true>(FIT_ARGS); });
-  }
-  // fuse_seed is the PWPP_FUSE_SEED bit mask: 1 = CTA kernels (L2, L3, X), 2 = warp kernels (M, L1); solve_call = PWPP_SOLVE_CALL
-  if (t->fuse_seed & 1) {
     simt::launch("k_fit_cta<8192,4,2,8,fuse>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true>(FIT_ARGS); });
-    simt::launch("k_fit_cta<4096,3,3,8,fuse>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true>(FIT_ARGS); });
+    simt::launch("k_fit_cta<4096,3,3,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true, true>(FIT_ARGS); });
+    simt::launch("k_fit_warp<false,2,2>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2>(FIT_ARGS); });
   }
-  if (t->fuse_seed & 2) {
-    simt::launch("k_fit_warp<false,2,2,fuse>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2, true>(FIT_ARGS); });
-    simt::launch("k_fit_warp<true,1,1,fuse>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2, true>(FIT_ARGS); });
-  } else if (t->solve_call) {
-    simt::launch("k_fit_warp<false,2,2,call>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2, false, true>(FIT_ARGS); });
-    simt::launch("k_fit_warp<true,1,1,call>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2, false, true>(FIT_ARGS); });
-  }
-  if (t->l3_nw == 16) simt::launch("k_fit_cta<8192,4,2,16>", pg, 512, sm_l3, [&] { k_fit_cta<8192, 4, 2, 16>(FIT_ARGS); });
-  else simt::launch("k_fit_cta<8192,4,2,8>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8>(FIT_ARGS); });
-  if (t->l2_nw == 16) simt::launch("k_fit_cta<4096,3,2,16>", pg, 512, sm_l2, [&] { k_fit_cta<4096, 3, 2, 16>(FIT_ARGS); });
-  else simt::launch("k_fit_cta<4096,3,4,8>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 4, 8>(FIT_ARGS); });
-  simt::launch("k_fit_warp<false,2,2>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2>(FIT_ARGS); });
   simt::launch("k_fit_warp<true,1,1>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2>(FIT_ARGS); });
   simt::launch("k_fit_resident<8,8,0>", pg, FIT_THREADS, 0, [&] { k_fit_resident<8, 8, 0, 2>(FIT_ARGS); });
-  }   // !group
-  if (t->x_kernel && t->x_fix) {
-    if (t->fuse_seed & 1) simt::launch("k_fit_big<16,1,fuse,fix>", pg, 512, 0, [&] { k_fit_big<16, 1, true, false, true>(FIT_ARGS); });
-    else simt::launch("k_fit_big<16,1,fix>", pg, 512, 0, [&] { k_fit_big<16, 1, false, false, true>(FIT_ARGS); });
-  }
-  if (t->x_kernel) {
-    if (t->x_nw == 32) { if (t->fuse_seed & 1) simt::launch("k_fit_big<32,1,fuse>", pg, 1024, 0, [&] { k_fit_big<32, 1, true>(FIT_ARGS); }); else simt::launch("k_fit_big<32,1>", pg, 1024, 0, [&] { k_fit_big<32, 1, false>(FIT_ARGS); }); }
-    else if (t->x_nw == 8) { if (t->fuse_seed & 1) simt::launch("k_fit_big<8,4,fuse>", pg, 256, 0, [&] { k_fit_big<8, 4, true>(FIT_ARGS); }); else simt::launch("k_fit_big<8,4>", pg, 256, 0, [&] { k_fit_big<8, 4, false>(FIT_ARGS); }); }
-    else { if (t->fuse_seed & 1) simt::launch("k_fit_big<16,2,fuse>", pg, 512, 0, [&] { k_fit_big<16, 2, true>(FIT_ARGS); }); else simt::launch("k_fit_big<16,2>", pg, 512, 0, [&] { k_fit_big<16, 2, false>(FIT_ARGS); }); }
-  }
-  simt::launch("k_fit_stream", pg, 128, 0, [&] { k_fit_stream(FIT_ARGS); });
+  simt::launch("k_fit_big<16,1,fuse>", pg, 512, 0, [&] { k_fit_big<16, 1, true>(FIT_ARGS); });
 #undef FIT_ARGS
   for (int c = 0; c < NUM_CLASSES; ++c)
     if (ctr[NUM_CLASSES + c] < ctr[c]) { std::fprintf(stderr, "simt_twin: class %d queue not drained (%d of %d)\n", c, ctr[NUM_CLASSES + c], ctr[c]); std::abort(); }

@@ -171,6 +171,7 @@ def test_index_lists_in_reference_order(kitti):
     assert compared >= len(frames) - 2
     # and back: bin order (ascending index inside a bin) gives the same sets
     eng.set_output_order(eng.ORDER_BIN)
+    eng.reset()
     eng.estimate_host(frames[:2])
     ref = O.Reference(stable_sort=True); ref.estimate(frames[0])
     assert np.array_equal(np.sort(ref.getGroundIndices()), np.sort(eng.ground_indices(0)))

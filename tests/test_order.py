@@ -18,10 +18,10 @@ def _lists_equal(ref, tw, what):
         assert a.shape == b.shape and np.array_equal(a, b), f"{what}: {name} differs (first at {np.nonzero(a[:len(b)] != b[:len(a)])[0][:3]})"
 
 
-@pytest.mark.parametrize("group", [0, 1])
-def test_fixture_lists_in_reference_order(kitti, group):
+@pytest.mark.parametrize("patch", [0, 1])
+def test_fixture_lists_in_reference_order(kitti, patch):
     for f in (0, 3):
-        ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1, group=group)
+        ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1, patch=patch)
         ref.estimate(kitti[f]); tw.estimate(kitti[f])
         _lists_equal(ref, tw, f"fixture {f}")
 
@@ -32,10 +32,10 @@ def test_rvpf_removals_come_first_in_iteration_order():
     rng = np.random.default_rng(11)
     wall = np.r_[np.c_[4 + rng.random(6000) * 0.05, rng.random(6000) * 0.6, -1.7 + rng.random(6000) * 2.0, rng.random(6000)],
                  np.c_[3 + rng.random(6000) * 4, rng.random(6000) * 0.6, -1.7 + rng.normal(0, 0.02, 6000), rng.random(6000)]].astype(np.float32)
-    for group in (0, 1):
-        ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1, group=group)
+    for patch in (0, 1):
+        ref, tw = O.Reference(stable_sort=True), SimtTwin(order=1, patch=patch)
         ref.estimate(wall); tw.estimate(wall)
-        _lists_equal(ref, tw, f"wall/group={group}")
+        _lists_equal(ref, tw, f"wall/patch={patch}")
 
 
 def test_other_parameter_set_and_synthetic_and_ties():

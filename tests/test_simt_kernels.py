@@ -70,28 +70,26 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(l2_nw=16, l3_nw=16), dict(scatter_pipe=1, hist_pipe=0), dict(fuse_seed=0), dict(fuse_seed=3), dict(solve_call=1), dict(emit_split=8), dict(part_ilp=1), dict(l2_wide=1), dict(l2_pls=1), dict(m_resident=1), dict(l1_cta=1), dict(m_half=1), dict(m_half=1, l1_cta=1, l2_wide=1)])
-def test_kernel_variants(kitti, opts):
-    """The A/B variants selectable through PWPP_* switches give the same result as the defaults."""
+@pytest.mark.parametrize("opts", [dict(front=0), dict(patch=1), dict(front=0, patch=1), dict(emit_split=8), dict(order=1)])
+def test_kernel_switches(kitti, opts):
+    """The remaining switches (PWPP_FRONT=0: the three stand-alone front-end kernels instead of the cluster kernel;
+    PWPP_FIT_PATCH=1: k_fit_patch for the patches above 512 points; the emit split; reference order) give the oracle's result."""
     a = kitti[3]
     orc, tw = O.Oracle(arith=O.ARITH_CANON64), SimtTwin(**opts)
     orc.estimate(a); tw.estimate(a)
-    assert _check(orc, tw, a, f"variant/{opts}") == 0
+    assert _check(orc, tw, a, f"switch/{opts}") == 0
 
 
-def test_persistent_front_end_is_identical(kitti):
-    """PWPP_FRONT: binning + scan + scatter as one persistent kernel over an ordered work list (pwpp_front.cuh), for several
-    pipeline depths W, with empty / one-point / ragged frames: bin ids, index lists and patch records identical to the
-    three stand-alone kernels."""
+def test_cluster_front_end_is_identical(kitti):
+    """k_front_cluster (one cluster of 8 CTAs per frame: TMA-staged tiles, histograms exchanged through distributed shared
+    memory) against the three stand-alone kernels: bin ids, index lists and patch records identical, for empty / one-point /
+    ragged frames (fewer tiles than CTAs) and under random interleavings of the cluster's CTAs."""
     import synth
     frames = [kitti[1], np.zeros((0, 4), np.float32), synth.make_frame(5, 1).numpy(), np.array([[5, 0, -1.7, 0.5]], np.float32), kitti[2][:50000],
-              synth.make_frame(5, 2).numpy()[:4096]]
-    a = SimtTwin(num_streams=len(frames)); a.estimate_multi(frames)
-    # (W, CTAs, concurrent): sequential CTAs check the list order; concurrent CTAs (all live at once, fibers of all of them
-    # interleaved) really wait for each other on the hist_done / scan_done counters
-    # seed != 0: the fibers of the concurrently live CTAs are interleaved at random instead of round-robin
-    for w, nc, conc, seed in ((1, 3, 0, 0), (5, 3, 0, 0), (1, 4, 1, 0), (2, 3, 1, 0), (20, 5, 1, 0), (1, 5, 1, 7), (3, 2, 1, 8), (2, 6, 1, 9)):
-        b = SimtTwin(num_streams=len(frames), front=1, front_w=w, persistent_ctas=nc, front_concurrent=conc)
+              synth.make_frame(5, 2).numpy()[:4096], kitti[3][:2049]]
+    a = SimtTwin(num_streams=len(frames), front=0); a.estimate_multi(frames)
+    for seed in (0, 7, 8):
+        b = SimtTwin(num_streams=len(frames), front=1)
         b.set_sched_seed(seed)
         try:
             b.estimate_multi(frames)
@@ -100,18 +98,8 @@ def test_persistent_front_end_is_identical(kitti):
         for f in range(len(frames)):
             a.select(f); b.select(f)
             assert np.array_equal(a.bin_ids(), b.bin_ids())
-            assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and np.array_equal(a.getNongroundIndices(), b.getNongroundIndices()), (w, f)
+            assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and np.array_equal(a.getNongroundIndices(), b.getNongroundIndices()), (seed, f)
             assert bytes(a.bin_results()) == bytes(b.bin_results())
-
-
-def test_fused_seed_rounds_are_bit_identical(kitti):
-    """PWPP_FUSE_SEED: the R-VPF and the R-GPF seed plane of a zone-0 patch from one selection and one pass. The fused
-    rounds accumulate in the same order as the two separate passes, so every patch record is bit-identical."""
-    for f in (1, 5):
-        a, b = SimtTwin(fuse_seed=0), SimtTwin(fuse_seed=3)
-        a.estimate(kitti[f]); b.estimate(kitti[f])
-        assert bytes(a.bin_results()) == bytes(b.bin_results())
-        assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and np.array_equal(a.getNongroundIndices(), b.getNongroundIndices())
 
 
 def _big_patch_cases():
@@ -127,9 +115,9 @@ def _big_patch_cases():
     }
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(fuse_seed=0), dict(x_nw=8, fuse_seed=3), dict(x_nw=32, emit_split=5), dict(x_kernel=0), dict(x_fix=1), dict(x_fix=1, fuse_seed=0)])
+@pytest.mark.parametrize("opts", [dict(), dict(emit_split=5), dict(order=1)])
 def test_big_patches(opts):
-    """Class X (more than 8192 points in one patch): k_fit_big in its CTA shapes and the one-warp fallback, including
+    """Class X (more than 8192 points in one patch): k_fit_big, including
     the tie-heavy selections that overflow the candidate buffer and an R-VPF wall removal in zone 0."""
     cases = _big_patch_cases()
     names = list(cases)
@@ -141,20 +129,18 @@ def test_big_patches(opts):
         assert _check(orc, tw, cases[k], f"big/{k}/{opts}") == 0
 
 
-def test_wide_l2_class_boundaries():
-    """PWPP_L2_WIDE: patches of 4097..5888 points move from the L3 to the L2 class (k_fit_cta<5888>); sizes on both sides of
-    every boundary give the same records as the default classes."""
+def test_patch_class_boundaries():
+    """Patch sizes on both sides of every class limit (64 / 512 / 2048 / 4096 / 8192) with both kernel sets."""
     rng = np.random.default_rng(2)
     mk = lambda n: np.c_[5 + rng.random(n) * 0.5, rng.random(n) * 0.5, -1.7 + rng.normal(0, 0.02, n), rng.random(n)].astype(np.float32)  # noqa: E731
-    frames = [mk(n) for n in (4096, 4097, 5000, 5888, 5889, 8192, 8193)]
-    a, b = SimtTwin(num_streams=len(frames)), SimtTwin(num_streams=len(frames), l2_wide=1, part_ilp=1)
-    a.estimate_multi(frames); b.estimate_multi(frames)
-    assert a.queue_sizes() != b.queue_sizes()
-    for f in range(len(frames)):
-        a.select(f); b.select(f)
-        assert np.array_equal(a.getGroundIndices(), b.getGroundIndices()) and bytes(a.bin_results()) == bytes(b.bin_results())
-        orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(frames[f])
-        assert _check(orc, b, frames[f], f"wide/{f}") == 0
+    frames = [mk(n) for n in (64, 65, 512, 513, 2048, 2049, 4096, 4097, 8192, 8193)]
+    for patch in (0, 1):
+        tw = SimtTwin(num_streams=len(frames), patch=patch)
+        tw.estimate_multi(frames)
+        for f in range(len(frames)):
+            tw.select(f)
+            orc = O.Oracle(arith=O.ARITH_CANON64); orc.estimate(frames[f])
+            assert _check(orc, tw, frames[f], f"boundary/{patch}/{f}") == 0
 
 
 def test_dense_frame():
@@ -184,7 +170,7 @@ def test_edge_cases():
                                      np.c_[3 + rng.random(3000) * 6, rng.random(3000) * 1.5, -1.7 + rng.normal(0, 0.02, 3000), rng.random(3000)]].astype(np.float32),
     }
     names = list(cases)
-    for opts in (dict(), dict(part_ilp=1, emit_split=3, fuse_seed=3)):
+    for opts in (dict(), dict(patch=1, emit_split=3, front=0)):
         tw = SimtTwin(num_streams=len(names), **opts)
         tw.estimate_multi([cases[k] for k in names])
         for f, k in enumerate(names):
@@ -215,8 +201,7 @@ def test_random_parameter_sets(kitti, seed):
     p.uprightness_thr = float(rng.choice([0.101, 0.5, 0.707, 0.95]))
     p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([1, 4, 8, 16, 32, 54, 64, 128, 200], 4)]
     p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 9, 4)]
-    opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 3, 8])), solve_call=int(rng.integers(0, 2)),
-                x_nw=int(rng.choice([8, 16, 32])), scatter_pipe=int(rng.integers(0, 2)), hist_pipe=int(rng.choice([0, 2])), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)), l2_pls=int(rng.integers(0, 2)), x_fix=int(rng.integers(0, 2)), m_resident=int(rng.integers(0, 2)), l1_cta=int(rng.integers(0, 2)), m_half=int(rng.integers(0, 2)))
+    opts = dict(emit_split=int(rng.choice([1, 3, 8])), front=int(rng.integers(0, 2)), patch=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
     pool = [kitti[0], kitti[4], synth.make_frame(7, 0).numpy()]
     orc, tw = O.Oracle(p, O.ARITH_CANON64), SimtTwin(p, **opts)
@@ -257,8 +242,7 @@ def test_mutated_inputs(kitti, seed):
         a[:, :3] *= np.float32(rng.choice([0.5, 2.0]))
     if rng.random() < 0.3:
         a = a[rng.permutation(len(a))]
-    opts = dict(fuse_seed=int(rng.integers(0, 4)), part_ilp=int(rng.integers(0, 2)), front=int(rng.integers(0, 2)), l2_wide=int(rng.integers(0, 2)),
-                m_half=int(rng.integers(0, 2)), x_fix=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 4])))
+    opts = dict(front=int(rng.integers(0, 2)), patch=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 4])))
     orc, ref, tw = O.Oracle(arith=O.ARITH_CANON64), O.Oracle(arith=O.ARITH_REF32), SimtTwin(**opts)
     orc.estimate(a); ref.estimate(a); tw.estimate(a)
     ids = orc.bin_ids()
