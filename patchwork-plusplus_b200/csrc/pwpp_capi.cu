@@ -325,7 +325,17 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   // left) overlaps the start of the next.
 #define FIT_ARGS ctx->d_sorted.p, ft, states, ctx->g, ctx->ap, nbp, bin_off, wq, ctx->d_part.p, fits
   const bool serial_fit = ctx->sw_serial_fit;   // PWPP_SERIAL_FIT: diagnostic switch
-  auto launch_fit = [&](int c, cudaStream_t st) { const FitLaunch& k = ctx->fit[c]; if (k.fn) { k.fn<<<k.grid, k.threads, k.smem, st>>>(FIT_ARGS); ++ctx->launches; } };
+  // persistent grids are sized for a full GPU; a small call (one frame per call is the reference's pattern) would launch hundreds
+  // of CTAs per class that find their queue empty and, worse, keep the six classes from running side by side: cap the grid
+  // by what the call can hold (a frame has at most a few hundred patches)
+  auto launch_fit = [&](int c, cudaStream_t st) {
+    const FitLaunch& k = ctx->fit[c];
+    if (!k.fn) return;
+    const long long cap = (long long) nframes * (k.threads <= 128 ? 96 : 48);
+    const int grid = (int) std::min<long long>(k.grid, std::max<long long>(1, cap));
+    k.fn<<<grid, k.threads, k.smem, st>>>(FIT_ARGS);
+    ++ctx->launches;
+  };
   if (prof || serial_fit) {
     static const int order[NUM_CLASSES] = {0, 4, 3, 2, 1, 5};   // stage slots: S, L3, L2, L1, M, X
     for (int q = 0; q < NUM_CLASSES; ++q) { launch_fit(order[q], s); STAGE_MARK(); }
@@ -346,7 +356,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   }
 #undef FIT_ARGS
   if (ctx->order_mode) {   // reference emission order inside every fitted patch (pwpp_order.cuh)
-    k_order<<<ctx->order_grid, ORD_THREADS, ORD_CAP * sizeof(unsigned long long), s>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
+    k_order<<<(int) std::min<long long>(ctx->order_grid, (long long) nframes * 64), ORD_THREADS, ORD_CAP * sizeof(unsigned long long), s>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
     ++ctx->launches;
   }
   int* d_ng = ctx->d_counts.p + f0;
@@ -362,7 +372,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     // a bin is copied by `split` warps: 1 for KITTI-sized frames (bins of a few thousand points), 16 for dense sensors whose
     // 20k..40k-point bins would otherwise be left to one warp each (r02: dense k_emit 1.15 -> 0.14 ms; KITTI 0.33 -> 0.94 ms at 16)
     const long long mean_pts = (ctx->pt_off[f0 + nf] - ctx->pt_off[f0]) / std::max(nf, 1);
-    const int split = ctx->sw_emit_split > 0 ? ctx->sw_emit_split : (mean_pts > 400000 ? 16 : 1);
+    const int split = ctx->sw_emit_split > 0 ? ctx->sw_emit_split : (mean_pts > 400000 ? 16 : (nframes <= 8 ? 4 : 1));
     dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, split);
     if (split > 1) k_emit<true><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     else k_emit<false><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);

@@ -23,11 +23,11 @@ namespace pwpp {
 
 constexpr int FC_CS = 8;                 // CTAs per cluster (portable maximum)
 constexpr int FC_THREADS = 256;
-constexpr int FC_TILE = 2048;            // points per tile: 32 KB, two buffers in flight
-constexpr int FC_ROWS = FC_TILE / FC_THREADS;   // 32-point rows per warp and tile: 8
+constexpr int FC_TILE = 1024;            // points per tile: 16 KB, two buffers in flight (48 KB of shared memory per CTA in all: 4 CTAs per SM)
+constexpr int FC_ROWS = FC_TILE / FC_THREADS;   // 32-point rows per warp and tile: 4
 
 __host__ __device__ inline size_t front_cluster_smem_bytes(int nbp) {
-  return (size_t) 2 * FC_TILE * sizeof(float4) + (size_t) (2 + FC_THREADS / 32) * nbp * sizeof(unsigned) + (size_t) (nbp + 1) * sizeof(int) + 16 + 64 + 3 * NUM_CLASSES * sizeof(int);
+  return (size_t) 2 * FC_TILE * sizeof(float4) + (size_t) 2 * nbp * sizeof(unsigned) + (size_t) (1 + FC_THREADS / 32) * nbp * sizeof(unsigned short) + (size_t) (nbp + 1) * sizeof(int) + 16 + 64 + 3 * NUM_CLASSES * sizeof(int);
 }
 
 template <bool FAST, int L2MAX>
@@ -35,15 +35,16 @@ __global__ void
 #if !defined(PWPP_SIMT_EMU)
 __cluster_dims__(FC_CS, 1, 1)
 #endif
-__launch_bounds__(FC_THREADS, 2) k_front_cluster(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
+__launch_bounds__(FC_THREADS, 4) k_front_cluster(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
                                                   int has_intensity, int nbp, int nbins, unsigned short* __restrict__ bin_ids, int* __restrict__ bin_off, WorkQueues wq,
                                                   BinFit* __restrict__ fits, float4* __restrict__ sorted) {
   PW_DYN_SHARED(unsigned char, s_raw);
   float4* s_tile = reinterpret_cast<float4*>(s_raw);                                   // [2][FC_TILE]
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_raw + (size_t) 2 * FC_TILE * 16);   // [nbp] this CTA's bin counts (read by the whole cluster)
   unsigned* s_base = s_hist + nbp;                                                     // [nbp] where this CTA's next point of a bin goes
-  unsigned* s_wcnt = s_base + nbp;                                                     // [8][nbp] per-warp counts / positions of a tile
-  int* s_scan = reinterpret_cast<int*>(s_wcnt + (FC_THREADS / 32) * nbp);              // [nbp + 1]
+  unsigned short* s_wcnt = reinterpret_cast<unsigned short*>(s_base + nbp);            // [8][nbp] per-warp counts, then positions inside the tile's share of a bin
+  unsigned short* s_tcnt = s_wcnt + (FC_THREADS / 32) * nbp;                           // [nbp] points of the current tile per bin (nbp is a multiple of 32: 4-byte aligned end)
+  int* s_scan = reinterpret_cast<int*>(s_tcnt + nbp);                                  // [nbp + 1]
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(s_scan) + (((size_t) (nbp + 1) * 4 + 15) & ~(size_t) 15));   // [2] (+ 48 B pad)
   int* s_cls = reinterpret_cast<int*>(s_bar + 8);                                      // [3][NUM_CLASSES]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -190,25 +191,25 @@ __launch_bounds__(FC_THREADS, 2) k_front_cluster(const float4* __restrict__ pts,
     int bins[FC_ROWS];
 #pragma unroll
     for (int r = 0; r < FC_ROWS; ++r) { const int i = base + r * 32 + lane; bins[r] = (i < n) ? (int) bin_ids[p0 + i] : -1; }   // written by this very thread in pass 1
-    for (int b = tid; b < (FC_THREADS / 32) * nbp; b += FC_THREADS) s_wcnt[b] = 0;
+    for (int b = tid; b < (FC_THREADS / 32) * nbp / 2; b += FC_THREADS) reinterpret_cast<unsigned*>(s_wcnt)[b] = 0u;
     __syncthreads();
-    unsigned* my = s_wcnt + w * nbp;
+    unsigned short* my = s_wcnt + w * nbp;
 #pragma unroll
     for (int r = 0; r < FC_ROWS; ++r) {
       const int bin = bins[r];
       const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
       if (bin >= 0) {
         const unsigned peers = __match_any_sync(act, bin);
-        if ((peers & lanemask_lt()) == 0) my[bin] += __popc(peers);   // only this warp writes its row
+        if ((peers & lanemask_lt()) == 0) my[bin] = (unsigned short) (my[bin] + __popc(peers));   // only this warp writes its row
       }
       __syncwarp();
     }
     __syncthreads();
-    for (int b = tid; b < nbp; b += FC_THREADS) {   // exclusive prefix over the 8 warps from the CTA's running position
-      unsigned run = s_base[b];
+    for (int b = tid; b < nbp; b += FC_THREADS) {   // exclusive prefix over the 8 warps (positions relative to the CTA's running base of the bin)
+      unsigned run = 0;
 #pragma unroll
-      for (int ww = 0; ww < FC_THREADS / 32; ++ww) { const unsigned v = s_wcnt[ww * nbp + b]; s_wcnt[ww * nbp + b] = run; run += v; }
-      s_base[b] = run;
+      for (int ww = 0; ww < FC_THREADS / 32; ++ww) { const unsigned v = s_wcnt[ww * nbp + b]; s_wcnt[ww * nbp + b] = (unsigned short) run; run += v; }
+      s_tcnt[b] = (unsigned short) run;
     }
     wait_tile(t, buf);
     __syncthreads();
@@ -221,16 +222,17 @@ __launch_bounds__(FC_THREADS, 2) k_front_cluster(const float4* __restrict__ pts,
       const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
       if (bin >= 0) {
         const unsigned peers = __match_any_sync(act, bin);
-        const unsigned pos = my[bin] + __popc(peers & lanemask_lt());
+        const unsigned pos = s_base[bin] + my[bin] + __popc(peers & lanemask_lt());
         float4 p = tp[li];
         p.w = __int_as_float(i);
         out[pos] = p;
         __syncwarp(peers);
-        if ((peers & lanemask_lt()) == 0) my[bin] += __popc(peers);
+        if ((peers & lanemask_lt()) == 0) my[bin] = (unsigned short) (my[bin] + __popc(peers));
       }
       __syncwarp();
     }
     __syncthreads();
+    for (int b = tid; b < nbp; b += FC_THREADS) s_base[b] += s_tcnt[b];   // the CTA's running base moves past this tile (ordered before the next tile's placement by its barriers)
   }
 }
 

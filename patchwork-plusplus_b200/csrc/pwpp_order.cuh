@@ -20,7 +20,7 @@
 namespace pwpp {
 
 constexpr int ORD_CAP = 8192;       // keys in shared memory (64 KB)
-constexpr int ORD_THREADS = 256;
+constexpr int ORD_THREADS = 512;
 
 __device__ __forceinline__ unsigned long long order_sort_key(float z, unsigned char label, unsigned pos) {
   const unsigned grp = label == PW_LABEL_GROUND ? 0u : (label == PW_LABEL_REJECT ? 9u : (unsigned) label);
@@ -56,18 +56,26 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict_
     if (n <= ORD_CAP) {
       for (int i = tid; i < n; i += ORD_THREADS) s_key[i] = order_sort_key(P[i].z, L[i], (unsigned) i);
       __syncthreads();
-      // bitonic network, every compare-exchange ascending: merge step k first pairs i with i ^ (k - 1), then i ^ j for j = k/4 .. 1
-      for (int k = 2; (k >> 1) < n; k <<= 1) {
-        for (int j = k - 1; j > 0; j = (j == k - 1) ? (k >> 2) : (j >> 1)) {
-          for (int i = tid; i < n; i += ORD_THREADS) {
-            const int l = i ^ j;
-            if (l > i && l < n) {
-              const unsigned long long a = s_key[i], b = s_key[l];
-              if (a > b) { s_key[i] = b; s_key[l] = a; }
-            }
-          }
+      // bitonic network, every compare-exchange ascending: merge step k first pairs i with i ^ (k - 1) (i in the lower half of its
+      // k-block), then i with i + j for j = k/4 .. 1. One loop iteration per PAIR; four pairs in flight per thread.
+      int n2 = 2;
+      while (n2 < n) n2 <<= 1;
+      const int npairs = n2 >> 1;
+      auto cex = [&](int i, int l) {
+        if (l < n) {
+          const unsigned long long a = s_key[i], b = s_key[l];
+          if (a > b) { s_key[i] = b; s_key[l] = a; }
+        }
+      };
+      for (int k = 2, lk = 1; k <= n2; k <<= 1, ++lk) {
+        const int hk = k >> 1;
+#pragma unroll 4
+        for (int q = tid; q < npairs; q += ORD_THREADS) { const int i = ((q >> (lk - 1)) << lk) | (q & (hk - 1)); cex(i, i ^ (k - 1)); }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll 4
+          for (int q = tid; q < npairs; q += ORD_THREADS) { const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)); cex(i, i | j); }
           __syncthreads();
-          if (j == 0) break;
         }
       }
       for (int i = tid; i < n; i += ORD_THREADS) out[i] = __float_as_int(P[(int) (s_key[i] & 0xffffffull)].w);

@@ -41,7 +41,7 @@ struct DeviceView {   // what the *Device getters return
     py::dict d;
     d["shape"] = py::make_tuple(n);
     d["typestr"] = "<i4";
-    d["data"] = py::make_tuple(ptr, true);
+    d["data"] = py::make_tuple(ptr, false);   // (torch refuses read-only device arrays; the lists are overwritten by the next call anyway)
     d["version"] = 3;
     d["strides"] = py::none();
     return d;
