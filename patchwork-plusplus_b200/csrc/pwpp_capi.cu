@@ -356,14 +356,14 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   }
 #undef FIT_ARGS
   if (ctx->order_mode) {   // reference emission order inside every fitted patch (pwpp_order.cuh)
-    k_order<<<(int) std::min<long long>(ctx->order_grid, (long long) nframes * 64), ORD_THREADS, ORD_CAP * sizeof(unsigned long long), s>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
+    k_order<<<(int) std::min<long long>(ctx->order_grid, (long long) nframes * 512), ORD_THREADS, ORD_CAP * sizeof(unsigned long long), s>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
     ++ctx->launches;
   }
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
   {
-    const size_t gle_smem = (size_t) 6 * ctx->max_sectors * sizeof(double) + (size_t) 2 * ctx->max_sectors * sizeof(int);
+    const size_t gle_smem = gle_smem_bytes(ctx->max_sectors);
     k_gle<<<nframes, 32, gle_smem, s>>>(ft, states, hist, ctx->hcap, ctx->g, ctx->ap, nbp, ctx->max_sectors, bin_off, fits, segs, d_ng, d_np, centers, normals, d_nd);
     ++ctx->launches;
   }
@@ -615,7 +615,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_order, ORD_THREADS, ORD_CAP * sizeof(unsigned long long)));
       ctx->order_grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
-    const size_t gle_smem = (size_t) 6 * max_sectors * sizeof(double) + (size_t) 2 * max_sectors * sizeof(int);
+    const size_t gle_smem = gle_smem_bytes(max_sectors);
     if (gle_smem > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_gle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gle_smem));
   }
   {

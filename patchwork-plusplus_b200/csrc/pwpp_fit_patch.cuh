@@ -22,36 +22,36 @@
 
 namespace pwpp {
 
-constexpr int GRP_CBUF = 128;   // candidates the exact LPR selection handles (4 keys per lane)
+constexpr int FP_CAND = 128;   // candidates the exact LPR selection handles (4 keys per lane)
 
-// exact selection among cc (<= GRP_CBUF) candidate keys in cbuf: mean of the `target` smallest (S:99-103) by RANKING: a
+// exact selection among cc (<= FP_CAND) candidate keys in cbuf: mean of the `target` smallest (S:99-103) by RANKING: a
 // candidate's rank = number of candidates before it in (key, position) order; all compares are independent (no serial
 // bisection). The sum of <= 32 floats in double is exact, so the result does not depend on the candidates' order. Uniform.
-__device__ __forceinline__ double grp_rank_mean(const unsigned* cbuf, int cc, int target) {
+__device__ __forceinline__ double rank_mean(const unsigned* cbuf, int cc, int target) {
   const int lane = lane_id();
-  unsigned ck[GRP_CBUF / 32];
-  int rank[GRP_CBUF / 32];
+  unsigned ck[FP_CAND / 32];
+  int rank[FP_CAND / 32];
   const int nq = (cc + 31) >> 5;
 #pragma unroll
-  for (int q = 0; q < GRP_CBUF / 32; ++q) { const int i = lane + 32 * q; ck[q] = i < cc ? cbuf[i] : 0xffffffffu; rank[q] = 0; }
+  for (int q = 0; q < FP_CAND / 32; ++q) { const int i = lane + 32 * q; ck[q] = i < cc ? cbuf[i] : 0xffffffffu; rank[q] = 0; }
   // candidates are broadcast 8 at a time (independent shared-memory reads in flight); entries past cc hold 0xffffffff (or
   // stale keys) and are masked by the position test
   for (int j0 = 0; j0 < cc; j0 += 8) {
     unsigned v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = cbuf[(j0 + u) < GRP_CBUF ? (j0 + u) : (GRP_CBUF - 1)];
+    for (int u = 0; u < 8; ++u) v[u] = cbuf[(j0 + u) < FP_CAND ? (j0 + u) : (FP_CAND - 1)];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int j = j0 + u;
       if (j < cc) {   // uniform
 #pragma unroll
-        for (int q = 0; q < GRP_CBUF / 32; ++q) { if (q >= nq) break; rank[q] += (v[u] < ck[q] || (v[u] == ck[q] && j < lane + 32 * q)) ? 1 : 0; }
+        for (int q = 0; q < FP_CAND / 32; ++q) { if (q >= nq) break; rank[q] += (v[u] < ck[q] || (v[u] == ck[q] && j < lane + 32 * q)) ? 1 : 0; }
       }
     }
   }
   double ps = 0.0;
 #pragma unroll
-  for (int q = 0; q < GRP_CBUF / 32; ++q) if (lane + 32 * q < cc && rank[q] < target) ps += (double) key_to_float(ck[q]);
+  for (int q = 0; q < FP_CAND / 32; ++q) if (lane + 32 * q < cc && rank[q] < target) ps += (double) key_to_float(ck[q]);
   ps = warp_sum(ps);
   return ps / (double) target;
 }
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
   __shared__ unsigned s_min[NT];            // per-thread minimum key of the LPR candidates
   __shared__ int s_tile[2][FP_SL * NW + 1];   // partition: ground / non-ground count of every (slot, warp) tile, then their exclusive prefix
   __shared__ int s_nv[NW];
-  __shared__ unsigned s_cand[GRP_CBUF];
+  __shared__ unsigned s_cand[FP_CAND];
   __shared__ int s_cc;
   __shared__ double s_plane[10];         // mean[3] normal[3] sv[3] d
   __shared__ double s_tot[10];           // running sums of the R-GPF phase + count
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
         for (int k = 0; k < FP_SL; ++k) {
           if ((smask >> k) & 1u) {
             const unsigned key = order_key(pz[k]);
-            if (key <= T) { const int pos = atomicAdd(&s_cc, 1); if (pos < GRP_CBUF) s_cand[pos] = key; }
+            if (key <= T) { const int pos = atomicAdd(&s_cc, 1); if (pos < FP_CAND) s_cand[pos] = key; }
           }
         }
         PW_EV(13);
@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_patch(const float4* __res
 #endif
         double lpr = 0.0;   // S:99-103 with no candidate: lpr_height stays 0
         if (target > 0) {
-          if (cc <= GRP_CBUF) lpr = grp_rank_mean(s_cand, cc, target);   // every warp, redundantly: no third barrier
+          if (cc <= FP_CAND) lpr = rank_mean(s_cand, cc, target);   // every warp, redundantly: no third barrier
           else {
-            // rare: num_lpr > 32 or more than GRP_CBUF points tie below the bound: CTA-wide bisection on the order keys
+            // rare: num_lpr > 32 or more than FP_CAND points tie below the bound: CTA-wide bisection on the order keys
 #if defined(PWPP_SIMT_EMU) && defined(PWPP_DEBUG_FALLBACK)
             if (tid == 0) std::fprintf(stderr, "fallback: n=%d cc=%d target=%d T=%08x nvalid=%d\n", n, cc, target, T, nvalid);
 #endif

@@ -7,13 +7,14 @@
 // k_scatter (pwpp_kernels.cuh), which remain as the PWPP_FRONT=0 path; this kernel removes what made them expensive:
 //   * the three kernels communicated through global memory (per-chunk histograms and scatter bases: chist / cbase) and
 //     each streamed the whole batch, so the cloud was read from HBM twice (r01: 49 B/point of DRAM traffic, 1.54 ms);
-//   * here the FC_CS CTAs of a cluster split one frame into slices. Pass 1: every CTA bins its slice tile by tile — tiles
-//     arrive through the TMA engine (cp.async.bulk global -> shared, mbarrier completion, double buffered: SASS UBLKCP) —
-//     and keeps its histogram in shared memory. After a cluster barrier every CTA reads the other CTAs' histograms through
-//     DISTRIBUTED SHARED MEMORY (cluster.map_shared_rank), scans the bins and knows where its points of every bin go;
-//     rank 0 also writes the bin offsets and fills the fit work queues. Pass 2: the CTA streams its slice again — 2 MB of a
-//     frame read a few microseconds earlier by the same cluster: L2 hits — and scatters. HBM sees the cloud once (16 B/pt in,
-//     16 B/pt out for the re-laid-out copy, 2 + 2 B/pt of bin ids that mostly stay in L2).
+//   * here the 8 CTAs (64 warps) of a cluster split one frame into 64 contiguous slices. Pass 1: every warp bins its slice
+//     chunk by chunk — chunks arrive through the TMA engine (cp.async.bulk global -> shared, mbarrier completion, two
+//     buffers per warp: SASS UBLKCP) — and counts into its own histogram row in shared memory. After a cluster barrier every
+//     CTA reads the other CTAs' histograms through DISTRIBUTED SHARED MEMORY (cluster.map_shared_rank), scans the bins and
+//     turns every warp's counts into the warp's first free position of every bin; rank 0 also writes the bin offsets and
+//     fills the fit work queues. Pass 2: the warp streams its slice again — 2 MB of a frame read a few microseconds earlier
+//     by the same cluster: L2 hits — and scatters. No block barrier and no atomic inside either pass. HBM sees the cloud
+//     once (16 B/pt in, 16 B/pt out for the re-laid-out copy, 2 + 2 B/pt of bin ids that mostly stay in L2).
 // The bin ids still go to global memory (pwpp_copy_bin_ids, and frames of any size: a dense frame's slice does not fit on chip).
 #pragma once
 #include "pwpp_common.cuh"
@@ -23,13 +24,23 @@ namespace pwpp {
 
 constexpr int FC_CS = 8;                 // CTAs per cluster (portable maximum)
 constexpr int FC_THREADS = 256;
-constexpr int FC_TILE = 1024;            // points per tile: 16 KB, two buffers in flight (48 KB of shared memory per CTA in all: 4 CTAs per SM)
-constexpr int FC_ROWS = FC_TILE / FC_THREADS;   // 32-point rows per warp and tile: 4
+constexpr int FC_WARPS = FC_THREADS / 32;
+constexpr int FC_ROWS = 4;               // 32-point rows per chunk
+constexpr int FC_CHUNK = FC_ROWS * 32;   // points per TMA chunk of one warp: 2 KB, two buffers per warp in flight
 
 __host__ __device__ inline size_t front_cluster_smem_bytes(int nbp) {
-  return (size_t) 2 * FC_TILE * sizeof(float4) + (size_t) 2 * nbp * sizeof(unsigned) + (size_t) (1 + FC_THREADS / 32) * nbp * sizeof(unsigned short) + (size_t) (nbp + 1) * sizeof(int) + 16 + 64 + 3 * NUM_CLASSES * sizeof(int);
+  // tiles [FC_WARPS][2][FC_CHUNK] float4 | per-warp counts, later bases [FC_WARPS][nbp] u32 | CTA histogram [nbp] u32 | scan [nbp + 1] i32 (padded to
+  // 16 B) | mbarriers [FC_WARPS][2] u64 | class counters [3][NUM_CLASSES] i32
+  return (size_t) FC_WARPS * 2 * FC_CHUNK * sizeof(float4) + (size_t) (FC_WARPS + 1) * nbp * sizeof(unsigned) + ((((size_t) nbp + 1) * sizeof(int) + 15) & ~(size_t) 15) +
+         (size_t) FC_WARPS * 2 * sizeof(unsigned long long) + 3 * NUM_CLASSES * sizeof(int);
 }
 
+// The 64 warps of a cluster split the frame's 32-point rows into 64 CONTIGUOUS slices in (CTA rank, warp) order; a warp walks its
+// slice twice, chunk by chunk, and never meets a block barrier while it streams: its chunks arrive in its own two TMA buffers
+// (its own mbarriers), it counts into its own histogram row (no atomics: one lane per distinct bin of a row adds), and after the
+// scan that row holds the warp's first free position of every bin, which pass 2 advances the same way. A point's position is
+// (points of the bin in lower slices) + (points of the bin earlier in this slice) + (lower lanes of the row with the same bin):
+// ascending point index inside a bin, as k_scatter produces.
 template <bool FAST, int L2MAX>
 __global__ void
 #if !defined(PWPP_SIMT_EMU)
@@ -39,85 +50,92 @@ __launch_bounds__(FC_THREADS, 4) k_front_cluster(const float4* __restrict__ pts,
                                                   int has_intensity, int nbp, int nbins, unsigned short* __restrict__ bin_ids, int* __restrict__ bin_off, WorkQueues wq,
                                                   BinFit* __restrict__ fits, float4* __restrict__ sorted) {
   PW_DYN_SHARED(unsigned char, s_raw);
-  float4* s_tile = reinterpret_cast<float4*>(s_raw);                                   // [2][FC_TILE]
-  unsigned* s_hist = reinterpret_cast<unsigned*>(s_raw + (size_t) 2 * FC_TILE * 16);   // [nbp] this CTA's bin counts (read by the whole cluster)
-  unsigned* s_base = s_hist + nbp;                                                     // [nbp] where this CTA's next point of a bin goes
-  unsigned short* s_wcnt = reinterpret_cast<unsigned short*>(s_base + nbp);            // [8][nbp] per-warp counts, then positions inside the tile's share of a bin
-  unsigned short* s_tcnt = s_wcnt + (FC_THREADS / 32) * nbp;                           // [nbp] points of the current tile per bin (nbp is a multiple of 32: 4-byte aligned end)
-  int* s_scan = reinterpret_cast<int*>(s_tcnt + nbp);                                  // [nbp + 1]
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(s_scan) + (((size_t) (nbp + 1) * 4 + 15) & ~(size_t) 15));   // [2] (+ 48 B pad)
-  int* s_cls = reinterpret_cast<int*>(s_bar + 8);                                      // [3][NUM_CLASSES]
+  float4* s_tile = reinterpret_cast<float4*>(s_raw);                                              // [FC_WARPS][2][FC_CHUNK]
+  unsigned* s_wb = reinterpret_cast<unsigned*>(s_raw + (size_t) FC_WARPS * 2 * FC_CHUNK * 16);    // [FC_WARPS][nbp] counts of a warp's slice, then its bases
+  unsigned* s_hist = s_wb + (size_t) FC_WARPS * nbp;                                              // [nbp] this CTA's bin counts (read by the whole cluster)
+  int* s_scan = reinterpret_cast<int*>(s_hist + nbp);                                             // [nbp + 1]
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(s_scan) + ((((size_t) nbp + 1) * 4 + 15) & ~(size_t) 15));   // [FC_WARPS][2]
+  int* s_cls = reinterpret_cast<int*>(s_bar + FC_WARPS * 2);                                      // [3][NUM_CLASSES]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int f = blockIdx.y;
   const int rank = (int) pw_cluster_rank();
   const long long p0 = ft.pt_off[f];
   const int n = (int) (ft.pt_off[f + 1] - p0);
-  const int ntiles = (n + FC_TILE - 1) / FC_TILE;
-  const int t0 = (int) ((long long) ntiles * rank / FC_CS), t1 = (int) ((long long) ntiles * (rank + 1) / FC_CS);   // this CTA's tiles
+  const int nrows = (n + 31) >> 5;
+  const int gw = rank * FC_WARPS + w;                                                             // slice index in the frame
+  const int i0 = (int) ((long long) nrows * gw / (FC_CS * FC_WARPS)) << 5;                        // this warp's points [i0, i1)
+  const int i1 = min(n, (int) ((long long) nrows * (gw + 1) / (FC_CS * FC_WARPS)) << 5);
   const float4* fp = pts + p0;
   const double sensor_height = states[f].sensor_height;
   const bool rnr_on = ap.enable_RNR && has_intensity;  // S:161, S:379-382
+  unsigned* my = s_wb + (size_t) w * nbp;
+  float4* my_tile = s_tile + (size_t) w * 2 * FC_CHUNK;
+  unsigned long long* my_bar = s_bar + w * 2;
 
-  for (int b = tid; b < nbp; b += FC_THREADS) s_hist[b] = 0;
+  for (int b = tid; b < FC_WARPS * nbp; b += FC_THREADS) s_wb[b] = 0u;
 #if !defined(PWPP_SIMT_EMU)
-  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (lane == 0) { mbar_init(&my_bar[0], 1); mbar_init(&my_bar[1], 1); }
+  if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
   __syncthreads();
-  unsigned ph[2] = {0u, 0u};   // mbarrier phase of each buffer
+  unsigned ph = 0u;   // bit b: mbarrier phase of buffer b
   (void) ph;
-  auto issue = [&](int t, int buf) {   // thread 0: tile t -> buffer buf
+  auto issue = [&](int c0, int buf) {   // lane 0: points [c0, c0 + FC_CHUNK) of the slice -> buffer buf
 #if !defined(PWPP_SIMT_EMU)
-    const int cnt = min(FC_TILE, n - t * FC_TILE);
+    const int cnt = min(FC_CHUNK, i1 - c0);
     fence_proxy_async();
-    mbar_expect_tx(&s_bar[buf], (unsigned) cnt * 16u);
-    bulk_g2s(s_tile + buf * FC_TILE, fp + (size_t) t * FC_TILE, (unsigned) cnt * 16u, &s_bar[buf]);
+    mbar_expect_tx(&my_bar[buf], (unsigned) cnt * 16u);
+    bulk_g2s(my_tile + buf * FC_CHUNK, fp + c0, (unsigned) cnt * 16u, &my_bar[buf]);
 #else
-    (void) t; (void) buf;
+    (void) c0; (void) buf;
 #endif
   };
-  auto wait_tile = [&](int t, int buf) {
+  auto wait_chunk = [&](int c0, int buf) {
 #if !defined(PWPP_SIMT_EMU)
-    (void) t;
-    mbar_wait(&s_bar[buf], ph[buf] & 1u);
-    ++ph[buf];
+    (void) c0;
+    mbar_wait(&my_bar[buf], (ph >> buf) & 1u);
+    ph ^= 1u << buf;
 #else
-    const int cnt = min(FC_TILE, n - t * FC_TILE);
-    for (int i = tid; i < cnt; i += FC_THREADS) s_tile[buf * FC_TILE + i] = fp[(size_t) t * FC_TILE + i];
-    __syncthreads();
+    for (int i = c0 + lane; i < min(c0 + FC_CHUNK, i1); i += 32) my_tile[buf * FC_CHUNK + (i - c0)] = fp[i];
+    __syncwarp();
 #endif
   };
 
-  // ---------------- pass 1: bin ids + this CTA's histogram ----------------
-  if (tid == 0 && t0 < t1) issue(t0, 0);
-  for (int t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
-    if (tid == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);   // (every thread left that buffer at the barrier that ended tile t - 1)
-    wait_tile(t, buf);
-    const float4* tp = s_tile + buf * FC_TILE;
-    const int base = t * FC_TILE + w * (FC_ROWS * 32);
+  // ---------------- pass 1: bin ids + this warp's histogram ----------------
+  if (lane == 0 && i0 < i1) issue(i0, 0);
+  for (int c0 = i0, buf = 0; c0 < i1; c0 += FC_CHUNK, buf ^= 1) {
+    if (lane == 0 && c0 + FC_CHUNK < i1) issue(c0 + FC_CHUNK, buf ^ 1);   // (the warp left that buffer at the __syncwarp that ended the previous chunk)
+    wait_chunk(c0, buf);
+    const float4* tp = my_tile + buf * FC_CHUNK;
 #pragma unroll 2
     for (int r = 0; r < FC_ROWS; ++r) {
-      const int li = w * (FC_ROWS * 32) + r * 32 + lane;   // index inside the tile
-      const int i = base + r * 32 + lane;                  // index inside the frame
+      const int i = c0 + r * 32 + lane;
       int bin = -1;
-      if (i < n) {
-        const float4 p = tp[li];
+      if (i < i1) {
+        const float4 p = tp[r * 32 + lane];
         if (rnr_on && rnr_hit(p.x, p.y, p.z, p.w, sensor_height, ap)) bin = PW_BIN_RNR(g.nbins);
         else if (p.z == FLT_MIN) bin = PW_BIN_DROP(g.nbins);  // S:591
         else bin = FAST ? bin_of_point(p.x, p.y, p.z, g) : bin_of_point_exact(p.x, p.y, p.z, g);
         bin_ids[p0 + i] = (unsigned short) bin;
       }
       const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
-      if (bin >= 0) {   // warp-aggregated histogram update: one shared atomic per distinct bin in the row
+      if (bin >= 0) {   // one lane per distinct bin of the row adds the row's count
         const unsigned peers = __match_any_sync(act, bin);
-        if ((peers & lanemask_lt()) == 0) atomicAdd(&s_hist[bin], __popc(peers));
+        if ((peers & lanemask_lt()) == 0) my[bin] += (unsigned) __popc(peers);
       }
+      __syncwarp();
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  for (int b = tid; b < nbp; b += FC_THREADS) {
+    unsigned t = 0;
+#pragma unroll
+    for (int ww = 0; ww < FC_WARPS; ++ww) t += s_wb[ww * nbp + b];
+    s_hist[b] = t;
   }
   pw_cluster_sync();   // every histogram of the frame is complete and visible cluster-wide
 
-  // ---------------- scan: totals over the cluster, bin offsets, this CTA's bases ----------------
+  // ---------------- scan: totals over the cluster, bin offsets, every warp's bases ----------------
   for (int b = tid; b < nbp; b += FC_THREADS) {
     unsigned tot = 0, before = 0;
 #pragma unroll
@@ -127,7 +145,7 @@ __launch_bounds__(FC_THREADS, 4) k_front_cluster(const float4* __restrict__ pts,
       tot += h;
     }
     s_scan[b] = (int) tot;
-    s_base[b] = before;
+    reinterpret_cast<unsigned*>(s_tile)[b] = before;   // the tile buffers are idle between the passes: [nbp] "points of the bin in lower CTAs"
   }
   __syncthreads();
   if (tid < 32) {   // exclusive scan over nbp (<= 4096) bins by warp 0
@@ -144,8 +162,12 @@ __launch_bounds__(FC_THREADS, 4) k_front_cluster(const float4* __restrict__ pts,
     if (tid == 0) s_scan[nbp] = carry;
   }
   __syncthreads();
-  for (int b = tid; b < nbp; b += FC_THREADS) s_base[b] += (unsigned) s_scan[b];
-  pw_cluster_sync();   // nobody reads a remote histogram after this point (a CTA may exit before its neighbours)
+  for (int b = tid; b < nbp; b += FC_THREADS) {   // counts -> first free position of every warp
+    unsigned run = (unsigned) s_scan[b] + reinterpret_cast<unsigned*>(s_tile)[b];
+#pragma unroll
+    for (int ww = 0; ww < FC_WARPS; ++ww) { const unsigned v = s_wb[ww * nbp + b]; s_wb[ww * nbp + b] = run; run += v; }
+  }
+  pw_cluster_sync();   // nobody reads a remote histogram after this point (a CTA may exit before its neighbours); also orders the reuse of the tile buffers
   if (rank == 0) {
     // what k_bin_scan leaves for the later stages: bin offsets, the fit work queues (S:191: patches below num_min_pts are
     // not fitted), the records of the patches that will not be fitted
@@ -177,62 +199,32 @@ __launch_bounds__(FC_THREADS, 4) k_front_cluster(const float4* __restrict__ pts,
       }
     }
   }
-  __syncthreads();
 
-  // ---------------- pass 2: stable scatter of this CTA's slice ----------------
-  // position of a point = s_base[bin] (first free slot of this CTA for the bin) + points of the bin in lower warps of the
-  // tile + earlier rows of this warp + lower lanes of the row
+  // ---------------- pass 2: stable scatter of this warp's slice ----------------
   float4* out = sorted + p0;
-  if (tid == 0 && t0 < t1) issue(t0, 0);
-  for (int t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
-    if (tid == 0 && t + 1 < t1) issue(t + 1, buf ^ 1);
-    const int base = t * FC_TILE + w * (FC_ROWS * 32);
+  if (lane == 0 && i0 < i1) issue(i0, 0);
+  for (int c0 = i0, buf = 0; c0 < i1; c0 += FC_CHUNK, buf ^= 1) {
+    if (lane == 0 && c0 + FC_CHUNK < i1) issue(c0 + FC_CHUNK, buf ^ 1);
     int bins[FC_ROWS];
 #pragma unroll
-    for (int r = 0; r < FC_ROWS; ++r) { const int i = base + r * 32 + lane; bins[r] = (i < n) ? (int) bin_ids[p0 + i] : -1; }   // written by this very thread in pass 1
-    for (int b = tid; b < (FC_THREADS / 32) * nbp / 2; b += FC_THREADS) reinterpret_cast<unsigned*>(s_wcnt)[b] = 0u;
-    __syncthreads();
-    unsigned short* my = s_wcnt + w * nbp;
+    for (int r = 0; r < FC_ROWS; ++r) { const int i = c0 + r * 32 + lane; bins[r] = (i < i1) ? (int) bin_ids[p0 + i] : -1; }   // written by this very thread in pass 1
+    wait_chunk(c0, buf);
+    const float4* tp = my_tile + buf * FC_CHUNK;
 #pragma unroll
     for (int r = 0; r < FC_ROWS; ++r) {
       const int bin = bins[r];
       const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
+      unsigned peers = 0u, first = 0u;
+      if (bin >= 0) { peers = __match_any_sync(act, bin); first = my[bin]; }
+      __syncwarp();
       if (bin >= 0) {
-        const unsigned peers = __match_any_sync(act, bin);
-        if ((peers & lanemask_lt()) == 0) my[bin] = (unsigned short) (my[bin] + __popc(peers));   // only this warp writes its row
+        float4 p = tp[r * 32 + lane];
+        p.w = __int_as_float(c0 + r * 32 + lane);
+        out[first + __popc(peers & lanemask_lt())] = p;
+        if ((peers & lanemask_lt()) == 0) my[bin] = first + (unsigned) __popc(peers);
       }
       __syncwarp();
     }
-    __syncthreads();
-    for (int b = tid; b < nbp; b += FC_THREADS) {   // exclusive prefix over the 8 warps (positions relative to the CTA's running base of the bin)
-      unsigned run = 0;
-#pragma unroll
-      for (int ww = 0; ww < FC_THREADS / 32; ++ww) { const unsigned v = s_wcnt[ww * nbp + b]; s_wcnt[ww * nbp + b] = (unsigned short) run; run += v; }
-      s_tcnt[b] = (unsigned short) run;
-    }
-    wait_tile(t, buf);
-    __syncthreads();
-    const float4* tp = s_tile + buf * FC_TILE;
-#pragma unroll
-    for (int r = 0; r < FC_ROWS; ++r) {
-      const int li = w * (FC_ROWS * 32) + r * 32 + lane;
-      const int i = base + r * 32 + lane;
-      const int bin = bins[r];
-      const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
-      if (bin >= 0) {
-        const unsigned peers = __match_any_sync(act, bin);
-        const unsigned pos = s_base[bin] + my[bin] + __popc(peers & lanemask_lt());
-        float4 p = tp[li];
-        p.w = __int_as_float(i);
-        out[pos] = p;
-        __syncwarp(peers);
-        if ((peers & lanemask_lt()) == 0) my[bin] = (unsigned short) (my[bin] + __popc(peers));
-      }
-      __syncwarp();
-    }
-    __syncthreads();
-    for (int b = tid; b < nbp; b += FC_THREADS) s_base[b] += s_tcnt[b];   // the CTA's running base moves past this tile (ordered before the next tile's placement by its barriers)
   }
 }
 

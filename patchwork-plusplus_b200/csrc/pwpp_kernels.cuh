@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS, MINB) k_scatter(const float4* _
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_gle: one warp per frame. Same decisions as gle_frame()/update_thresholds() in pwpp_gle.cuh (the sequential
+// k_gle: one warp per frame. Same decisions as gle_frame()/update_thresholds() in tests/gle_sequential.cuh (the sequential
 // statement of S:211-311, S:402-464, S:338-375 that the CPU twin runs) but lane-parallel over the sectors of a ring:
 // per-sector flags are computed by the lanes, sequence-dependent quantities (history append positions, candidate
 // order, output offsets) come from ballots / warp scans, and the per-array sums of calc_mean_stdev stay sequential
@@ -273,6 +273,8 @@ __device__ __forceinline__ int warp_excl_scan(int v, int& total) {
   total = __shfl_sync(0xffffffffu, incl, 31);
   return incl - v;
 }
+constexpr int GLE_CH = 128;   // samples of each history row staged per step of the threshold update
+__host__ __device__ inline size_t gle_smem_bytes(int max_sectors) { return (size_t) 6 * max_sectors * sizeof(double) + (size_t) 2 * max_sectors * sizeof(int) + (size_t) 8 * GLE_CH * sizeof(double); }
 #define PW_SEG_TO_NG(x) (-3 - (x))   /* "ground part goes to the non-ground list at offset x" until the final shift */
 
 __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restrict__ states, double* __restrict__ hist, int hcap, Geometry g, AlgoParams ap,
@@ -502,10 +504,42 @@ __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restri
   int cnt = 0;
   bool elev_active = false;
   if (lane < 4) {
-    if (lane < nroi) { cnt = n_e[0]; for (int i = 1; i < 4; ++i) if (lane == i) cnt = n_e[i]; elev_active = cnt > 0; if (elev_active) calc_mean_stdev(h_elev + lane * hcap, cnt, m, sd); }
+    if (lane < nroi) { cnt = n_e[0]; for (int i = 1; i < 4; ++i) if (lane == i) cnt = n_e[i]; elev_active = cnt > 0; }
   } else if (lane < 8) {
     const int r = lane - 4;
-    if (r < nroi) { cnt = n_f[0]; for (int i = 1; i < 4; ++i) if (r == i) cnt = n_f[i]; if (cnt > 1) calc_mean_stdev(h_flat + r * hcap, cnt, m, sd); }
+    if (r < nroi) { cnt = n_f[0]; for (int i = 1; i < 4; ++i) if (r == i) cnt = n_f[i]; }
+  }
+  {
+    // calc_mean_stdev (S:557-566) of the eight histories at once: the whole warp stages GLE_CH samples of every row in
+    // shared memory (coalesced loads), then lane r sums row r's samples in order — the same operations in the same order as
+    // the sequential function, without a global-memory round trip per sample (a full history holds max_*_storage = 1000)
+    double* s_h = reinterpret_cast<double*>(s_cng + max_sectors);   // [8][GLE_CH] (8-byte aligned: 2 * max_sectors ints precede it)
+    const int my_n = (lane < 8 && cnt > 1) ? cnt : 0;               // calc_mean_stdev leaves mean / stdev untouched when n <= 1
+    const int max_n = __reduce_max_sync(0xffffffffu, my_n);
+    for (int pass = 0; pass < 2; ++pass) {
+      double acc = 0.0;
+      for (int c0 = 0; c0 < max_n; c0 += GLE_CH) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int nr = __shfl_sync(0xffffffffu, my_n, r);
+          const double* src = (r < 4 ? h_elev + r * hcap : h_flat + (r - 4) * hcap) + c0;
+          const int len = min(GLE_CH, nr - c0);
+          for (int i = lane; i < len; i += 32) s_h[r * GLE_CH + i] = src[i];
+        }
+        __syncwarp();
+        if (lane < 8) {
+          const int len = min(GLE_CH, my_n - c0);
+          const double* v = s_h + lane * GLE_CH;
+          if (pass == 0) { for (int i = 0; i < len; ++i) acc = dadd(acc, v[i]); }
+          else { for (int i = 0; i < len; ++i) { const double d = dsub(v[i], m); acc = dadd(acc, dmul(d, d)); } }
+        }
+        __syncwarp();
+      }
+      if (my_n > 1) {
+        if (pass == 0) m = ddiv(acc, (double) my_n);
+        else sd = dsqrt(ddiv(acc, (double) (my_n - 1)));
+      }
+    }
   }
   // the flatness loop BREAKS at the first ring with <= 1 samples (S:363-364)
   const unsigned flat_ok = __ballot_sync(0xffffffffu, lane >= 4 && lane < 8 && (lane - 4) < nroi && cnt > 1) >> 4;

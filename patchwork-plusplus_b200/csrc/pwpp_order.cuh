@@ -33,10 +33,10 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict_
   PW_DYN_SHARED(unsigned long long, s_key);   // [ORD_CAP]
   __shared__ int s_t;
   const int tid = threadIdx.x;
-  int cum[NUM_CLASSES + 1];
+  int cum[NUM_CLASSES + 1];   // tickets run over the queues from the largest size class to the smallest (long sorts first)
   cum[0] = 0;
 #pragma unroll
-  for (int c = 0; c < NUM_CLASSES; ++c) cum[c + 1] = cum[c] + wq.count[c];
+  for (int c = 0; c < NUM_CLASSES; ++c) cum[c + 1] = cum[c] + wq.count[NUM_CLASSES - 1 - c];
   const int total = cum[NUM_CLASSES];
   for (;;) {
     __syncthreads();
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict_
     int c = 0;
 #pragma unroll
     for (int q = 1; q < NUM_CLASSES; ++q) if (t >= cum[q]) c = q;
-    const int4 wi = wq.items[c][t - cum[c]];
+    const int4 wi = wq.items[NUM_CLASSES - 1 - c][t - cum[c]];
     const int n = wi.y;
     const long long start = work_item_start(wi);
     const float4* P = sorted + start;

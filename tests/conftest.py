@@ -45,7 +45,7 @@ def build_twin(force=False):
     """CPU twin of the CUDA pipeline (tests/host_twin.cu), nvcc host pass; prebuilt .so travels to the GPU box."""
     out = os.path.join(HERE, "_build", "libpwpp_twin.so")
     src = os.path.join(HERE, "host_twin.cu")
-    deps = [src] + [os.path.join(REPO, "patchwork-plusplus_b200", "csrc", f) for f in ("pwpp_math.cuh", "pwpp_gle.cuh", "pwpp_host.hpp")]
+    deps = [src] + [os.path.join(REPO, "patchwork-plusplus_b200", "csrc", f) for f in ("pwpp_math.cuh", "pwpp_gle.cuh", "pwpp_host.hpp")] + [os.path.join(HERE, "gle_sequential.cuh")]
     if force or not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-x", "cu", "-Wno-deprecated-gpu-targets",

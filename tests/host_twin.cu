@@ -1,7 +1,7 @@
 // host_twin.cu — TEST-ONLY CPU twin of the CUDA pipeline.
 //
 // Runs the product's __host__ __device__ code (csrc/pwpp_math.cuh: binning filter, Jacobi SVD, plane from
-// shifted moments, point-plane distance; csrc/pwpp_gle.cuh: A-GLE / TGR / thresholds / output layout) on the
+// shifted moments, point-plane distance) and the sequential A-GLE / TGR / thresholds stage (tests/gle_sequential.cuh) on the
 // CPU, with the warp-parallel glue of the kernels replaced by plain sequential loops that follow the same
 // algorithmic restructuring as k_fit (no z-sort, K-smallest LPR selection, R-VPF "alive" test by stored
 // planes, one-pass moments about a reference point). tests/test_host_twin.py compares it with the oracle,
@@ -14,6 +14,7 @@
 
 #include "pwpp.h"
 #include "pwpp_host.hpp"
+#include "gle_sequential.cuh"
 
 using namespace pwpp;
 

@@ -387,7 +387,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   int* d_np = counts.data() + nframes;
   int* d_nd = counts.data() + 2 * nframes;
   {
-    const size_t gle_smem = (size_t) 6 * t->max_sectors * sizeof(double) + (size_t) 2 * t->max_sectors * sizeof(int);
+    const size_t gle_smem = gle_smem_bytes(t->max_sectors);
     simt::launch("k_gle", nframes, 32, gle_smem, [&] {
       k_gle(ft, states, t->hist.data(), t->hcap, g, ap, nbp, t->max_sectors, bin_off.data(), fits.data(), segs.data(), d_ng, d_np, centers.data(), normals.data(), d_nd);
     });

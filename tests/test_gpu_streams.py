@@ -174,7 +174,8 @@ def test_pybind_device_tensors(kitti):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         t = torch.from_numpy(a).cuda()
-        pw.estimateGround(t, stream=s.cuda_stream)          # enqueued on the producer's stream
-        gd2 = torch.as_tensor(pw.getGroundIndicesDevice(), device="cuda").clone()
+        pw4 = m.patchworkpp(P)                               # fresh temporal state, like `ref`
+        pw4.estimateGround(t, stream=s.cuda_stream)         # enqueued on the producer's stream
+        gd2 = torch.as_tensor(pw4.getGroundIndicesDevice(), device="cuda").clone()
     s.synchronize()
     assert np.array_equal(gd2.cpu().numpy(), g_ref)

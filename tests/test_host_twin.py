@@ -1,6 +1,6 @@
 """CPU twin of the CUDA pipeline vs the oracle (CANON64).
 
-tests/host_twin.cu runs the product's own host+device code (csrc/pwpp_math.cuh, csrc/pwpp_gle.cuh) sequentially on
+tests/host_twin.cu runs the product's own host+device math (csrc/pwpp_math.cuh) and tests/gle_sequential.cuh sequentially on
 the CPU with the same algorithmic restructuring as the kernels. Agreement with the oracle validates, without a GPU:
 the fp32-filtered polar binning (bit-exact bin ids), the 3x3 Jacobi SVD, the shifted one-pass covariance, the
 sort-free LPR selection, the R-VPF 'alive' test by stored planes, A-GLE/TGR/threshold logic and the output layout."""
