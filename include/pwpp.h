@@ -87,7 +87,15 @@ void pwpp_params_default(pwpp_params* p);
 /* Temporal state of one stream — exactly the members the reference mutates between frames
  * (S:347-350, S:368, S:255-256, S:354-355, S:372-373). Used by tests and for
  * checkpoint / stream migration between GPUs. Histories hold at most
- * max_*_storage + (max bins per ring) entries; `hist_cap` is the row capacity in doubles. */
+ * max_*_storage + (max bins per ring) entries; `hist_cap` is the row capacity in doubles.
+ * BOUND (defined deviation): a history row keeps its newest
+ * hist_cap = max(max_elevation_storage, max_flatness_storage) + 4 * (max sectors of a zone) + 64 samples. The reference's
+ * vectors are unbounded while ring 0 holds <= 1 flatness samples (the `break` of S:363-364 then skips the trimming of rings
+ * 1..3); after more than hist_cap accepted patches of one ring in that state the reference averages over the whole history, this
+ * library over the newest hist_cap samples. The state blob of pwpp_export_state depends on hist_cap (checked on import).
+ * NO-PLANE PATCHES (defined deviation): a patch all of whose seed sets are empty has no plane of its own; the reference
+ * (S:49) then partitions it with the normal_/d_ left behind by the previous estimate_plane call. Here all points of such a patch
+ * are non-ground and A-GLE sees the carried mean / normal / singular values (pwpp_bin_result.verdict == -1 marks the patch). */
 typedef struct pwpp_state {
   double sensor_height;
   double elevation_thr[PWPP_MAX_RINGS_OF_INTEREST];
@@ -168,6 +176,10 @@ int pwpp_copy_normals(pwpp_ctx* ctx, int f, float* dst);
 double pwpp_height(pwpp_ctx* ctx, int f);
 /* getTimeTaken (H:155): microseconds of the last estimate call (whole call, all frames). */
 double pwpp_time_us(pwpp_ctx* ctx);
+/* Device-side split of that time for the last pwpp_estimate_host call, when the call ran as one chunk on one stream (calls of
+ * a few frames — the reference's one-frame-per-call pattern): out = { host->device copy, kernels, device->host copy, all three }
+ * in microseconds, from CUDA events on the call's stream. pwpp_time_us minus out[3] is host-side overhead. */
+int pwpp_call_times_us(pwpp_ctx* ctx, float out[4]);
 
 /* Device-side view of the index lists of the last call (zero-copy consumers, benchmark):
  * *d_indices -> int32 array laid out like the input (frame f's region starts at its point

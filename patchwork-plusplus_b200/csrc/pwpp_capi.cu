@@ -115,10 +115,11 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_emit_split = 1, sw_front = 1, sw_patch = 0;
+  int sw_emit_split = 1, sw_front = 1, sw_patch = 0, small_call_frames = 0;
   bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
+  bool call_times_valid = false;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
   cudaStream_t side[5] = {};              // side streams of the concurrent fit kernels
   cudaEvent_t ev_fork = nullptr, ev_join[5] = {};
@@ -148,6 +149,7 @@ struct pwpp_ctx {
   DevBuf<unsigned char> d_labels; // reference-order output only: what became of every point of a fitted patch
   int order_mode = 0;             // PWPP_ORDER_*
   FitLaunch fit[NUM_CLASSES];   // persistent fit kernel of every patch-size class (variant chosen in pwpp_create)
+  FitLaunch fit_small[NUM_CLASSES];   // the same for calls of at most small_call_frames frames (one CTA per patch above 512 points)
   int max_sectors = 0, order_grid = 0;
   DevBuf<int> d_out_idx;
   DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
@@ -285,7 +287,13 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   wq.count = ctx->d_wq_ctr.p;
   wq.head = ctx->d_wq_ctr.p + NUM_CLASSES;
   wq.labels = ctx->order_mode ? ctx->d_labels.p : nullptr;
-  if (ctx->sw_front) {
+  // A call of a few frames (the reference's pattern is one frame per call) cannot fill the GPU with warp-sized work items: there the
+  // latency of the longest patch counts, so patches above 512 points go to the CTA-per-patch kernels, and one frame's cloud is
+  // binned by ~30 independent CTAs (the three stand-alone kernels) rather than by the 8 CTAs of one cluster. r02, one KITTI frame:
+  // longest fit kernel 80 -> 39 us, front end 61 -> 41 us (profiles/r02/ab2_front_bids_latency_solve.log).
+  const bool small_call = nframes <= ctx->small_call_frames;
+  const FitLaunch* fitk = small_call ? ctx->fit_small : ctx->fit;
+  if (ctx->sw_front && !small_call) {
     // one thread-block cluster per frame: binning, scan and stable scatter in one kernel (pwpp_front.cuh)
     if (nframes > 0) {
       const size_t sm_f = front_cluster_smem_bytes(nbp);
@@ -329,7 +337,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   // of CTAs per class that find their queue empty and, worse, keep the six classes from running side by side: cap the grid
   // by what the call can hold (a frame has at most a few hundred patches)
   auto launch_fit = [&](int c, cudaStream_t st) {
-    const FitLaunch& k = ctx->fit[c];
+    const FitLaunch& k = fitk[c];
     if (!k.fn) return;
     const long long cap = (long long) nframes * (k.threads <= 128 ? 96 : 48);
     const int grid = (int) std::min<long long>(k.grid, std::max<long long>(1, cap));
@@ -355,9 +363,16 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     stage += 6;
   }
 #undef FIT_ARGS
-  if (ctx->order_mode) {   // reference emission order inside every fitted patch (pwpp_order.cuh)
-    k_order<<<(int) std::min<long long>(ctx->order_grid, (long long) nframes * 512), ORD_THREADS, ORD_CAP * sizeof(unsigned long long), s>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
+  // reference emission order inside every fitted patch (pwpp_order.cuh). k_order only permutes `part` inside a patch and k_gle only
+  // reads the patch records, so the two run side by side (k_order on a side stream, joined before k_emit): on a one-frame call
+  // the sort of the largest patch (~80 us) and the ring walk of k_gle (~50 us) are both pure latency.
+  const bool order_aside = ctx->order_mode && !prof && !serial_fit;
+  if (ctx->order_mode) {
+    cudaStream_t so = order_aside ? ctx->side[0] : s;
+    if (order_aside) { CU_TRY(cudaEventRecord(ctx->ev_fork, s)); CU_TRY(cudaStreamWaitEvent(so, ctx->ev_fork, 0)); }
+    k_order<<<(int) std::min<long long>(ctx->order_grid, (long long) nframes * 512), ORD_THREADS, ORD_SMEM_KEYS * sizeof(unsigned long long), so>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
     ++ctx->launches;
+    if (order_aside) CU_TRY(cudaEventRecord(ctx->ev_join[0], so));
   }
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
@@ -368,6 +383,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     ++ctx->launches;
   }
   STAGE_MARK();
+  if (order_aside) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[0], 0));
   if (max_chunks > 0) {
     // a bin is copied by `split` warps: 1 for KITTI-sized frames (bins of a few thousand points), 16 for dense sensors whose
     // 20k..40k-point bins would otherwise be left to one warp each (r02: dense k_emit 1.15 -> 0.14 ms; KITTI 0.33 -> 0.94 ms at 16)
@@ -543,6 +559,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);        // 1: cluster-per-frame front end, 0: k_bin_hist + k_bin_scan + k_scatter
   ctx->sw_patch = env_int("PWPP_FIT_PATCH", PWPP_FIT_PATCH_DEFAULT, 0, 1);   // 1: patches above 512 points on k_fit_patch
   ctx->sw_graph = env_int("PWPP_GRAPH", 1, 0, 1);
+  ctx->small_call_frames = env_int("PWPP_SMALL_CALL", PWPP_SMALL_CALL_DEFAULT, 0, 64);   // calls of at most this many frames take the small-call kernels (0: never)
   ctx->nbp = ((ctx->g.nbins + PW_NUM_PSEUDO + 31) / 32) * 32;
   int max_sectors = 0;
   for (int k = 0; k < 4; ++k) max_sectors = std::max(max_sectors, ctx->g.num_sectors[k]);
@@ -563,6 +580,8 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev0));
   CU_TRY_CTX(cudaEventCreate(&ctx->ev1));
+  CU_TRY_CTX(cudaEventCreate(&ctx->ev_begin));
+  CU_TRY_CTX(cudaEventCreate(&ctx->ev_end));
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
   for (int i = 0; i < 2; ++i) CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
   CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -602,17 +621,21 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       ctx->fit[3] = {k_fit_patch<8, 2, 3>, 0, 8 * 32, (size_t) 8 * FP_STG * sizeof(float4)};
       ctx->fit[4] = {k_fit_patch<16, 1, 4>, 0, 16 * 32, (size_t) 16 * FP_STG * sizeof(float4)};
     }
-    for (int c = 0; c < NUM_CLASSES; ++c) {
-      FitLaunch& k = ctx->fit[c];
+    for (int c = 0; c < NUM_CLASSES; ++c) ctx->fit_small[c] = ctx->fit[c];
+    ctx->fit_small[2] = {k_fit_patch<4, 4, 2>, 0, 4 * 32, (size_t) 4 * FP_STG * sizeof(float4)};
+    ctx->fit_small[3] = {k_fit_patch<8, 2, 3>, 0, 8 * 32, (size_t) 8 * FP_STG * sizeof(float4)};
+    ctx->fit_small[4] = {k_fit_patch<16, 1, 4>, 0, 16 * 32, (size_t) 16 * FP_STG * sizeof(float4)};
+    for (int c = 0; c < 2 * NUM_CLASSES; ++c) {
+      FitLaunch& k = c < NUM_CLASSES ? ctx->fit[c] : ctx->fit_small[c - NUM_CLASSES];
       if (k.smem > 0) CU_TRY_CTX(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k.smem));
       int per_sm = 1;
       CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, k.threads, k.smem));
       k.grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
     {
-      CU_TRY_CTX(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (ORD_CAP * sizeof(unsigned long long))));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (ORD_SMEM_KEYS * sizeof(unsigned long long))));
       int per_sm = 1;
-      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_order, ORD_THREADS, ORD_CAP * sizeof(unsigned long long)));
+      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_order, ORD_THREADS, ORD_SMEM_KEYS * sizeof(unsigned long long)));
       ctx->order_grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
     const size_t gle_smem = gle_smem_bytes(max_sectors);
@@ -662,6 +685,8 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   ctx->h_centers.release(); ctx->h_normals.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
   if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
@@ -728,6 +753,7 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
   const long long total = ctx->pt_off[nframes];
   CU_TRY(ctx->d_in.reserve((size_t) std::max<long long>(total, 1)));
   cudaStream_t s = ctx->stream, s_in = ctx->stream_h2d, s_out = ctx->stream_d2h;
+  ctx->call_times_valid = false;
   // the staging buffers of the previous call must not be in flight any more (nor a device-input call on a caller's stream)
   if (ctx->last_stream && ctx->last_stream != s) CU_TRY(cudaStreamSynchronize(ctx->last_stream));
   CU_TRY(cudaStreamSynchronize(s));
@@ -747,6 +773,10 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
     chunk_frames = (int) std::min<long long>(nframes, std::max<long long>(1, (4LL << 20) / per_frame));
   }
   const int nchunks = (nframes + chunk_frames - 1) / chunk_frames;
+  // a call that is a single chunk has nothing to pipeline: copies and kernels share one stream (no cross-stream event hops,
+  // ~10 us each on the critical path of a one-frame call) and four events bracket its three phases (pwpp_call_times_us)
+  const bool one_stream = (nchunks == 1);
+  if (one_stream) { s_in = s; s_out = s; CU_TRY(cudaEventRecord(ctx->ev_begin, s)); }
   for (int k = 0; k < nchunks; ++k) {
     const int f0 = k * chunk_frames, f1 = std::min(nframes, f0 + chunk_frames);
     for (int f = f0; f < f1; ++f) {
@@ -791,19 +821,25 @@ int pwpp_estimate_host(pwpp_ctx* ctx, int nframes, const float* const* pts, cons
       CU_TRY(cudaMemcpyAsync(ctx->d_in.p + ctx->pt_off[f], dst, (size_t) cnt * sizeof(float4), cudaMemcpyHostToDevice, s_in));
     }
     CU_TRY(cudaEventRecord(ctx->ev0, s_in));
-    CU_TRY(cudaStreamWaitEvent(s, ctx->ev0, 0));
+    if (!one_stream) CU_TRY(cudaStreamWaitEvent(s, ctx->ev0, 0));
     rc = launch_range(ctx, f0, f1 - f0, ctx->d_in.p, cols == 4 ? 1 : 0, s, ctx->profiling && nchunks == 1);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(ctx->ev1, s));
-    CU_TRY(cudaStreamWaitEvent(s_out, ctx->ev1, 0));
+    if (!one_stream) CU_TRY(cudaStreamWaitEvent(s_out, ctx->ev1, 0));
     const long long o0 = ctx->pt_off[f0], o1 = ctx->pt_off[f1];
+    if (f0 == 0 && f1 == ctx->num_streams) {   // the three count rows are one contiguous block when the chunk covers every stream
+      CU_TRY(cudaMemcpyAsync(ctx->h_counts.p, ctx->d_counts.p, (size_t) 3 * ctx->num_streams * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+    } else {
+      for (int q = 0; q < 3; ++q)
+        CU_TRY(cudaMemcpyAsync(ctx->h_counts.p + (size_t) q * ctx->num_streams + f0, ctx->d_counts.p + (size_t) q * ctx->num_streams + f0,
+                               (size_t) (f1 - f0) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+    }
     if (o1 > o0) CU_TRY(cudaMemcpyAsync(ctx->h_out_idx.p + o0, ctx->d_out_idx.p + o0, (size_t) (o1 - o0) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
-    for (int q = 0; q < 3; ++q)
-      CU_TRY(cudaMemcpyAsync(ctx->h_counts.p + (size_t) q * ctx->num_streams + f0, ctx->d_counts.p + (size_t) q * ctx->num_streams + f0,
-                             (size_t) (f1 - f0) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
   }
+  if (one_stream) CU_TRY(cudaEventRecord(ctx->ev_end, s));
   CU_TRY(cudaStreamSynchronize(s_out));
   CU_TRY(cudaStreamSynchronize(s));
+  ctx->call_times_valid = one_stream;
   ctx->counts_fetched = true;
   ctx->idx_fetched = true;
   ctx->last_time_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
@@ -959,6 +995,20 @@ double pwpp_height(pwpp_ctx* ctx, int f) {
   return s.sensor_height;
 }
 double pwpp_time_us(pwpp_ctx* ctx) { return ctx ? ctx->last_time_us : NAN; }
+
+int pwpp_call_times_us(pwpp_ctx* ctx, float out[4]) {
+  if (!ctx || !out) return fail(PWPP_ERR_INVALID_ARG, "NULL argument");
+  if (!ctx->call_times_valid) return fail(PWPP_ERR_INVALID_ARG, "no single-chunk pwpp_estimate_host call to report on");
+  int rc = bind_device(ctx);
+  if (rc) return rc;
+  float ms[4];
+  CU_TRY(cudaEventElapsedTime(&ms[0], ctx->ev_begin, ctx->ev0));
+  CU_TRY(cudaEventElapsedTime(&ms[1], ctx->ev0, ctx->ev1));
+  CU_TRY(cudaEventElapsedTime(&ms[2], ctx->ev1, ctx->ev_end));
+  CU_TRY(cudaEventElapsedTime(&ms[3], ctx->ev_begin, ctx->ev_end));
+  for (int i = 0; i < 4; ++i) out[i] = ms[i] * 1000.f;
+  return PWPP_OK;
+}
 
 int pwpp_copy_history(pwpp_ctx* ctx, int f, int ring, int which, double* dst) {
   if (!ctx || !dst || f < 0 || f >= ctx->num_streams || ring < 0 || ring > 3 || which < 0 || which > 1) return fail(PWPP_ERR_INVALID_ARG, "bad argument");

@@ -19,7 +19,8 @@
 
 namespace pwpp {
 
-constexpr int ORD_CAP = 8192;       // keys in shared memory (64 KB)
+constexpr int ORD_CAP = 8192;       // keys in shared memory
+constexpr int ORD_SMEM_KEYS = ORD_CAP + ORD_CAP / 16;   // one pad key per 16-key block (68 KB)
 constexpr int ORD_THREADS = 512;
 
 __device__ __forceinline__ unsigned long long order_sort_key(float z, unsigned char label, unsigned pos) {
@@ -30,7 +31,7 @@ __device__ __forceinline__ unsigned long long order_sort_key(float z, unsigned c
 
 // One CTA per fitted patch, persistent over all class queues (items: make_work_item format).
 __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict__ sorted, WorkQueues wq, int* __restrict__ order_head, int* __restrict__ part) {
-  PW_DYN_SHARED(unsigned long long, s_key);   // [ORD_CAP]
+  PW_DYN_SHARED(unsigned long long, s_key);   // [ORD_SMEM_KEYS]
   __shared__ int s_t;
   const int tid = threadIdx.x;
   int cum[NUM_CLASSES + 1];   // tickets run over the queues from the largest size class to the smallest (long sorts first)
@@ -54,31 +55,73 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict_
     const unsigned char* L = wq.labels + start;
     int* out = part + start;
     if (n <= ORD_CAP) {
-      for (int i = tid; i < n; i += ORD_THREADS) s_key[i] = order_sort_key(P[i].z, L[i], (unsigned) i);
+      // Bitonic network with every compare-exchange ascending: merge level k first pairs i with i ^ (k - 1) (i in the lower half
+      // of its k-block), then i with i + j for j = k/4 .. 1. Thread t OWNS the 16 consecutive keys [16 t, 16 t + 16): every step
+      // whose partner distance is below 16 — all of levels 2..16 and the last four steps of every later level — runs in its
+      // registers without a barrier, the other steps go through shared memory (one loop iteration per PAIR). 8192 keys: 54
+      // barrier intervals instead of the 91 of the plain network (a one-frame call waits for the sort of its largest patch).
+      // Shared-memory index of key i is i + (i >> 4): the pad keeps a thread's 16-key block off its neighbours' banks.
+      auto at = [&](int i) -> unsigned long long& { return s_key[i + (i >> 4)]; };
+      for (int i = tid; i < n; i += ORD_THREADS) at(i) = order_sort_key(P[i].z, L[i], (unsigned) i);
       __syncthreads();
-      // bitonic network, every compare-exchange ascending: merge step k first pairs i with i ^ (k - 1) (i in the lower half of its
-      // k-block), then i with i + j for j = k/4 .. 1. One loop iteration per PAIR; four pairs in flight per thread.
-      int n2 = 2;
+      int n2 = 16;
       while (n2 < n) n2 <<= 1;
       const int npairs = n2 >> 1;
-      auto cex = [&](int i, int l) {
-        if (l < n) {
-          const unsigned long long a = s_key[i], b = s_key[l];
-          if (a > b) { s_key[i] = b; s_key[l] = a; }
+      const int base = tid << 4;
+      const bool own = base < n;   // blocks at or above n hold only the virtual +inf padding, which never moves
+      unsigned long long r[16];
+      auto cexr = [&](int a, int b) { if (r[a] > r[b]) { const unsigned long long t = r[a]; r[a] = r[b]; r[b] = t; } };
+      auto load_block = [&]() {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = (base + e < n) ? at(base + e) : ~0ull;
+      };
+      auto store_block = [&]() {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) if (base + e < n) at(base + e) = r[e];
+      };
+      auto local_tail = [&]() {   // steps j = 8, 4, 2, 1 of a level
+#pragma unroll
+        for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) if (!(e & j)) cexr(e, e | j);
         }
       };
-      for (int k = 2, lk = 1; k <= n2; k <<= 1, ++lk) {
+      if (own) {
+        load_block();
+#pragma unroll
+        for (int k = 2; k <= 16; k <<= 1) {   // levels 2..16 entirely in registers
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { const int l = e ^ (k - 1); if (l > e && (e & (k - 1)) < (k >> 1)) cexr(e, l); }
+#pragma unroll
+          for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) if (!(e & j)) cexr(e, e | j);
+          }
+        }
+        store_block();
+      }
+      __syncthreads();
+      auto cex = [&](int i, int l) {
+        if (l < n) {
+          unsigned long long &pa = at(i), &pb = at(l);
+          const unsigned long long a = pa, b = pb;
+          if (a > b) { pa = b; pb = a; }
+        }
+      };
+      for (int k = 32, lk = 5; k <= n2; k <<= 1, ++lk) {
         const int hk = k >> 1;
 #pragma unroll 4
         for (int q = tid; q < npairs; q += ORD_THREADS) { const int i = ((q >> (lk - 1)) << lk) | (q & (hk - 1)); cex(i, i ^ (k - 1)); }
         __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int j = k >> 2; j >= 16; j >>= 1) {
 #pragma unroll 4
           for (int q = tid; q < npairs; q += ORD_THREADS) { const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)); cex(i, i | j); }
           __syncthreads();
         }
+        if (own) { load_block(); local_tail(); store_block(); }
+        __syncthreads();
       }
-      for (int i = tid; i < n; i += ORD_THREADS) out[i] = __float_as_int(P[(int) (s_key[i] & 0xffffffull)].w);
+      for (int i = tid; i < n; i += ORD_THREADS) out[i] = __float_as_int(P[(int) (at(i) & 0xffffffull)].w);
     } else {
       // in place in global memory: `out` holds positions, compared through their keys; same network
       for (int i = tid; i < n; i += ORD_THREADS) out[i] = i;

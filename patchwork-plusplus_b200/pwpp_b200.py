@@ -43,6 +43,7 @@ def load_library():
     lib.pwpp_num_patches.argtypes = [vp, i32]; lib.pwpp_num_patches.restype = i32
     lib.pwpp_height.argtypes = [vp, i32]; lib.pwpp_height.restype = C.c_double
     lib.pwpp_time_us.argtypes = [vp]; lib.pwpp_time_us.restype = C.c_double
+    lib.pwpp_call_times_us.argtypes = [vp, C.POINTER(C.c_float)]; lib.pwpp_call_times_us.restype = i32
     lib.pwpp_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]; lib.pwpp_device_results.restype = i32
     lib.pwpp_get_state.argtypes = [vp, i32, C.POINTER(PwppState)]; lib.pwpp_get_state.restype = i32
     lib.pwpp_copy_history.argtypes = [vp, i32, i32, i32, vp]; lib.pwpp_copy_history.restype = i32
@@ -167,6 +168,12 @@ class Engine:
 
     def height(self, f=0): return float(self.lib.pwpp_height(self._h, f))
     def time_us(self): return float(self.lib.pwpp_time_us(self._h))
+
+    def call_times_us(self):
+        """{h2d, kernels, d2h, device_total} of the last single-chunk estimate_host call, microseconds (CUDA events)."""
+        arr = (C.c_float * 4)()
+        _check(self.lib.pwpp_call_times_us(self._h, arr))
+        return dict(zip(("h2d", "kernels", "d2h", "device_total"), (float(v) for v in arr)))
 
     def bin_results(self, f=0):
         arr = (PwppBinResult * self.nbins)()

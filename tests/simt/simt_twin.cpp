@@ -382,7 +382,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     std::snprintf(buf, sizeof buf, "S=%d M=%d L1=%d L2=%d L3=%d X=%d", ctr[0], ctr[1], ctr[2], ctr[3], ctr[4], ctr[5]);
     t->last_launches = buf;
   }
-  if (t->order) simt::launch("k_order", pg, ORD_THREADS, ORD_CAP * sizeof(unsigned long long), [&] { k_order(sorted.data(), wq, ctr.data() + 2 * NUM_CLASSES, part.data()); });
+  if (t->order) simt::launch("k_order", pg, ORD_THREADS, ORD_SMEM_KEYS * sizeof(unsigned long long), [&] { k_order(sorted.data(), wq, ctr.data() + 2 * NUM_CLASSES, part.data()); });
   int* d_ng = counts.data();
   int* d_np = counts.data() + nframes;
   int* d_nd = counts.data() + 2 * nframes;

@@ -19,10 +19,12 @@ for order in (0, 1):
     eng.set_profiling(False)
     for _ in range(20):
         eng.estimate_host([a])
-    ts = []
+    ts, ct = [], []
     for _ in range(200):
         t0 = time.perf_counter(); eng.estimate_host([a]); ts.append((time.perf_counter() - t0) * 1e6)
+        ct.append(eng.call_times_us())
     ts.sort()
+    print("order", order, "device split us (median):", {k: round(sorted(c[k] for c in ct)[100], 1) for k in ct[0]})
     print("order", order, "stage us:", {k: round(v, 1) for k, v in acc.items()}, "sum", round(sum(acc.values()), 1), "| call median us", round(ts[100], 1), "min", round(ts[0], 1), "time_us", round(eng.time_us(), 1))
     eng.close()
 os.environ["PWPP_GRAPH"] = "0"
