@@ -145,12 +145,13 @@ struct pwpp_ctx {
   DevBuf<BinFit> d_fits;          // [F][nbins]
   DevBuf<BinSeg> d_segs;          // [F][nbins+3]
   DevBuf<int4> d_wq_items[NUM_CLASSES];  // fit work queues
-  DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES + 1]: counts, heads, k_order's head
+  DevBuf<int> d_wq_ctr;           // [2*NUM_CLASSES + ORD_NUM_HEADS]: counts, heads, the heads of the five k_order launches
   DevBuf<unsigned char> d_labels; // reference-order output only: what became of every point of a fitted patch
   int order_mode = 0;             // PWPP_ORDER_*
   FitLaunch fit[NUM_CLASSES];   // persistent fit kernel of every patch-size class (variant chosen in pwpp_create)
   FitLaunch fit_small[NUM_CLASSES];   // the same for calls of at most small_call_frames frames (one CTA per patch above 512 points)
-  int max_sectors = 0, order_grid = 0;
+  int max_sectors = 0;
+  FitLaunch order_k[ORD_NUM_HEADS];   // k_order_cta<512, X>, <512, L3>, <256, L2>, <128, L1>, k_order_warp (same argument list as the fit kernels' type is not needed: launched by name)
   DevBuf<int> d_out_idx;
   DevBuf<int> d_counts;           // [3][F]: num_ground, num_patches, num_dropped
   DevBuf<float> d_centers, d_normals;  // [F][nbins][3]
@@ -278,7 +279,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   BinSeg* segs = ctx->d_segs.p + (size_t) f0 * nb_all;
   float* centers = ctx->d_centers.p + (size_t) f0 * nb * 3;
   float* normals = ctx->d_normals.p + (size_t) f0 * nb * 3;
-  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, (2 * NUM_CLASSES + 1) * sizeof(int), s));
+  CU_TRY(cudaMemsetAsync(ctx->d_wq_ctr.p, 0, (2 * NUM_CLASSES + ORD_NUM_HEADS) * sizeof(int), s));
   int stage = 0;
 #define STAGE_MARK() do { if (prof) CU_TRY(cudaEventRecord(ctx->stage_ev[stage], s)); ++stage; } while (0)
   STAGE_MARK();
@@ -363,16 +364,30 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     stage += 6;
   }
 #undef FIT_ARGS
-  // reference emission order inside every fitted patch (pwpp_order.cuh). k_order only permutes `part` inside a patch and k_gle only
-  // reads the patch records, so the two run side by side (k_order on a side stream, joined before k_emit): on a one-frame call
-  // the sort of the largest patch (~80 us) and the ring walk of k_gle (~50 us) are both pure latency.
+  // reference emission order inside every fitted patch (pwpp_order.cuh): five launches (classes X, L3, L2, L1 with a CTA sized to the
+  // class, M + S one warp per patch). They only permute `part` inside a patch and k_gle only reads the patch records, so they run
+  // beside k_gle on the side streams and are joined before k_emit: on a one-frame call the sort of the largest patch (~50 us) and
+  // the ring walk of k_gle (~50 us) are both pure latency.
   const bool order_aside = ctx->order_mode && !prof && !serial_fit;
   if (ctx->order_mode) {
-    cudaStream_t so = order_aside ? ctx->side[0] : s;
-    if (order_aside) { CU_TRY(cudaEventRecord(ctx->ev_fork, s)); CU_TRY(cudaStreamWaitEvent(so, ctx->ev_fork, 0)); }
-    k_order<<<(int) std::min<long long>(ctx->order_grid, (long long) nframes * 512), ORD_THREADS, ORD_SMEM_KEYS * sizeof(unsigned long long), so>>>(ctx->d_sorted.p, wq, ctx->d_wq_ctr.p + 2 * NUM_CLASSES, ctx->d_part.p);
-    ++ctx->launches;
-    if (order_aside) CU_TRY(cudaEventRecord(ctx->ev_join[0], so));
+    if (order_aside) CU_TRY(cudaEventRecord(ctx->ev_fork, s));
+    int* heads = ctx->d_wq_ctr.p + 2 * NUM_CLASSES;
+    for (int q = 0; q < ORD_NUM_HEADS; ++q) {
+      cudaStream_t so = order_aside ? ctx->side[q] : s;
+      if (order_aside) CU_TRY(cudaStreamWaitEvent(so, ctx->ev_fork, 0));
+      const int grid = (int) std::min<long long>(ctx->order_k[q].grid, std::max<long long>(1, (long long) nframes * (q == 4 ? 64 : 32)));
+      const int th = ctx->order_k[q].threads;
+      const size_t sm = ctx->order_k[q].smem;
+      switch (q) {
+        case 0: k_order_cta<512, 5><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+        case 1: k_order_cta<512, 4><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+        case 2: k_order_cta<256, 3><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+        case 3: k_order_cta<128, 2><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+        default: k_order_warp<<<grid, th, 0, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+      }
+      ++ctx->launches;
+      if (order_aside) CU_TRY(cudaEventRecord(ctx->ev_join[q], so));
+    }
   }
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
@@ -383,7 +398,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     ++ctx->launches;
   }
   STAGE_MARK();
-  if (order_aside) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[0], 0));
+  if (order_aside) for (int q = 0; q < ORD_NUM_HEADS; ++q) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
   if (max_chunks > 0) {
     // a bin is copied by `split` warps: 1 for KITTI-sized frames (bins of a few thousand points), 16 for dense sensors whose
     // 20k..40k-point bins would otherwise be left to one warp each (r02: dense k_emit 1.15 -> 0.14 ms; KITTI 0.33 -> 0.94 ms at 16)
@@ -598,7 +613,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   }
   CU_TRY_CTX(ctx->d_hist.reserve((size_t) num_streams * 2 * 4 * ctx->hcap));
   CU_TRY_CTX(ctx->d_counts.reserve((size_t) 3 * num_streams));
-  CU_TRY_CTX(ctx->d_wq_ctr.reserve(2 * NUM_CLASSES + 1));
+  CU_TRY_CTX(ctx->d_wq_ctr.reserve(2 * NUM_CLASSES + ORD_NUM_HEADS));
   {
     cudaDeviceProp prop;
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
@@ -633,10 +648,18 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
       k.grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
     {
-      CU_TRY_CTX(cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (ORD_SMEM_KEYS * sizeof(unsigned long long))));
-      int per_sm = 1;
-      CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_order, ORD_THREADS, ORD_SMEM_KEYS * sizeof(unsigned long long)));
-      ctx->order_grid = std::max(1, per_sm) * prop.multiProcessorCount;
+      typedef void (*OrdKernel)(const float4*, WorkQueues, int*, int*);
+      const OrdKernel fn[ORD_NUM_HEADS] = {k_order_cta<512, 5>, k_order_cta<512, 4>, k_order_cta<256, 3>, k_order_cta<128, 2>, k_order_warp};
+      const int th[ORD_NUM_HEADS] = {512, 512, 256, 128, ORD_WARP_THREADS};
+      for (int q = 0; q < ORD_NUM_HEADS; ++q) {
+        const size_t sm = q < 4 ? ord_cta_smem_bytes(th[q]) : 0;
+        if (sm > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+        int per_sm = 1;
+        CU_TRY_CTX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[q], th[q], sm));
+        ctx->order_k[q].grid = std::max(1, per_sm) * prop.multiProcessorCount;
+        ctx->order_k[q].threads = th[q];
+        ctx->order_k[q].smem = sm;
+      }
     }
     const size_t gle_smem = gle_smem_bytes(max_sectors);
     if (gle_smem > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_gle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gle_smem));

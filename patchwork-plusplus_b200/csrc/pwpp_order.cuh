@@ -11,17 +11,29 @@
 // (oracle/_ref/libpwref_stable.so; with std::sort the order of equal z is unspecified in the reference itself).
 // Sort key of a point: (group, z, position in the bin) with group 0 = ground, 1..num_iter = R-VPF iteration, 9 = final
 // reject — one sort per patch yields ground part + non-ground part at once. Positions come from the labels the fit kernels
-// leave (WorkQueues::labels). Patches up to ORD_CAP points are sorted in shared memory (64-bit keys, bitonic network with
-// all compare-exchanges ascending, so the virtual +inf padding above n never moves and is never stored); larger patches
-// (class X, dense sensors) are sorted in place in global memory through an index array with the same network.
+// leave (WorkQueues::labels).
+//
+// The sort is a bitonic network with every compare-exchange ascending (merge level k first pairs i with i ^ (k - 1), i in the lower
+// half of its k-block, then i with i + j for j = k/4 .. 1), so the virtual +inf padding above n never moves. A thread owns 16
+// consecutive keys in registers: steps with partner distance < 16 never leave them.
+//   * k_order_warp — patches of at most 512 points (classes S and M: 83 % of the patches of a KITTI frame): ONE WARP per patch,
+//     distances 16..256 are warp shuffles, no shared memory, no block barrier (the first form of this stage gave each of them a
+//     512-thread CTA and ~25 barrier intervals);
+//   * k_order_cta<NT> — one CTA of NT = 128 / 256 / 512 threads per patch of class L1 / L2 / L3 (16 NT keys): distances >= 16 go
+//     through shared memory behind a block barrier (54 barrier intervals for 8192 keys; the plain shared-memory network has 91);
+//     the CTA is sized to the class so that no warp idles at the barriers;
+//   * class X (dense sensors, more than 8192 points): sorted in place in global memory through an index array (k_order_cta<512>).
+// r02 on 1024 KITTI-shaped frames (profiles/README.md): one 512-thread CTA per patch for everything 8.0 ms; 512-key register
+// blocks per warp with 16-warp CTAs for every patch above 512 points 14.5 ms (one CTA per SM at 92 registers, 4 of 16 warps busy on
+// an L1 patch: rejected); this form: see profiles/README.md.
 #pragma once
 #include "pwpp_fit.cuh"
 
 namespace pwpp {
 
 constexpr int ORD_CAP = 8192;       // keys in shared memory
-constexpr int ORD_SMEM_KEYS = ORD_CAP + ORD_CAP / 16;   // one pad key per 16-key block (68 KB)
-constexpr int ORD_THREADS = 512;
+constexpr int ORD_NUM_HEADS = 5;    // ticket counters of the five launches: classes X, L3, L2, L1 and the warp-sorted classes M + S
+__host__ __device__ constexpr size_t ord_cta_smem_bytes(int nt) { return (size_t) nt * 17 * sizeof(unsigned long long); }   // 16 keys + one pad key per thread
 
 __device__ __forceinline__ unsigned long long order_sort_key(float z, unsigned char label, unsigned pos) {
   const unsigned grp = label == PW_LABEL_GROUND ? 0u : (label == PW_LABEL_REJECT ? 9u : (unsigned) label);
@@ -29,48 +41,95 @@ __device__ __forceinline__ unsigned long long order_sort_key(float z, unsigned c
   return ((unsigned long long) grp << 56) | ((unsigned long long) order_key(z + 0.0f) << 24) | (unsigned long long) (pos & 0xffffffu);
 }
 
-// One CTA per fitted patch, persistent over all class queues (items: make_work_item format).
-__global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict__ sorted, WorkQueues wq, int* __restrict__ order_head, int* __restrict__ part) {
-  PW_DYN_SHARED(unsigned long long, s_key);   // [ORD_SMEM_KEYS]
-  __shared__ int s_t;
-  const int tid = threadIdx.x;
-  int cum[NUM_CLASSES + 1];   // tickets run over the queues from the largest size class to the smallest (long sorts first)
-  cum[0] = 0;
+typedef unsigned long long OrdKey;
+
+__device__ __forceinline__ void ord_cex(OrdKey& a, OrdKey& b) { if (a > b) { const OrdKey t = a; a = b; b = t; } }
+
+// steps j = 8, 4, 2, 1 of a level: inside a lane's 16 keys
+__device__ __forceinline__ void ord_local_tail(OrdKey (&r)[16]) {
 #pragma unroll
-  for (int c = 0; c < NUM_CLASSES; ++c) cum[c + 1] = cum[c] + wq.count[NUM_CLASSES - 1 - c];
-  const int total = cum[NUM_CLASSES];
+  for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (!(e & j)) ord_cex(r[e], r[e | j]);
+  }
+}
+// levels 2..16 entirely inside a lane
+__device__ __forceinline__ void ord_local_presort(OrdKey (&r)[16]) {
+#pragma unroll
+  for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const int l = e ^ (k - 1); if (l > e && (e & (k - 1)) < (k >> 1)) ord_cex(r[e], r[l]); }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) if (!(e & j)) ord_cex(r[e], r[e | j]);
+    }
+  }
+}
+// step "i with i + j" for j = 16 m (m = 1..16): key e of a lane meets key e of lane ^ m; the lane with bit m clear keeps the smaller
+__device__ __forceinline__ void ord_lane_step(OrdKey (&r)[16], int m, int lane) {
+  const bool upper = (lane & m) != 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const OrdKey o = __shfl_xor_sync(0xffffffffu, r[e], m);
+    const bool take = upper ? (o > r[e]) : (o < r[e]);
+    r[e] = take ? o : r[e];
+  }
+}
+// first step of level k (32 <= k <= 512): i meets i ^ (k - 1) = key 15 - e of lane ^ (k/16 - 1); the upper half of a k-block keeps the larger
+__device__ __forceinline__ void ord_lane_flip(OrdKey (&r)[16], int k, int lane) {
+  const int mm = (k >> 4) - 1;
+  const bool upper = (lane & (k >> 5)) != 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const OrdKey a = __shfl_xor_sync(0xffffffffu, r[15 - e], mm);   // the partner's key 15 - e
+    const OrdKey b = __shfl_xor_sync(0xffffffffu, r[e], mm);        // the partner's key e
+    const bool ta = upper ? (a > r[e]) : (a < r[e]);
+    const bool tb = upper ? (b > r[15 - e]) : (b < r[15 - e]);
+    r[e] = ta ? a : r[e];
+    r[15 - e] = tb ? b : r[15 - e];
+  }
+}
+// a warp's 512 keys, sorted up to level kmax (a power of two in [16, 512]: blocks of kmax keys come out sorted)
+__device__ __forceinline__ void ord_warp_sort(OrdKey (&r)[16], int kmax, int lane) {
+  ord_local_presort(r);
+  for (int k = 32; k <= kmax; k <<= 1) {
+    ord_lane_flip(r, k, lane);
+    for (int m = k >> 6; m > 0; m >>= 1) ord_lane_step(r, m, lane);
+    ord_local_tail(r);
+  }
+}
+
+// One CTA of NT threads per patch of queue CLS (items: make_work_item format), persistent; `head` is this launch's ticket counter.
+template <int NT, int CLS>
+__global__ void __launch_bounds__(NT) k_order_cta(const float4* __restrict__ sorted, WorkQueues wq, int* __restrict__ head, int* __restrict__ part) {
+  PW_DYN_SHARED(unsigned long long, s_key);   // [NT * 17]
+  __shared__ int s_t;
+  constexpr int CAP = NT * 16;
+  const int tid = threadIdx.x;
+  const int total = wq.count[CLS];
+  auto at = [&](int i) -> OrdKey& { return s_key[i + (i >> 4)]; };   // the pad keeps a thread's 16-key block off its neighbours' banks
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_t = atomicAdd(order_head, 1);
+    if (tid == 0) s_t = atomicAdd(head, 1);
     __syncthreads();
     const int t = s_t;
     if (t >= total) return;
-    int c = 0;
-#pragma unroll
-    for (int q = 1; q < NUM_CLASSES; ++q) if (t >= cum[q]) c = q;
-    const int4 wi = wq.items[NUM_CLASSES - 1 - c][t - cum[c]];
+    const int4 wi = wq.items[CLS][t];
     const int n = wi.y;
     const long long start = work_item_start(wi);
     const float4* P = sorted + start;
     const unsigned char* L = wq.labels + start;
     int* out = part + start;
-    if (n <= ORD_CAP) {
-      // Bitonic network with every compare-exchange ascending: merge level k first pairs i with i ^ (k - 1) (i in the lower half
-      // of its k-block), then i with i + j for j = k/4 .. 1. Thread t OWNS the 16 consecutive keys [16 t, 16 t + 16): every step
-      // whose partner distance is below 16 — all of levels 2..16 and the last four steps of every later level — runs in its
-      // registers without a barrier, the other steps go through shared memory (one loop iteration per PAIR). 8192 keys: 54
-      // barrier intervals instead of the 91 of the plain network (a one-frame call waits for the sort of its largest patch).
-      // Shared-memory index of key i is i + (i >> 4): the pad keeps a thread's 16-key block off its neighbours' banks.
-      auto at = [&](int i) -> unsigned long long& { return s_key[i + (i >> 4)]; };
-      for (int i = tid; i < n; i += ORD_THREADS) at(i) = order_sort_key(P[i].z, L[i], (unsigned) i);
+    if (n <= CAP) {
+      for (int i = tid; i < n; i += NT) at(i) = order_sort_key(P[i].z, L[i], (unsigned) i);   // coalesced
       __syncthreads();
       int n2 = 16;
       while (n2 < n) n2 <<= 1;
       const int npairs = n2 >> 1;
       const int base = tid << 4;
       const bool own = base < n;   // blocks at or above n hold only the virtual +inf padding, which never moves
-      unsigned long long r[16];
-      auto cexr = [&](int a, int b) { if (r[a] > r[b]) { const unsigned long long t = r[a]; r[a] = r[b]; r[b] = t; } };
+      OrdKey r[16];
       auto load_block = [&]() {
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = (base + e < n) ? at(base + e) : ~0ull;
@@ -79,56 +138,36 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict_
 #pragma unroll
         for (int e = 0; e < 16; ++e) if (base + e < n) at(base + e) = r[e];
       };
-      auto local_tail = [&]() {   // steps j = 8, 4, 2, 1 of a level
-#pragma unroll
-        for (int j = 8; j > 0; j >>= 1) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) if (!(e & j)) cexr(e, e | j);
-        }
-      };
-      if (own) {
-        load_block();
-#pragma unroll
-        for (int k = 2; k <= 16; k <<= 1) {   // levels 2..16 entirely in registers
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { const int l = e ^ (k - 1); if (l > e && (e & (k - 1)) < (k >> 1)) cexr(e, l); }
-#pragma unroll
-          for (int j = k >> 2; j > 0; j >>= 1) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) if (!(e & j)) cexr(e, e | j);
-          }
-        }
-        store_block();
-      }
+      if (own) { load_block(); ord_local_presort(r); store_block(); }
       __syncthreads();
       auto cex = [&](int i, int l) {
         if (l < n) {
-          unsigned long long &pa = at(i), &pb = at(l);
-          const unsigned long long a = pa, b = pb;
+          OrdKey &pa = at(i), &pb = at(l);
+          const OrdKey a = pa, b = pb;
           if (a > b) { pa = b; pb = a; }
         }
       };
       for (int k = 32, lk = 5; k <= n2; k <<= 1, ++lk) {
         const int hk = k >> 1;
 #pragma unroll 4
-        for (int q = tid; q < npairs; q += ORD_THREADS) { const int i = ((q >> (lk - 1)) << lk) | (q & (hk - 1)); cex(i, i ^ (k - 1)); }
+        for (int q = tid; q < npairs; q += NT) { const int i = ((q >> (lk - 1)) << lk) | (q & (hk - 1)); cex(i, i ^ (k - 1)); }
         __syncthreads();
         for (int j = k >> 2; j >= 16; j >>= 1) {
 #pragma unroll 4
-          for (int q = tid; q < npairs; q += ORD_THREADS) { const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)); cex(i, i | j); }
+          for (int q = tid; q < npairs; q += NT) { const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)); cex(i, i | j); }
           __syncthreads();
         }
-        if (own) { load_block(); local_tail(); store_block(); }
+        if (own) { load_block(); ord_local_tail(r); store_block(); }
         __syncthreads();
       }
-      for (int i = tid; i < n; i += ORD_THREADS) out[i] = __float_as_int(P[(int) (at(i) & 0xffffffull)].w);
+      for (int i = tid; i < n; i += NT) out[i] = __float_as_int(P[(int) (at(i) & 0xffffffull)].w);
     } else {
       // in place in global memory: `out` holds positions, compared through their keys; same network
-      for (int i = tid; i < n; i += ORD_THREADS) out[i] = i;
+      for (int i = tid; i < n; i += NT) out[i] = i;
       __syncthreads();
       for (int k = 2; (k >> 1) < n; k <<= 1) {
         for (int j = k - 1; j > 0; j = (j == k - 1) ? (k >> 2) : (j >> 1)) {
-          for (int i = tid; i < n; i += ORD_THREADS) {
+          for (int i = tid; i < n; i += NT) {
             const int l = i ^ j;
             if (l > i && l < n) {
               const int pa = out[i], pb = out[l];
@@ -140,8 +179,37 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const float4* __restrict_
           if (j == 0) break;
         }
       }
-      for (int i = tid; i < n; i += ORD_THREADS) out[i] = __float_as_int(P[out[i]].w);
+      for (int i = tid; i < n; i += NT) out[i] = __float_as_int(P[out[i]].w);
     }
+  }
+}
+
+// Classes M and S: every warp on its own, one patch per ticket, keys straight into registers.
+constexpr int ORD_WARP_THREADS = 128;
+__global__ void __launch_bounds__(ORD_WARP_THREADS) k_order_warp(const float4* __restrict__ sorted, WorkQueues wq, int* __restrict__ head, int* __restrict__ part) {
+  static_assert(CLS_M_MAX <= 512, "classes S and M are sorted by one warp per patch (16 keys per lane)");
+  const int lane = threadIdx.x & 31;
+  const int n_m = wq.count[1], total = n_m + wq.count[0];
+  OrdKey r[16];
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(head, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= total) return;
+    const int4 wi = t < n_m ? wq.items[1][t] : wq.items[0][t - n_m];
+    const int n = wi.y;
+    const long long start = work_item_start(wi);
+    const float4* P = sorted + start;
+    const unsigned char* L = wq.labels + start;
+    int* out = part + start;
+    const int base = lane << 4;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const int i = base + e; r[e] = i < n ? order_sort_key(P[i].z, L[i], (unsigned) i) : ~0ull; }
+    int n2 = 16;
+    while (n2 < n) n2 <<= 1;
+    ord_warp_sort(r, n2, lane);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const int i = base + e; if (i < n) out[i] = __float_as_int(P[(int) (r[e] & 0xffffffull)].w); }
   }
 }
 

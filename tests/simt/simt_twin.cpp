@@ -321,7 +321,7 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   std::vector<BinSeg> segs((size_t) nframes * nb_all);
   std::vector<int4> items[NUM_CLASSES];
   for (auto& v : items) v.resize((size_t) nframes * nb + 1);
-  std::vector<int> ctr(2 * NUM_CLASSES + 1, 0);
+  std::vector<int> ctr(2 * NUM_CLASSES + ORD_NUM_HEADS, 0);
   std::vector<unsigned char> labels((size_t) total + 1, 0);
   std::vector<int> counts((size_t) 3 * nframes, 0);
   std::vector<float> centers((size_t) nframes * nb * 3), normals((size_t) nframes * nb * 3);
@@ -382,7 +382,14 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     std::snprintf(buf, sizeof buf, "S=%d M=%d L1=%d L2=%d L3=%d X=%d", ctr[0], ctr[1], ctr[2], ctr[3], ctr[4], ctr[5]);
     t->last_launches = buf;
   }
-  if (t->order) simt::launch("k_order", pg, ORD_THREADS, ORD_SMEM_KEYS * sizeof(unsigned long long), [&] { k_order(sorted.data(), wq, ctr.data() + 2 * NUM_CLASSES, part.data()); });
+  if (t->order) {
+    int* heads = ctr.data() + 2 * NUM_CLASSES;
+    simt::launch("k_order_cta<X>", pg, 512, ord_cta_smem_bytes(512), [&] { k_order_cta<512, 5>(sorted.data(), wq, heads + 0, part.data()); });
+    simt::launch("k_order_cta<L3>", pg, 512, ord_cta_smem_bytes(512), [&] { k_order_cta<512, 4>(sorted.data(), wq, heads + 1, part.data()); });
+    simt::launch("k_order_cta<L2>", pg, 256, ord_cta_smem_bytes(256), [&] { k_order_cta<256, 3>(sorted.data(), wq, heads + 2, part.data()); });
+    simt::launch("k_order_cta<L1>", pg, 128, ord_cta_smem_bytes(128), [&] { k_order_cta<128, 2>(sorted.data(), wq, heads + 3, part.data()); });
+    simt::launch("k_order_warp", pg, ORD_WARP_THREADS, 0, [&] { k_order_warp(sorted.data(), wq, heads + 4, part.data()); });
+  }
   int* d_ng = counts.data();
   int* d_np = counts.data() + nframes;
   int* d_nd = counts.data() + 2 * nframes;
