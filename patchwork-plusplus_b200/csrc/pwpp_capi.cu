@@ -115,7 +115,7 @@ struct pwpp_ctx {
   int hcap = 0;     // history row capacity (doubles)
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
-  int sw_emit_split = 1, sw_front = 1, sw_patch = 0, small_call_frames = 0;
+  int sw_front = 1, sw_patch = 0, small_call_frames = 0;
   bool sw_serial_fit = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
@@ -400,13 +400,9 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   STAGE_MARK();
   if (order_aside) for (int q = 0; q < ORD_NUM_HEADS; ++q) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
   if (max_chunks > 0) {
-    // a bin is copied by `split` warps: 1 for KITTI-sized frames (bins of a few thousand points), 16 for dense sensors whose
-    // 20k..40k-point bins would otherwise be left to one warp each (r02: dense k_emit 1.15 -> 0.14 ms; KITTI 0.33 -> 0.94 ms at 16)
-    const long long mean_pts = (ctx->pt_off[f0 + nf] - ctx->pt_off[f0]) / std::max(nf, 1);
-    const int split = ctx->sw_emit_split > 0 ? ctx->sw_emit_split : (mean_pts > 400000 ? 16 : (nframes <= 8 ? 4 : 1));
-    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, split);
-    if (split > 1) k_emit<true><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
-    else k_emit<false><<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
+    const long long max_pts = (long long) max_chunks * CHUNK_PTS;   // upper bound of the largest frame of the range
+    dim3 grid((unsigned) ((max_pts + (long long) EMIT_TILE * EMIT_WARPS - 1) / ((long long) EMIT_TILE * EMIT_WARPS)), nframes);
+    k_emit<<<grid, EMIT_WARPS * 32, 0, s>>>(ft, ctx->g, nbp, bin_off, fits, segs, ctx->d_part.p, ctx->d_sorted.p, ctx->d_out_idx.p);
     ++ctx->launches;
   }
   STAGE_MARK();
@@ -570,7 +566,6 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   ctx->num_streams = num_streams;
   build_geometry(*params, ctx->g, ctx->ap, ctx->fast_bin);
   ctx->sw_serial_fit = env_int("PWPP_SERIAL_FIT", 0, 0, 1) != 0;       // diagnostic: the fit kernels one after another on the call's stream
-  ctx->sw_emit_split = env_int("PWPP_EMIT_SPLIT", 0, 0, 32);             // 0 = chosen from the frame size
   ctx->sw_front = env_int("PWPP_FRONT", PWPP_FRONT_DEFAULT, 0, 1);        // 1: cluster-per-frame front end, 0: k_bin_hist + k_bin_scan + k_scatter
   ctx->sw_patch = env_int("PWPP_FIT_PATCH", PWPP_FIT_PATCH_DEFAULT, 0, 1);   // 1: patches above 512 points on k_fit_patch
   ctx->sw_graph = env_int("PWPP_GRAPH", 1, 0, 1);

@@ -591,58 +591,77 @@ __global__ void __launch_bounds__(32) k_gle(FrameTable ft, StreamState* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_emit: grid (chunks, F): one thread per sorted position; copies every patch's ground / non-ground part to its
-// place in the final index lists (addCloud S:28-31 + toIndices S:18-26). Fitted patches were partitioned by the fit
-// kernels (part[]: ground ascending, then non-ground ascending); patches that were not fitted (below num_min_pts,
-// RNR hits, out-of-range points) are emitted straight from the sorted array in ascending point index.
-constexpr int EMIT_WARPS = 8;     // bins per CTA: every warp copies the two parts of one bin, big bins are split
+// k_emit: copies every patch's ground / non-ground part to its place in the final index lists (addCloud S:28-31 + toIndices
+// S:18-26). Fitted patches were partitioned by the fit kernels (part[]: ground part, then non-ground part); patches that were not
+// fitted (below num_min_pts, RNR hits, out-of-range points) are emitted straight from the sorted array in ascending point index.
+// The ground part and the non-ground part of a bin are contiguous both in `part` / `sorted` and in the output lists.
+// The work is cut by POSITION, not by bin: every warp owns EMIT_TILE consecutive positions of a
+// frame's bin-sorted order, finds the bin of its first position (32-ary search over the bin offsets: two round trips for 507 bins),
+// then walks the bins 32 at a time — offsets, destinations and ground counts of a window are loaded lane-parallel and broadcast by
+// shuffles — and copies the intersection of every bin with its tile, four loads in flight per lane. All warps do the same amount of
+// copying whatever the bin sizes are. r02 (profiles/r02/ab8_emit_tiles_front_l2.log) against the first form, one warp per bin (most
+// warps owned a tiny bin and spent their time in the three dependent loads before the copy loop; the 20k..40k-point bins of a dense
+// frame had to be split over 16 warps): 0.327 -> 0.240 ms per 1024 KITTI frames, 0.135 -> 0.078 ms per 32 dense frames.
+constexpr int EMIT_WARPS = 8;
+constexpr int EMIT_TILE = 1024;
 
-// One warp per (frame, bin): the ground part and the non-ground part of a bin are contiguous both in `part` /
-// `sorted` and in the output lists, so the copy is two coalesced streams (typical bins: a few to a few thousand
-// points; a pathological bin holding a whole frame is copied by one warp, which is slow but correct).
-template <bool SPLIT>
 __global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit(FrameTable ft, Geometry g, int nbp, const int* __restrict__ bin_off, const BinFit* __restrict__ fits,
-                                                          const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
-                                                          int* __restrict__ out_idx) {
+                                                                const BinSeg* __restrict__ segs, const int* __restrict__ part, const float4* __restrict__ sorted,
+                                                                int* __restrict__ out_idx) {
   const int f = blockIdx.y;
-  const int nb_all = g.nbins + PW_NUM_PSEUDO;
-  const int b = blockIdx.x * EMIT_WARPS + (threadIdx.x >> 5);
-  if (b >= nb_all) return;
   const int lane = lane_id();
   const long long p0 = ft.pt_off[f];
+  const int n = (int) (ft.pt_off[f + 1] - p0);
+  const int w0 = (blockIdx.x * EMIT_WARPS + (threadIdx.x >> 5)) * EMIT_TILE;
+  if (w0 >= n) return;
+  const int w1 = min(n, w0 + EMIT_TILE);
+  const int nb_all = g.nbins + PW_NUM_PSEUDO;
   const int* bo = bin_off + (size_t) f * (nbp + 1);
-  const int off = bo[b], nbin = bo[b + 1] - off;
-  if (nbin == 0) return;
-  const BinSeg sg = segs[(size_t) f * nb_all + b];
-  int ng = -1;
-  if (b < g.nbins) { const BinFit& r = fits[(size_t) f * g.nbins + b]; if (r.fitted) ng = r.n_ground; }
-  // gridDim.z > 1 (PWPP_EMIT_SPLIT): a bin is copied in gridDim.z slices of at least 1024 entries, so that the 20k..40k-point
-  // bins of a dense frame are not left to one warp each (r01: k_emit is 28 % of a dense step, 5 % of a KITTI step)
-  int j0 = 0, j1 = nbin;
-  if (SPLIT && gridDim.z > 1) {
-    int seg = (nbin + (int) gridDim.z - 1) / (int) gridDim.z;
-    seg = (seg + 127) & ~127;
-    if (seg < 1024) seg = 1024;
-    j0 = (int) blockIdx.z * seg;
-    if (j0 >= nbin) return;
-    j1 = j0 + seg < nbin ? j0 + seg : nbin;
+  // largest b with bo[b] <= w0: the bin that holds position w0 (empty bins share their offset with the next bin)
+  int lo = 0, hi = nb_all;
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) >> 5;
+    const int q = lo + lane * step;
+    const bool le = q < hi && bo[q] <= w0;
+    const unsigned m = __ballot_sync(0xffffffffu, le);   // lane 0 probes lo itself, whose offset is <= w0: m is never empty
+    const int k = 31 - __clz(m);
+    lo += k * step;
+    hi = min(hi, lo + step);
   }
-  if (ng >= 0) {
-    const int* src = part + p0 + off;
-    for (int j = j0 + lane; j < j1; j += 128) {   // four independent loads in flight per lane
-      int v[4];
+  for (int bb = lo; bb < nb_all; bb += 32) {
+    const int b = bb + lane;
+    const bool valid = b < nb_all;
+    const int off = valid ? bo[b] : n, end = valid ? bo[b + 1] : n;
+    const bool need = valid && end > off && off < w1 && end > w0;
+    int g_dst = -1, ng_dst = -1, ng = -1;
+    if (need) {
+      const BinSeg sg = segs[(size_t) f * nb_all + b];
+      g_dst = sg.g_dst; ng_dst = sg.ng_dst;
+      if (b < g.nbins) { const BinFit& r = fits[(size_t) f * g.nbins + b]; if (r.fitted) ng = r.n_ground; }
+    }
+    for (unsigned m = __ballot_sync(0xffffffffu, need); m; m &= m - 1) {
+      const int l = __ffs(m) - 1;
+      const int o = __shfl_sync(0xffffffffu, off, l), e = __shfl_sync(0xffffffffu, end, l);
+      const int gd = __shfl_sync(0xffffffffu, g_dst, l), nd = __shfl_sync(0xffffffffu, ng_dst, l), ngr = __shfl_sync(0xffffffffu, ng, l);
+      const int j0 = max(o, w0), j1 = min(e, w1);
+      if (ngr >= 0) {
+        const int* src = part + p0;
+        for (int j = j0 + lane; j < j1; j += 128) {   // four independent loads in flight per lane
+          int v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int jj = j + 32 * u; v[u] = src[jj < j1 ? jj : j1 - 1]; }
+          for (int u = 0; u < 4; ++u) { const int jj = j + 32 * u; v[u] = src[jj < j1 ? jj : j1 - 1]; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int jj = j + 32 * u;
-        if (jj < j1) out_idx[p0 + ((jj < ng) ? (sg.g_dst + jj) : (sg.ng_dst + (jj - ng)))] = v[u];
+          for (int u = 0; u < 4; ++u) {
+            const int jj = j + 32 * u, rel = jj - o;
+            if (jj < j1) out_idx[p0 + ((rel < ngr) ? (gd + rel) : (nd + (rel - ngr)))] = v[u];
+          }
+        }
+      } else if (nd >= 0) {   // not fitted: everything to the non-ground list (nd < 0: dropped points, S:591)
+        const float4* src = sorted + p0;
+        for (int j = j0 + lane; j < j1; j += 32) out_idx[p0 + nd + (j - o)] = __float_as_int(src[j].w);
       }
     }
-  } else {
-    if (sg.ng_dst < 0) return;  // dropped points (S:591)
-    const float4* src = sorted + p0 + off;
-    for (int j = j0 + lane; j < j1; j += 32) out_idx[p0 + sg.ng_dst + j] = __float_as_int(src[j].w);
+    if (__ballot_sync(0xffffffffu, valid && off >= w1)) break;   // the window reached the end of the tile
   }
 }
 

@@ -247,7 +247,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // switches (the PWPP_* environment switches of pwpp_create)
-  int persistent_ctas = 2, emit_split = 1, front = 1, patch = 0, order = 0;
+  int persistent_ctas = 2, front = 1, patch = 0, order = 0;
   std::string last_launches;
 };
 
@@ -278,7 +278,6 @@ int simt_set_option(void* h, const char* name, int v) {
   SimtTwin* t = (SimtTwin*) h;
   const std::string n(name);
   if (n == "persistent_ctas") t->persistent_ctas = v;
-  else if (n == "emit_split") t->emit_split = v;
   else if (n == "front") t->front = v;
   else if (n == "patch") t->patch = v;
   else if (n == "order") t->order = v;
@@ -400,9 +399,9 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
     });
   }
   if (max_chunks > 0) {
-    dim3 grid((nb_all + EMIT_WARPS - 1) / EMIT_WARPS, nframes, t->emit_split);
-    if (t->emit_split > 1) simt::launch("k_emit<split>", grid, EMIT_WARPS * 32, 0, [&] { k_emit<true>(ft, g, nbp, bin_off.data(), fits.data(), segs.data(), part.data(), sorted.data(), out_idx.data()); });
-    else simt::launch("k_emit", grid, EMIT_WARPS * 32, 0, [&] { k_emit<false>(ft, g, nbp, bin_off.data(), fits.data(), segs.data(), part.data(), sorted.data(), out_idx.data()); });
+    const long long max_pts = (long long) max_chunks * CHUNK_PTS;
+    dim3 grid((unsigned) ((max_pts + (long long) EMIT_TILE * EMIT_WARPS - 1) / ((long long) EMIT_TILE * EMIT_WARPS)), nframes);
+    simt::launch("k_emit", grid, EMIT_WARPS * 32, 0, [&] { k_emit(ft, g, nbp, bin_off.data(), fits.data(), segs.data(), part.data(), sorted.data(), out_idx.data()); });
   }
   for (int f = 0; f < nframes; ++f) {
     FrameOut& o = t->out[f];

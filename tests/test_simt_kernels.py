@@ -70,7 +70,7 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(front=0), dict(patch=1), dict(front=0, patch=1), dict(emit_split=8), dict(order=1)])
+@pytest.mark.parametrize("opts", [dict(front=0), dict(patch=1), dict(front=0, patch=1), dict(order=1)])
 def test_kernel_switches(kitti, opts):
     """The remaining switches (PWPP_FRONT=0: the three stand-alone front-end kernels instead of the cluster kernel;
     PWPP_FIT_PATCH=1: k_fit_patch for the patches above 512 points; the emit split; reference order) give the oracle's result."""
@@ -115,7 +115,7 @@ def _big_patch_cases():
     }
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(emit_split=5), dict(order=1)])
+@pytest.mark.parametrize("opts", [dict(), dict(order=1)])
 def test_big_patches(opts):
     """Class X (more than 8192 points in one patch): k_fit_big, including
     the tie-heavy selections that overflow the candidate buffer and an R-VPF wall removal in zone 0."""
@@ -170,7 +170,7 @@ def test_edge_cases():
                                      np.c_[3 + rng.random(3000) * 6, rng.random(3000) * 1.5, -1.7 + rng.normal(0, 0.02, 3000), rng.random(3000)]].astype(np.float32),
     }
     names = list(cases)
-    for opts in (dict(), dict(patch=1, emit_split=3, front=0)):
+    for opts in (dict(), dict(patch=1, front=0)):
         tw = SimtTwin(num_streams=len(names), **opts)
         tw.estimate_multi([cases[k] for k in names])
         for f, k in enumerate(names):
@@ -201,7 +201,8 @@ def test_random_parameter_sets(kitti, seed):
     p.uprightness_thr = float(rng.choice([0.101, 0.5, 0.707, 0.95]))
     p.num_sectors_each_zone[:] = [int(x) for x in rng.choice([1, 4, 8, 16, 32, 54, 64, 128, 200], 4)]
     p.num_rings_each_zone[:] = [int(x) for x in rng.integers(1, 9, 4)]
-    opts = dict(emit_split=int(rng.choice([1, 3, 8])), front=int(rng.integers(0, 2)), patch=int(rng.integers(0, 2)))
+    rng.choice([1, 3, 8]); rng.integers(0, 2)   # (two draws kept so that the parameter sets below stay the ones of the earlier runs)
+    opts = dict(front=int(rng.integers(0, 2)), patch=int(rng.integers(0, 2)))
     cols = 4 if rng.random() < 0.8 else 3
     pool = [kitti[0], kitti[4], synth.make_frame(7, 0).numpy()]
     orc, tw = O.Oracle(p, O.ARITH_CANON64), SimtTwin(p, **opts)
@@ -242,7 +243,7 @@ def test_mutated_inputs(kitti, seed):
         a[:, :3] *= np.float32(rng.choice([0.5, 2.0]))
     if rng.random() < 0.3:
         a = a[rng.permutation(len(a))]
-    opts = dict(front=int(rng.integers(0, 2)), patch=int(rng.integers(0, 2)), emit_split=int(rng.choice([1, 4])))
+    opts = dict(front=int(rng.integers(0, 2)), patch=int(rng.integers(0, 2)))
     orc, ref, tw = O.Oracle(arith=O.ARITH_CANON64), O.Oracle(arith=O.ARITH_REF32), SimtTwin(**opts)
     orc.estimate(a); ref.estimate(a); tw.estimate(a)
     ids = orc.bin_ids()
