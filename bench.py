@@ -518,8 +518,8 @@ def run_ours(args):
                        "note": "k_order on: ground part of every patch in ascending z, then the R-VPF removals per iteration and the final rejects, each in ascending z (S:199, S:264-284)"}
 
     # real scans: the six KITTI fixture scans of tests/golden/ cycled to a batch of F frames (fresh state per frame, device-resident,
-    # native emission order) — the synthetic generator is denser near the sensor than KITTI (zone-0 share 0.65-0.76 vs 0.63-0.65,
-    # largest bin up to 7.9k vs 5.6k points: tests/test_generator.py), so this is the number to expect on recorded data
+    # native emission order): the number to expect on recorded data. The synthetic generator differs from KITTI in both directions
+    # (denser near the sensor and larger bins, but fewer points per frame and less vertical structure: tests/test_generator.py)
     real, rms = None, -1.0
     if not args.no_extras and args.sensor == "kitti64":
         try:
@@ -546,6 +546,7 @@ def run_ours(args):
                     rstep()
                 r1.record(); torch.cuda.synchronize()
                 rms = r0.elapsed_time(r1) / 5
+                reng.set_profiling(True); rstep(); rstage = merge_front_stages(reng.stage_times_ms()); reng.set_profiling(False)
                 assert reng.num_ground(7) + reng.num_nonground(7) == sizes[7]
                 rground = float(np.mean([reng.num_ground(f) / sizes[f] for f in range(6)]))
                 reng.close(); del rpts, dscans
@@ -554,7 +555,7 @@ def run_ours(args):
         rms = dist.max_over_ranks(rms)
         if real is None and rms > 0:
             real = {"frames_per_gpu": F, "mean_points": float(roffs_np[-1]) / F, "ms_per_step": rms, "value": world * F / (rms / 1e3), "unit": UNIT,
-                    "ground_fraction": rground, "whole_path_frac": (ALGO_BYTES_PER_POINT * float(roffs_np[-1]) / (rms / 1e3) / 1e9) / peak,
+                    "ground_fraction": rground, "whole_path_frac": (ALGO_BYTES_PER_POINT * float(roffs_np[-1]) / (rms / 1e3) / 1e9) / peak, "stage_ms": rstage,
                     "workload": f"batch={F}: the six recorded KITTI scans of tests/golden/ cycled, fresh state per frame, device-resident"}
 
     # single-frame latency of the drop-in C++ class (BASELINE config 2): examples/pwpp_latency.cpp on the first fixture scan

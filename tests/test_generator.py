@@ -4,9 +4,10 @@ bins below 10 points (the six recorded KITTI scans of tests/golden/ measure 0.55
 4.9k-5.6k and 0.46-0.50). The generator follows the survey's construction (64 beams x 2083 azimuth steps ray-cast against a tilted
 ground plane and 20-40 boxes / walls / poles) and is DENSER near the sensor and more varied than the recorded scans: zone-0 share
 0.65-0.76 on ordinary frames, largest bin up to ~8k points (the recorded scans stop at 5.6k), a frame in a walled court now and then.
-That over-weights the largest patch-size classes — the slowest ones of the CUDA path — so the synthetic batch is the conservative
-workload; bench.py reports the recorded scans beside it (`kitti_scans`). This test pins the statistics so that a change of the generator
-cannot silently make the benchmark easier."""
+That over-weights the largest patch-size classes; on the other hand the recorded scans carry 6 % more points per frame and more
+vertical structure near the sensor (more R-VPF rounds), and measure SLOWER on the CUDA path than the synthetic batch (r02: 6.7 vs 5.3 ms
+per 1024 frames) — bench.py therefore reports the recorded scans beside the synthetic batch (`kitti_scans`). This test pins the
+statistics so that a change of the generator cannot silently make the benchmark easier."""
 import numpy as np
 
 import oracle_py as O
