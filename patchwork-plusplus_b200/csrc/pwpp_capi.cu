@@ -626,6 +626,10 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     ctx->fit[3] = {k_fit_cta<4096, 3, 3, 8, true, true>, 0, FIT_THREADS, sm_l2};
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
     ctx->fit[5] = {k_fit_big<16, 1, true>, 0, 512, 0};
+    const int warp_pls = env_int("PWPP_WARP_PLS", PWPP_WARP_PLS_DEFAULT, 0, 7);
+    if (warp_pls & 1) ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
+    if (warp_pls & 2) ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 3, false, true>, 0, FITW_WARPS * 32, 0};
+    if (warp_pls & 4) ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 4, false, true>, 0, FITW_WARPS * 32, 0};
     if (ctx->sw_patch) {
       ctx->fit[2] = {k_fit_patch<4, 4, 2>, 0, 4 * 32, (size_t) 4 * FP_STG * sizeof(float4)};
       ctx->fit[3] = {k_fit_patch<8, 2, 3>, 0, 8 * 32, (size_t) 8 * FP_STG * sizeof(float4)};

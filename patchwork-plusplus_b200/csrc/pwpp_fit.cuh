@@ -1037,7 +1037,10 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   return lpr;
 }
 
-template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false>
+// PLS: the current plane and the running moment sums of a warp's patch live in shared memory (160 B per warp) instead of ~40
+// registers per lane: the passes only need the plane as four floats (PlaneF), the doubles are read in the rare exact distance
+// test and by the solve. That is what lets the kernel run at 3 CTAs per SM (85 registers) without spilling.
+template <bool STAGE, int CLS_HI, int CLS_LO, int U, int MINB, bool FUSE = false, bool PLS = false>
 __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4* __restrict__ sorted, FrameTable ft, const StreamState* __restrict__ states,
                                                                              Geometry g, AlgoParams ap, int nbp, const int* __restrict__ bin_off, WorkQueues wq,
                                                                              int* __restrict__ part, BinFit* __restrict__ fits) {
@@ -1045,6 +1048,9 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
   __shared__ unsigned s_alive[FITW_WARPS][CAP / 32];
   __shared__ unsigned s_member[FITW_WARPS][CAP / 32];
   __shared__ float s_sel[FITW_WARPS][128];
+  __shared__ Plane s_pl[PLS ? FITW_WARPS : 1];
+  __shared__ Moments s_tot[PLS ? FITW_WARPS : 1];
+  static_assert(!(PLS && FUSE), "the fused seed round keeps two planes in registers");
   PW_DYN_SHARED(float4, s_stage);              // STAGE: [FITW_WARPS][CLS_M_MAX]
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const unsigned lt = lanemask_lt();
@@ -1104,14 +1110,23 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
     double c[3] = {(double) first.x, (double) first.y, 0.0};   // reference point of all moment sums of this patch
 
     bool have_plane = false, any_removed = false;
-    Plane pl;
-    pl.d = 0.0;
+    Plane pl_reg;
+    Plane& pl = PLS ? s_pl[warp] : pl_reg;
+    // PLS: every lane computes the same plane / sums; lane 0 stores them, a __syncwarp() publishes them
+    auto set_plane = [&](const Plane& t) { if (!PLS) pl_reg = t; else { __syncwarp(); if (lane == 0) s_pl[warp] = t; __syncwarp(); } };
+    {
+      Plane z;
+      z.d = 0.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { pl.mean[q] = 0.0; pl.normal[q] = 0.0; pl.sv[q] = 0.0; }
+      for (int q = 0; q < 3; ++q) { z.mean[q] = 0.0; z.normal[q] = 0.0; z.sv[q] = 0.0; }
+      set_plane(z);
+    }
 
     // ---- seed rounds: R-VPF iterations (zone 0 only; for other zones the R-VPF fit is dead code, see k_fit_stream)
     //      followed by the R-GPF seed fit (S:484-514). Each is a selection pass + a full accumulation pass. ----
-    Moments tot;   // running sums of the current member set (valid after the last seed round)
+    Moments tot_reg;   // running sums of the current member set (valid after the last seed round)
+    Moments& tot = PLS ? s_tot[warp] : tot_reg;
+    auto set_tot = [&](const Moments& t) { if (!PLS) tot_reg = t; else { __syncwarp(); if (lane == 0) s_tot[warp] = t; __syncwarp(); } };
     int rvpf_left = (ap.enable_RVPF && zone0) ? ap.num_iter : 0;
     // FUSE: an R-VPF round that removes nothing is followed by the R-GPF seed fit over the SAME alive set with the
     // same margin, hence the same LPR height (S:84-103 depend on nothing else); its seed set {z < lpr + th_seeds} is a
@@ -1204,12 +1219,12 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
         if (m.n > 0) { pl = bcast(0); have_plane = true; }     // the R-VPF fit (S:486); S:49 keeps the previous plane otherwise
         if (!(have_plane && pl.normal[2] < ap.uprightness_thr)) {   // S:506 break: nothing removed, the seed fit follows
           if (mi.n > 0) { pl = bcast(16); have_plane = true; }  // S:513-514 on the same alive set
-          tot = mi;
+          set_tot(mi);
           break;
         }
       } else {
-        if (m.n > 0) { plane_from_moments(m, c, pl); have_plane = true; }   // S:49: an empty set keeps the previous plane
-        tot = m;
+        if (m.n > 0) { Plane t; plane_from_moments(m, c, t); set_plane(t); have_plane = true; }   // S:49: an empty set keeps the previous plane
+        set_tot(m);
         if (!rvpf_round) break;
       }
       if (have_plane && pl.normal[2] < ap.uprightness_thr) {   // S:489: remove the vertical structure, iterate
@@ -1275,12 +1290,16 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
         }
       }
       if (changed_any == 0) break;   // fixpoint: every later iteration would reproduce this set and this plane
+      {
+        Moments t = tot;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) tot.s1[q] += warp_sum(dm.s1[q]);
+        for (int q = 0; q < 3; ++q) t.s1[q] += warp_sum(dm.s1[q]);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) tot.s2[q] += warp_sum(dm.s2[q]);
-      tot.n += warp_sum_i(dm.n);
-      if (tot.n > 0) plane_from_moments(tot, c, pl);   // S:49 otherwise
+        for (int q = 0; q < 6; ++q) t.s2[q] += warp_sum(dm.s2[q]);
+        t.n += warp_sum_i(dm.n);
+        set_tot(t);
+        if (t.n > 0) { Plane np; plane_from_moments(t, c, np); set_plane(np); }   // S:49 otherwise
+      }
       __syncwarp();
     }
     const int n_ground = have_plane ? tot.n : 0;
