@@ -614,22 +614,18 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
     // Fit kernel of every patch-size class (launch shapes from the r01 / r02 measurements, profiles/):
     //   S  <= 64      k_fit_resident: 8 lanes x 8 register slots per patch
-    //   M  <= 512     k_fit_warp, patch staged in shared memory
-    //   L1 <= 2048    k_fit_warp streaming from L2            | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
+    //   M  <= 512     k_fit_warp, patch staged in shared memory, plane + moment sums in shared memory, 3 CTAs/SM (r02: 0.72 -> 0.68 ms)
+    //   L1 <= 2048    k_fit_warp streaming from L2, the same  (0.83 -> 0.76 ms; 4 CTAs/SM at 64 registers: 0.81)  | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
     //   L2 <= 4096    k_fit_cta, plane in shared memory, 3/SM |                   4 / 8 / 16 warps
     //   L3 <= 8192    k_fit_cta, 2 CTAs/SM                    |
     //   X  >  8192    k_fit_big (dense sensors)
     const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
     ctx->fit[0] = {k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
-    ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 2>, 0, FITW_WARPS * 32, sm_m};
-    ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 2>, 0, FITW_WARPS * 32, 0};
+    ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
+    ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 3, false, true>, 0, FITW_WARPS * 32, 0};
     ctx->fit[3] = {k_fit_cta<4096, 3, 3, 8, true, true>, 0, FIT_THREADS, sm_l2};
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
     ctx->fit[5] = {k_fit_big<16, 1, true>, 0, 512, 0};
-    const int warp_pls = env_int("PWPP_WARP_PLS", PWPP_WARP_PLS_DEFAULT, 0, 7);
-    if (warp_pls & 1) ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
-    if (warp_pls & 2) ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 3, false, true>, 0, FITW_WARPS * 32, 0};
-    if (warp_pls & 4) ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 4, false, true>, 0, FITW_WARPS * 32, 0};
     if (ctx->sw_patch) {
       ctx->fit[2] = {k_fit_patch<4, 4, 2>, 0, 4 * 32, (size_t) 4 * FP_STG * sizeof(float4)};
       ctx->fit[3] = {k_fit_patch<8, 2, 3>, 0, 8 * 32, (size_t) 8 * FP_STG * sizeof(float4)};

@@ -972,15 +972,24 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   bool fallback = num_lpr > 32;
   double lpr = 0.0;
   if (!fallback) {
+    // (both scans: LPR_U loads in flight per lane — for class L1 the patch streams from L2 and these two loops were the kernel's
+    // top long-scoreboard sites in the r02 profile, one dependent round trip per 32 points)
+    constexpr int LPR_U = 8;
     unsigned kminL = 0xffffffffu;
     int nv = 0;
-    for (int it = 0; it < nit; ++it) {
-      const int j = it * 32 + lane;
-      bool valid = j < n;
-      const float z = P[j < n ? j : n - 1].z;
-      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
-      if (zone0 && ((double) z < margin_z)) valid = false;
-      if (valid) { kminL = min(kminL, order_key(z)); ++nv; }
+    for (int it0 = 0; it0 < nit; it0 += LPR_U) {
+      float zb[LPR_U];
+#pragma unroll
+      for (int u = 0; u < LPR_U; ++u) { const int j = (it0 + u) * 32 + lane; zb[u] = P[j < n ? j : n - 1].z; }
+#pragma unroll
+      for (int u = 0; u < LPR_U; ++u) {
+        const int it = it0 + u, j = it * 32 + lane;
+        bool valid = j < n;
+        const float z = zb[u];
+        if (any_removed && it < nit) valid = valid && ((alive_w[it] >> lane) & 1u);
+        if (zone0 && ((double) z < margin_z)) valid = false;
+        if (valid) { kminL = min(kminL, order_key(z)); ++nv; }
+      }
     }
     const int nvalid = __reduce_add_sync(0xffffffffu, nv);
     const int target = nvalid < num_lpr ? nvalid : num_lpr;
@@ -993,17 +1002,23 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
       T = kth_key(gmn, gmx, target, [&](unsigned cand) { return __reduce_add_sync(0xffffffffu, kminL < cand ? 1 : 0); });
     }
     int cc = 0;
-    for (int it = 0; it < nit; ++it) {
-      const int j = it * 32 + lane;
-      bool valid = j < n;
-      const float z = P[j < n ? j : n - 1].z;
-      if (any_removed) valid = valid && ((alive_w[it] >> lane) & 1u);
-      if (zone0 && ((double) z < margin_z)) valid = false;
-      const unsigned key = order_key(z);
-      const bool c = valid && key <= T;
-      const unsigned bal = __ballot_sync(0xffffffffu, c);
-      if (c) { const int pos = cc + __popc(bal & lt); if (pos < 128) cbuf[pos] = key; }
-      cc += __popc(bal);
+    for (int it0 = 0; it0 < nit; it0 += LPR_U) {
+      float zb[LPR_U];
+#pragma unroll
+      for (int u = 0; u < LPR_U; ++u) { const int j = (it0 + u) * 32 + lane; zb[u] = P[j < n ? j : n - 1].z; }
+#pragma unroll
+      for (int u = 0; u < LPR_U; ++u) {
+        const int it = it0 + u, j = it * 32 + lane;
+        bool valid = j < n;
+        const float z = zb[u];
+        if (any_removed && it < nit) valid = valid && ((alive_w[it] >> lane) & 1u);
+        if (zone0 && ((double) z < margin_z)) valid = false;
+        const unsigned key = order_key(z);
+        const bool c = valid && key <= T;
+        const unsigned bal = __ballot_sync(0xffffffffu, c);
+        if (c) { const int pos = cc + __popc(bal & lt); if (pos < 128) cbuf[pos] = key; }
+        cc += __popc(bal);
+      }
     }
     __syncwarp();
     if (cc <= 128) {
@@ -1307,20 +1322,27 @@ __global__ void __launch_bounds__(FITW_WARPS * 32, MINB) k_fit_warp(const float4
     // stable partition: ground indices ascending, then non-ground indices ascending
     {
       int g_run = 0, ng_run = 0;
-      for (int it = 0; it < nit; ++it) {
-        const int j = it * 32 + lane;
-        const bool v = j < n;
-        const unsigned bg = have_plane ? member_w[it] : 0u;
-        const unsigned bv = __ballot_sync(0xffffffffu, v);
-        const unsigned bn = bv & ~bg;
-        if (v) {
-          const int idx = __float_as_int(P[j].w);
-          if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idx;
-          else out[n_ground + ng_run + __popc(bn & lt)] = idx;
-          if (wq.labels) { const bool isg = (bg >> lane) & 1u; if (isg || !any_removed || ((alive_w[it] >> lane) & 1u)) wq.labels[start + j] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT; }
+      for (int it0 = 0; it0 < nit; it0 += U) {   // U index loads in flight per lane
+        int idxb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int j = (it0 + u) * 32 + lane; idxb[u] = __float_as_int(P[j < n ? j : n - 1].w); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int it = it0 + u, j = it * 32 + lane;
+          if (it >= nit) break;
+          const bool v = j < n;
+          const unsigned bg = have_plane ? member_w[it] : 0u;
+          const unsigned bv = __ballot_sync(0xffffffffu, v);
+          const unsigned bn = bv & ~bg;
+          if (v) {
+            const int idx = idxb[u];
+            if ((bg >> lane) & 1u) out[g_run + __popc(bg & lt)] = idx;
+            else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+            if (wq.labels) { const bool isg = (bg >> lane) & 1u; if (isg || !any_removed || ((alive_w[it] >> lane) & 1u)) wq.labels[start + j] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT; }
+          }
+          g_run += __popc(bg);
+          ng_run += __popc(bn);
         }
-        g_run += __popc(bg);
-        ng_run += __popc(bn);
       }
     }
     if (lane == 0) {

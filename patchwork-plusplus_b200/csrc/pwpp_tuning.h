@@ -5,4 +5,3 @@
 #define PWPP_FRONT_DEFAULT 1       /* 1: cluster-per-frame front end (pwpp_front.cuh); 0: k_bin_hist + k_bin_scan + k_scatter */
 #define PWPP_FIT_PATCH_DEFAULT 0   /* 1: patches above 512 points on k_fit_patch (pwpp_fit_patch.cuh) instead of k_fit_warp<L1> / k_fit_cta */
 #define PWPP_SMALL_CALL_DEFAULT 4  /* calls of at most this many frames: CTA-per-patch fit kernels above 512 points and the three stand-alone front-end kernels (latency path) */
-#define PWPP_WARP_PLS_DEFAULT 0    /* bit 0: class M, bit 1: class L1 on k_fit_warp with plane + moment sums in shared memory at 3 CTAs per SM */

@@ -247,7 +247,7 @@ struct SimtTwin {
   std::vector<FrameOut> out;
   int sel = 0;
   // switches (the PWPP_* environment switches of pwpp_create)
-  int persistent_ctas = 2, front = 1, patch = 0, order = 0, warp_pls = 0;
+  int persistent_ctas = 2, front = 1, patch = 0, order = 0;
   std::string last_launches;
 };
 
@@ -279,7 +279,6 @@ int simt_set_option(void* h, const char* name, int v) {
   const std::string n(name);
   if (n == "persistent_ctas") t->persistent_ctas = v;
   else if (n == "front") t->front = v;
-  else if (n == "warp_pls") t->warp_pls = v;
   else if (n == "patch") t->patch = v;
   else if (n == "order") t->order = v;
   else return -1;
@@ -369,11 +368,9 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   } else {
     simt::launch("k_fit_cta<8192,4,2,8,fuse>", pg, FIT_THREADS, sm_l3, [&] { k_fit_cta<8192, 4, 2, 8, true>(FIT_ARGS); });
     simt::launch("k_fit_cta<4096,3,3,8,fuse,pls>", pg, FIT_THREADS, sm_l2, [&] { k_fit_cta<4096, 3, 3, 8, true, true>(FIT_ARGS); });
-    if (t->warp_pls & 2) simt::launch("k_fit_warp<false,2,2,pls>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 3, false, true>(FIT_ARGS); });
-    else simt::launch("k_fit_warp<false,2,2>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 2>(FIT_ARGS); });
+    simt::launch("k_fit_warp<false,2,2,pls>", pg, FITW_WARPS * 32, 0, [&] { k_fit_warp<false, 2, 2, FITW_U, 3, false, true>(FIT_ARGS); });
   }
-  if (t->warp_pls & 1) simt::launch("k_fit_warp<true,1,1,pls>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 3, false, true>(FIT_ARGS); });
-  else simt::launch("k_fit_warp<true,1,1>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 2>(FIT_ARGS); });
+  simt::launch("k_fit_warp<true,1,1,pls>", pg, FITW_WARPS * 32, sm_m, [&] { k_fit_warp<true, 1, 1, 2, 3, false, true>(FIT_ARGS); });
   simt::launch("k_fit_resident<8,8,0>", pg, FIT_THREADS, 0, [&] { k_fit_resident<8, 8, 0, 2>(FIT_ARGS); });
   simt::launch("k_fit_big<16,1,fuse>", pg, 512, 0, [&] { k_fit_big<16, 1, true>(FIT_ARGS); });
 #undef FIT_ARGS

@@ -70,7 +70,7 @@ def test_batched_call_with_mixed_frames(kitti):
         _check(orc, tw, a, f"batch/{f}", allow_degenerate=True)
 
 
-@pytest.mark.parametrize("opts", [dict(front=0), dict(patch=1), dict(front=0, patch=1), dict(order=1), dict(warp_pls=3)])
+@pytest.mark.parametrize("opts", [dict(front=0), dict(patch=1), dict(front=0, patch=1), dict(order=1)])
 def test_kernel_switches(kitti, opts):
     """The remaining switches (PWPP_FRONT=0: the three stand-alone front-end kernels instead of the cluster kernel;
     PWPP_FIT_PATCH=1: k_fit_patch for the patches above 512 points; the emit split; reference order) give the oracle's result."""
