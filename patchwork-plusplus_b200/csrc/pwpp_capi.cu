@@ -105,6 +105,8 @@ struct FitLaunch {
   size_t smem = 0;
 };
 
+constexpr int NUM_SIDE = 6;
+
 struct pwpp_ctx {
   pwpp_params prm;
   Geometry g;
@@ -121,8 +123,8 @@ struct pwpp_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
   bool call_times_valid = false;
   cudaEvent_t stage_ev[PWPP_NUM_STAGES + 1] = {};
-  cudaStream_t side[5] = {};              // side streams of the concurrent fit kernels
-  cudaEvent_t ev_fork = nullptr, ev_join[5] = {};
+  cudaStream_t side[NUM_SIDE] = {};       // one side stream per patch-size class: its fit kernel, then its sort (reference order)
+  cudaEvent_t ev_fork = nullptr, ev_fit[NUM_SIDE] = {}, ev_join[NUM_SIDE] = {};
   bool profiling = false, stage_valid = false;
   long long launches = 0;
 
@@ -345,50 +347,52 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     k.fn<<<grid, k.threads, k.smem, st>>>(FIT_ARGS);
     ++ctx->launches;
   };
-  if (prof || serial_fit) {
+  // reference emission order inside every fitted patch (pwpp_order.cuh): one launch per class (X, L3, L2, L1 with a CTA sized to the
+  // class; M + S one warp per patch). A sort only permutes `part` inside the patches of its own class, so it runs on its class's
+  // side stream right behind the fit kernel, beside the other classes' fits and beside k_gle (which only reads the patch records);
+  // k_emit joins everything. On a one-frame call the sort of the largest patch (~50 us) and the ring walk of k_gle (~50 us) are
+  // both pure latency.
+  int* heads = ctx->d_wq_ctr.p + 2 * NUM_CLASSES;
+  auto launch_order = [&](int q, cudaStream_t so) {   // q: 0 = X, 1 = L3, 2 = L2, 3 = L1, 4 = M + S
+    const int grid = (int) std::min<long long>(ctx->order_k[q].grid, std::max<long long>(1, (long long) nframes * (q == 4 ? 64 : 32)));
+    const int th = ctx->order_k[q].threads;
+    const size_t sm = ctx->order_k[q].smem;
+    switch (q) {
+      case 0: k_order_cta<512, 5><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+      case 1: k_order_cta<512, 4><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+      case 2: k_order_cta<256, 3><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+      case 3: k_order_cta<128, 2><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+      default: k_order_warp<<<grid, th, 0, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
+    }
+    ++ctx->launches;
+  };
+  const bool aside = !(prof || serial_fit);
+  if (!aside) {
     static const int order[NUM_CLASSES] = {0, 4, 3, 2, 1, 5};   // stage slots: S, L3, L2, L1, M, X
     for (int q = 0; q < NUM_CLASSES; ++q) { launch_fit(order[q], s); STAGE_MARK(); }
+    if (ctx->order_mode) for (int q = 0; q < ORD_NUM_HEADS; ++q) launch_order(q, s);
   } else {
+    // side stream of every class, longest patches first: L3, L2, L1, M, S, X
+    static const int cls_of_side[NUM_SIDE] = {4, 3, 2, 1, 0, 5};
+    static const int order_of_side[NUM_SIDE] = {1, 2, 3, 4, -1, 0};   // the sort that follows the fit on that stream (M + S: behind M)
     CU_TRY(cudaEventRecord(ctx->ev_fork, s));
-    for (int q = 0; q < 5; ++q) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
-    // longest classes first
-    {
-    launch_fit(4, s);   // longest patches first
-    launch_fit(3, ctx->side[0]);
-    launch_fit(2, ctx->side[1]);
-    launch_fit(1, ctx->side[2]);
-    launch_fit(0, ctx->side[3]);
-    launch_fit(5, ctx->side[4]);
+    for (int q = 0; q < NUM_SIDE; ++q) {
+      CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0));
+      launch_fit(cls_of_side[q], ctx->side[q]);
+      CU_TRY(cudaEventRecord(ctx->ev_fit[q], ctx->side[q]));
     }
-    for (int q = 0; q < 5; ++q) { CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q])); CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0)); }
+    if (ctx->order_mode) {
+      for (int q = 0; q < NUM_SIDE; ++q) {
+        if (order_of_side[q] < 0) continue;
+        if (order_of_side[q] == 4) CU_TRY(cudaStreamWaitEvent(ctx->side[q], ctx->ev_fit[4], 0));   // the warp sort also covers class S (side 4)
+        launch_order(order_of_side[q], ctx->side[q]);
+        CU_TRY(cudaEventRecord(ctx->ev_join[q], ctx->side[q]));
+      }
+    }
+    for (int q = 0; q < NUM_SIDE; ++q) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_fit[q], 0));   // k_gle needs every fit, no sort
     stage += 6;
   }
 #undef FIT_ARGS
-  // reference emission order inside every fitted patch (pwpp_order.cuh): five launches (classes X, L3, L2, L1 with a CTA sized to the
-  // class, M + S one warp per patch). They only permute `part` inside a patch and k_gle only reads the patch records, so they run
-  // beside k_gle on the side streams and are joined before k_emit: on a one-frame call the sort of the largest patch (~50 us) and
-  // the ring walk of k_gle (~50 us) are both pure latency.
-  const bool order_aside = ctx->order_mode && !prof && !serial_fit;
-  if (ctx->order_mode) {
-    if (order_aside) CU_TRY(cudaEventRecord(ctx->ev_fork, s));
-    int* heads = ctx->d_wq_ctr.p + 2 * NUM_CLASSES;
-    for (int q = 0; q < ORD_NUM_HEADS; ++q) {
-      cudaStream_t so = order_aside ? ctx->side[q] : s;
-      if (order_aside) CU_TRY(cudaStreamWaitEvent(so, ctx->ev_fork, 0));
-      const int grid = (int) std::min<long long>(ctx->order_k[q].grid, std::max<long long>(1, (long long) nframes * (q == 4 ? 64 : 32)));
-      const int th = ctx->order_k[q].threads;
-      const size_t sm = ctx->order_k[q].smem;
-      switch (q) {
-        case 0: k_order_cta<512, 5><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
-        case 1: k_order_cta<512, 4><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
-        case 2: k_order_cta<256, 3><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
-        case 3: k_order_cta<128, 2><<<grid, th, sm, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
-        default: k_order_warp<<<grid, th, 0, so>>>(ctx->d_sorted.p, wq, heads + q, ctx->d_part.p); break;
-      }
-      ++ctx->launches;
-      if (order_aside) CU_TRY(cudaEventRecord(ctx->ev_join[q], so));
-    }
-  }
   int* d_ng = ctx->d_counts.p + f0;
   int* d_np = ctx->d_counts.p + ctx->num_streams + f0;
   int* d_nd = ctx->d_counts.p + 2 * ctx->num_streams + f0;
@@ -398,7 +402,7 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
     ++ctx->launches;
   }
   STAGE_MARK();
-  if (order_aside) for (int q = 0; q < ORD_NUM_HEADS; ++q) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+  if (aside && ctx->order_mode) for (int q = 0; q < NUM_SIDE; ++q) if (q != 4) CU_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
   if (max_chunks > 0) {
     const long long max_pts = (long long) max_chunks * CHUNK_PTS;   // upper bound of the largest frame of the range
     dim3 grid((unsigned) ((max_pts + (long long) EMIT_TILE * EMIT_WARPS - 1) / ((long long) EMIT_TILE * EMIT_WARPS)), nframes);
@@ -595,8 +599,9 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   for (int i = 0; i <= PWPP_NUM_STAGES; ++i) CU_TRY_CTX(cudaEventCreate(&ctx->stage_ev[i]));
   for (int i = 0; i < 2; ++i) CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->tab_ev[i], cudaEventDisableTiming));
   CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  for (int q = 0; q < 5; ++q) {
+  for (int q = 0; q < NUM_SIDE; ++q) {
     CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking));
+    CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_fit[q], cudaEventDisableTiming));
     CU_TRY_CTX(cudaEventCreateWithFlags(&ctx->ev_join[q], cudaEventDisableTiming));
   }
   CU_TRY_CTX(ctx->d_states.reserve(num_streams));
@@ -615,7 +620,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     // Fit kernel of every patch-size class (launch shapes from the r01 / r02 measurements, profiles/):
     //   S  <= 64      k_fit_resident: 8 lanes x 8 register slots per patch
     //   M  <= 512     k_fit_warp, patch staged in shared memory, plane + moment sums in shared memory, 3 CTAs/SM (r02: 0.72 -> 0.68 ms)
-    //   L1 <= 2048    k_fit_warp streaming from L2, the same  (0.83 -> 0.76 ms; 4 CTAs/SM at 64 registers: 0.81)  | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
+    //   L1 <= 2048    k_fit_warp streaming from L2, the same  (0.83 -> 0.76 ms; 4 CTAs/SM at 64 registers: 0.81; a cp.async chunk ring in shared memory for the passes: 0.77)  | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
     //   L2 <= 4096    k_fit_cta, plane in shared memory, 3/SM |                   4 / 8 / 16 warps
     //   L3 <= 8192    k_fit_cta, 2 CTAs/SM                    |
     //   X  >  8192    k_fit_big (dense sensors)
@@ -692,7 +697,7 @@ void pwpp_destroy(pwpp_ctx* ctx) {
   for (int i = 0; i < 2; ++i) if (ctx->gexec[i]) cudaGraphExecDestroy(ctx->gexec[i]);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int i = 0; i < 2; ++i) if (ctx->tab_ev[i]) cudaEventDestroy(ctx->tab_ev[i]);
-  for (int q = 0; q < 5; ++q) { if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
+  for (int q = 0; q < NUM_SIDE; ++q) { if (ctx->ev_fit[q]) cudaEventDestroy(ctx->ev_fit[q]); if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]); if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]); }
   ctx->d_states.release(); ctx->d_states_init.release(); ctx->d_hist.release(); ctx->d_in.release(); ctx->d_cm.release(); ctx->d_pt_off.release(); ctx->d_chunk_off.release();
   ctx->d_bin_ids.release(); ctx->d_chist.release(); ctx->d_cbase.release(); ctx->d_bin_off.release(); ctx->d_sorted.release();
   ctx->d_part.release(); ctx->d_labels.release(); ctx->d_fits.release(); ctx->d_segs.release(); ctx->d_wq_ctr.release();

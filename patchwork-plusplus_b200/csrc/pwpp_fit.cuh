@@ -815,18 +815,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
       int g_run = 0, ng_run = 0;
       for (int q = 0; q < w; ++q) { g_run += s_cnt[q][0]; ng_run += s_cnt[q][1]; }
       const unsigned lt = lanemask_lt();
-      for (int it = 0; it < nit; ++it) {
-        const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
-        const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
-        const unsigned bn = __ballot_sync(0xffffffffu, v && !isg);
-        if (v) {
-          const int idx = __float_as_int(P[jbase + it * 32].w);
-          if (isg) out[g_run + __popc(bg & lt)] = idx;
-          else out[n_ground + ng_run + __popc(bn & lt)] = idx;
-          if (wq.labels && (isg || ((amask >> it) & 1u))) wq.labels[start + jbase + it * 32] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
+      for (int it0 = 0; it0 < nit; it0 += 4) {   // four index loads in flight per thread (they come from L2: the r02 profile had 7-8 % of this kernel's stall samples on this load)
+        int idxb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int it = it0 + u; idxb[u] = (it < nit && ((vmask >> it) & 1u)) ? __float_as_int(P[jbase + it * 32].w) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int it = it0 + u;
+          if (it >= nit) break;
+          const bool v = (vmask >> it) & 1u, isg = (gmask >> it) & 1u;
+          const unsigned bg = __ballot_sync(0xffffffffu, v && isg);
+          const unsigned bn = __ballot_sync(0xffffffffu, v && !isg);
+          if (v) {
+            const int idx = idxb[u];
+            if (isg) out[g_run + __popc(bg & lt)] = idx;
+            else out[n_ground + ng_run + __popc(bn & lt)] = idx;
+            if (wq.labels && (isg || ((amask >> it) & 1u))) wq.labels[start + jbase + it * 32] = isg ? PW_LABEL_GROUND : PW_LABEL_REJECT;
+          }
+          g_run += __popc(bg);
+          ng_run += __popc(bn);
         }
-        g_run += __popc(bg);
-        ng_run += __popc(bn);
       }
       if (tid == 0) {
         BinFit& r = fits[(size_t) f * g.nbins + bin];
