@@ -118,7 +118,7 @@ struct pwpp_ctx {
   bool fast_bin = true;
   // kernel-variant switches, read from the environment when the context is created (see pwpp_create)
   int sw_front = 1, sw_patch = 0, small_call_frames = 0;
-  bool sw_serial_fit = false;
+  bool sw_serial_fit = false, front_dense_ok = false;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
   bool call_times_valid = false;
@@ -299,11 +299,20 @@ int launch_range_impl(pwpp_ctx* ctx, int f0, int nf, const float4* d_pts, int ha
   if (ctx->sw_front && !small_call) {
     // one thread-block cluster per frame: binning, scan and stable scatter in one kernel (pwpp_front.cuh)
     if (nframes > 0) {
-      const size_t sm_f = front_cluster_smem_bytes(nbp);
+      // 64 warps per frame for KITTI-sized frames, 128 for dense ones (pwpp_front.cuh)
+      const long long mean_front = (ctx->pt_off[f0 + nf] - ctx->pt_off[f0]) / std::max(nf, 1);
+      const bool dense = mean_front > 400000 && ctx->front_dense_ok;
+      const int nt = dense ? FC_THREADS_DENSE : FC_THREADS;
+      const size_t sm_f = front_cluster_smem_bytes(nbp, nt);
       dim3 grid(FC_CS, nframes);
 #define FC_ARGS d_pts, ft, states, ctx->g, ctx->ap, has_intensity, nbp, nb, ctx->d_bin_ids.p, bin_off, wq, fits, ctx->d_sorted.p
-      if (ctx->fast_bin) k_front_cluster<true, CLS_L2_MAX><<<grid, FC_THREADS, sm_f, s>>>(FC_ARGS);
-      else k_front_cluster<false, CLS_L2_MAX><<<grid, FC_THREADS, sm_f, s>>>(FC_ARGS);
+      if (dense) {
+        if (ctx->fast_bin) k_front_cluster<true, CLS_L2_MAX, FC_THREADS_DENSE><<<grid, nt, sm_f, s>>>(FC_ARGS);
+        else k_front_cluster<false, CLS_L2_MAX, FC_THREADS_DENSE><<<grid, nt, sm_f, s>>>(FC_ARGS);
+      } else {
+        if (ctx->fast_bin) k_front_cluster<true, CLS_L2_MAX, FC_THREADS><<<grid, nt, sm_f, s>>>(FC_ARGS);
+        else k_front_cluster<false, CLS_L2_MAX, FC_THREADS><<<grid, nt, sm_f, s>>>(FC_ARGS);
+      }
 #undef FC_ARGS
       ++ctx->launches;
     }
@@ -667,11 +676,16 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
   {
     const size_t scat = (size_t) (CHUNK_THREADS / 32) * ctx->nbp * sizeof(unsigned int);
     if (scat > 48 * 1024) CU_TRY_CTX(cudaFuncSetAttribute(k_scatter<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scat));
-    const size_t sm_f = front_cluster_smem_bytes(ctx->nbp);
+    const size_t sm_f = front_cluster_smem_bytes(ctx->nbp, FC_THREADS), sm_fd = front_cluster_smem_bytes(ctx->nbp, FC_THREADS_DENSE);
     if (sm_f > 220 * 1024) ctx->sw_front = 0;   // (thousands of bins: the per-warp count tables no longer fit next to the tiles)
+    ctx->front_dense_ok = sm_fd <= 220 * 1024;
     if (ctx->sw_front) {
-      CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<true, CLS_L2_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
-      CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<false, CLS_L2_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<true, CLS_L2_MAX, FC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
+      CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<false, CLS_L2_MAX, FC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_f));
+      if (ctx->front_dense_ok) {
+        CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<true, CLS_L2_MAX, FC_THREADS_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_fd));
+        CU_TRY_CTX(cudaFuncSetAttribute(k_front_cluster<false, CLS_L2_MAX, FC_THREADS_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_fd));
+      }
     }
   }
   *out = ctx;

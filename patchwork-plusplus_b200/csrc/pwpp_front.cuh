@@ -23,12 +23,15 @@
 namespace pwpp {
 
 constexpr int FC_CS = 8;                 // CTAs per cluster (portable maximum)
-constexpr int FC_THREADS = 256;
-constexpr int FC_WARPS = FC_THREADS / 32;
+// Threads per CTA are a template parameter: 256 (64 warps per frame, 4 CTAs per SM) for KITTI-sized frames, 512 (128 warps per frame,
+// 2 CTAs per SM) for dense frames whose slices are ten times longer. r02 (profiles/r02/ab14_front_shapes.log), 8 x 256 / 8 x 512 /
+// 4 x 512: 1.200 / 1.402 / 1.199 ms per 1024 KITTI frames, 0.668 / 0.472 / 0.677 ms per 32 dense frames.
+constexpr int FC_THREADS = 256, FC_THREADS_DENSE = 512;
 constexpr int FC_ROWS = 4;               // 32-point rows per chunk
 constexpr int FC_CHUNK = FC_ROWS * 32;   // points per TMA chunk of one warp: 2 KB, two buffers per warp in flight
 
-__host__ __device__ inline size_t front_cluster_smem_bytes(int nbp) {
+__host__ __device__ inline size_t front_cluster_smem_bytes(int nbp, int nthreads) {
+  const int FC_WARPS = nthreads / 32;
   // tiles [FC_WARPS][2][FC_CHUNK] float4 | per-warp counts, later bases [FC_WARPS][nbp] u32 | CTA histogram [nbp] u32 | scan [nbp + 1] i32 (padded to
   // 16 B) | mbarriers [FC_WARPS][2] u64 | class counters [3][NUM_CLASSES] i32
   return (size_t) FC_WARPS * 2 * FC_CHUNK * sizeof(float4) + (size_t) (FC_WARPS + 1) * nbp * sizeof(unsigned) + ((((size_t) nbp + 1) * sizeof(int) + 15) & ~(size_t) 15) +
@@ -41,14 +44,15 @@ __host__ __device__ inline size_t front_cluster_smem_bytes(int nbp) {
 // scan that row holds the warp's first free position of every bin, which pass 2 advances the same way. A point's position is
 // (points of the bin in lower slices) + (points of the bin earlier in this slice) + (lower lanes of the row with the same bin):
 // ascending point index inside a bin, as k_scatter produces.
-template <bool FAST, int L2MAX>
+template <bool FAST, int L2MAX, int NT>
 __global__ void
 #if !defined(PWPP_SIMT_EMU)
 __cluster_dims__(FC_CS, 1, 1)
 #endif
-__launch_bounds__(FC_THREADS, 4) k_front_cluster(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
+__launch_bounds__(NT, 1024 / NT) k_front_cluster(const float4* __restrict__ pts, FrameTable ft, const StreamState* __restrict__ states, Geometry g, AlgoParams ap,
                                                   int has_intensity, int nbp, int nbins, unsigned short* __restrict__ bin_ids, int* __restrict__ bin_off, WorkQueues wq,
                                                   BinFit* __restrict__ fits, float4* __restrict__ sorted) {
+  constexpr int FC_THREADS = NT, FC_WARPS = NT / 32;   // (shadow the namespace-scope defaults)
   PW_DYN_SHARED(unsigned char, s_raw);
   float4* s_tile = reinterpret_cast<float4*>(s_raw);                                              // [FC_WARPS][2][FC_CHUNK]
   unsigned* s_wb = reinterpret_cast<unsigned*>(s_raw + (size_t) FC_WARPS * 2 * FC_CHUNK * 16);    // [FC_WARPS][nbp] counts of a warp's slice, then its bases

@@ -334,11 +334,18 @@ void simt_estimate_multi(void* h, int nframes, const float* const* pts_in, const
   wq.head = ctr.data() + NUM_CLASSES;
   wq.labels = t->order ? labels.data() : nullptr;
   if (t->front) {   // one cluster per frame (pwpp_front.cuh): the CTAs of a cluster run concurrently, frames one after another
-    const size_t sm_f = front_cluster_smem_bytes(nbp);
+    // front=1: 8 x 256 threads (KITTI-sized frames), front=3: 8 x 512 (what dense frames get)
+    const int nt = t->front == 3 ? FC_THREADS_DENSE : FC_THREADS;
+    const size_t sm_f = front_cluster_smem_bytes(nbp, nt);
     for (int f = 0; f < nframes; ++f) {
 #define FC_ARGS d_pts, ft, states, g, ap, has_intensity, nbp, nb, bin_ids.data(), bin_off.data(), wq, fits.data(), sorted.data()
-      if (t->fast) simt::launch_concurrent("k_front_cluster<fast>", FC_CS, FC_THREADS, sm_f, [&] { k_front_cluster<true, CLS_L2_MAX>(FC_ARGS); }, (unsigned) f);
-      else simt::launch_concurrent("k_front_cluster<exact>", FC_CS, FC_THREADS, sm_f, [&] { k_front_cluster<false, CLS_L2_MAX>(FC_ARGS); }, (unsigned) f);
+      if (nt == FC_THREADS_DENSE) {
+        if (t->fast) simt::launch_concurrent("k_front_cluster<fast,512>", FC_CS, nt, sm_f, [&] { k_front_cluster<true, CLS_L2_MAX, FC_THREADS_DENSE>(FC_ARGS); }, (unsigned) f);
+        else simt::launch_concurrent("k_front_cluster<exact,512>", FC_CS, nt, sm_f, [&] { k_front_cluster<false, CLS_L2_MAX, FC_THREADS_DENSE>(FC_ARGS); }, (unsigned) f);
+      } else {
+        if (t->fast) simt::launch_concurrent("k_front_cluster<fast>", FC_CS, nt, sm_f, [&] { k_front_cluster<true, CLS_L2_MAX, FC_THREADS>(FC_ARGS); }, (unsigned) f);
+        else simt::launch_concurrent("k_front_cluster<exact>", FC_CS, nt, sm_f, [&] { k_front_cluster<false, CLS_L2_MAX, FC_THREADS>(FC_ARGS); }, (unsigned) f);
+      }
 #undef FC_ARGS
     }
   } else {

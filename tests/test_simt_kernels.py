@@ -88,8 +88,8 @@ def test_cluster_front_end_is_identical(kitti):
     frames = [kitti[1], np.zeros((0, 4), np.float32), synth.make_frame(5, 1).numpy(), np.array([[5, 0, -1.7, 0.5]], np.float32), kitti[2][:50000],
               synth.make_frame(5, 2).numpy()[:4096], kitti[3][:2049]]
     a = SimtTwin(num_streams=len(frames), front=0); a.estimate_multi(frames)
-    for seed in (0, 7, 8):
-        b = SimtTwin(num_streams=len(frames), front=1)
+    for seed, mode in ((0, 1), (7, 1), (8, 3)):   # front=3: the 8 x 512-thread shape dense frames get
+        b = SimtTwin(num_streams=len(frames), front=mode)
         b.set_sched_seed(seed)
         try:
             b.estimate_multi(frames)
