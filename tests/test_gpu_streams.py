@@ -179,3 +179,26 @@ def test_pybind_device_tensors(kitti):
         gd2 = torch.as_tensor(pw4.getGroundIndicesDevice(), device="cuda").clone()
     s.synchronize()
     assert np.array_equal(gd2.cpu().numpy(), g_ref)
+
+
+def test_small_call_path_matches_the_batch_path(kitti, monkeypatch):
+    """Calls of at most PWPP_SMALL_CALL frames take other kernels than batches (one CTA per patch above 512 points, the stand-alone
+    front-end kernels): the same two scans through both paths give identical bin ids and index lists, patch planes within the
+    GPU-vs-oracle tolerance, the same adaptive state; pwpp_call_times_us reports the device-side split of the one-chunk call."""
+    frames = [kitti[0], kitti[4]]
+    a = _engine(num_streams=2)                     # default: 2 frames <= 4 -> small-call kernels
+    a.estimate_host(frames)
+    ct = a.call_times_us()
+    assert ct["device_total"] > 0 and abs(ct["h2d"] + ct["kernels"] + ct["d2h"] - ct["device_total"]) < 0.05 * ct["device_total"] + 5.0
+    monkeypatch.setenv("PWPP_SMALL_CALL", "0")     # read when a context is created
+    b = _engine(num_streams=2)
+    b.estimate_host(frames)
+    rec = np.dtype([("d", np.float64, 10), ("n", np.int32), ("ng", np.int32), ("verdict", np.int32), ("fitted", np.int32)])
+    for f in range(2):
+        assert np.array_equal(a.bin_ids(f), b.bin_ids(f))
+        assert np.array_equal(a.ground_indices(f), b.ground_indices(f)) and np.array_equal(a.nonground_indices(f), b.nonground_indices(f))
+        ra, rb = np.frombuffer(a.bin_results(f), rec), np.frombuffer(b.bin_results(f), rec)
+        assert np.array_equal(ra["n"], rb["n"]) and np.array_equal(ra["ng"], rb["ng"]) and np.array_equal(ra["verdict"], rb["verdict"])
+        fit = (ra["fitted"] != 0) & (ra["n"] >= 3)
+        assert np.abs(ra["d"][fit][:, :6] - rb["d"][fit][:, :6]).max() <= 2e-9      # mean, normal
+        assert abs(a.height(f) - b.height(f)) <= 1e-9
