@@ -628,7 +628,7 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
     // Fit kernel of every patch-size class (launch shapes from the r01 / r02 measurements, profiles/):
     //   S  <= 64      k_fit_resident: 8 lanes x 8 register slots per patch
-    //   M  <= 512     k_fit_warp, patch staged in shared memory, plane + moment sums in shared memory, 3 CTAs/SM (r02: 0.72 -> 0.68 ms)
+    //   M  <= 512     k_fit_warp, patch staged in shared memory, plane + moment sums in shared memory, 3 CTAs/SM (r02: 0.72 -> 0.68 ms; four instead of two rows per batch of the passes: 0.69 -> 0.76 ms)
     //   L1 <= 2048    k_fit_warp streaming from L2, the same  (0.83 -> 0.76 ms; 4 CTAs/SM at 64 registers: 0.81; a cp.async chunk ring in shared memory for the passes: 0.77)  | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
     //   L2 <= 4096    k_fit_cta, plane in shared memory, 3/SM |                   4 / 8 / 16 warps
     //   L3 <= 8192    k_fit_cta, 2 CTAs/SM                    |

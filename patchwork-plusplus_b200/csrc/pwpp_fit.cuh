@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fit_cta(const float4* __restr
     const int nit = chunk >> 5;                      // slots per thread actually used (<= ITERS)
     const int jbase = w * chunk + lane;
     unsigned vmask = 0;
-#pragma unroll 4
+#pragma unroll 4   // (eight staging loads in flight for the L3 kernel: no difference, r02 ab17)
     for (int it = 0; it < nit; ++it) {
       const int j = jbase + it * 32;
       if (j < n) { const float4 p = P[j]; sx[j] = p.x; sy[j] = p.y; sz[j] = p.z; vmask |= 1u << it; }
