@@ -27,7 +27,7 @@
  *       Jacobi SVD in double, point-plane distance in double. This is the arithmetic the CUDA path
  *       implements (it cannot reproduce a sequential fp32 sum order in parallel; an order-free
  *       definition makes ground/non-ground index SETS comparable bit-exactly). The two modes are
- *       compared in tests/test_oracle_modes.py (identical index sets on all fixtures; plane
+ *       compared in tests/test_oracle_golden.py (identical index sets on all fixtures; plane
  *       parameters within fp32 noise).
  *
  * Defined behaviour where the reference has none:

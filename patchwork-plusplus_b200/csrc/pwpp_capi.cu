@@ -105,6 +105,12 @@ struct FitLaunch {
   size_t smem = 0;
 };
 
+#ifndef PWPP_M_U
+#define PWPP_M_U 2
+#endif
+#ifndef PWPP_L1_U
+#define PWPP_L1_U FITW_U
+#endif
 constexpr int NUM_SIDE = 6;
 
 struct pwpp_ctx {
@@ -635,8 +641,8 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     //   X  >  8192    k_fit_big (dense sensors)
     const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
     ctx->fit[0] = {k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
-    ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
-    ctx->fit[2] = {k_fit_warp<false, 2, 2, FITW_U, 3, false, true>, 0, FITW_WARPS * 32, 0};
+    ctx->fit[1] = {k_fit_warp<true, 1, 1, PWPP_M_U, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
+    ctx->fit[2] = {k_fit_warp<false, 2, 2, PWPP_L1_U, 3, false, true>, 0, FITW_WARPS * 32, 0};
     ctx->fit[3] = {k_fit_cta<4096, 3, 3, 8, true, true>, 0, FIT_THREADS, sm_l2};
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
     ctx->fit[5] = {k_fit_big<16, 1, true>, 0, 512, 0};

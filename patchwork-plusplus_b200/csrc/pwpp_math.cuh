@@ -1,6 +1,6 @@
 // pwpp_math.cuh — scalar math of the ground-segmentation path, shared by every kernel.
 //
-// Everything here is __host__ __device__ so that tests/host_math_test.cu can run the exact same
+// Everything here is __host__ __device__ so that tests/host_twin.cu (tests/test_host_twin.py) can run the exact same
 // code on the CPU (nvcc host pass) against the oracle before it ever runs on a GPU.
 //
 // Arithmetic contract ("CANON64"): the reference's formulas
