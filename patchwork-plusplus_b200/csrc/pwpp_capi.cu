@@ -105,12 +105,6 @@ struct FitLaunch {
   size_t smem = 0;
 };
 
-#ifndef PWPP_M_U
-#define PWPP_M_U 2
-#endif
-#ifndef PWPP_L1_U
-#define PWPP_L1_U FITW_U
-#endif
 constexpr int NUM_SIDE = 6;
 
 struct pwpp_ctx {
@@ -634,15 +628,19 @@ int pwpp_create(const pwpp_params* params, int device, int num_streams, int64_t 
     CU_TRY_CTX(cudaGetDeviceProperties(&prop, device));
     // Fit kernel of every patch-size class (launch shapes from the r01 / r02 measurements, profiles/):
     //   S  <= 64      k_fit_resident: 8 lanes x 8 register slots per patch
-    //   M  <= 512     k_fit_warp, patch staged in shared memory, plane + moment sums in shared memory, 3 CTAs/SM (r02: 0.72 -> 0.68 ms; four instead of two rows per batch of the passes: 0.69 -> 0.76 ms)
-    //   L1 <= 2048    k_fit_warp streaming from L2, the same  (0.83 -> 0.76 ms; 4 CTAs/SM at 64 registers: 0.81; a cp.async chunk ring in shared memory for the passes: 0.77)  | PWPP_FIT_PATCH=1: k_fit_patch (one patch per CTA held in registers)
-    //   L2 <= 4096    k_fit_cta, plane in shared memory, 3/SM |                   4 / 8 / 16 warps
-    //   L3 <= 8192    k_fit_cta, 2 CTAs/SM                    |
+    //   M  <= 512     k_fit_warp, patch staged in shared memory, plane + moment sums in shared memory, 3 CTAs/SM (r02: 0.72 -> 0.68 ms)
+    //   L1 <= 2048    k_fit_warp streaming from L2, the same  (0.83 -> 0.76 ms; 4 CTAs/SM at 64 registers: 0.81; a cp.async chunk ring: 0.77)
+    //                 Both are instruction-fetch sensitive (125 KB of code each): the passes take TWO rows per batch, the LPR scans two
+    //                 loads in flight — r02 ab17-19: rows per batch 1 / 2 / 4 / 8: L1 0.63 / 0.60 / 0.74 / 1.06 ms, M 0.69 / 0.69 / 0.76;
+    //                 LPR scans 8 / 4 / 2 in flight: M 0.69 / 0.64 / 0.63, L1 0.60 / 0.58 / 0.57 ms.
+    //                 PWPP_FIT_PATCH=1 (and calls of <= 4 frames): k_fit_patch, one patch per CTA of 4 / 8 / 16 warps held in registers
+    //   L2 <= 4096    k_fit_cta, plane in shared memory, 3 CTAs/SM
+    //   L3 <= 8192    k_fit_cta, 2 CTAs/SM
     //   X  >  8192    k_fit_big (dense sensors)
     const size_t sm_m = FITW_WARPS * CLS_M_MAX * sizeof(float4), sm_l2 = 3 * 4096 * sizeof(float), sm_l3 = 3 * 8192 * sizeof(float);
     ctx->fit[0] = {k_fit_resident<8, 8, 0, 2>, 0, FIT_THREADS, 0};
-    ctx->fit[1] = {k_fit_warp<true, 1, 1, PWPP_M_U, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
-    ctx->fit[2] = {k_fit_warp<false, 2, 2, PWPP_L1_U, 3, false, true>, 0, FITW_WARPS * 32, 0};
+    ctx->fit[1] = {k_fit_warp<true, 1, 1, 2, 3, false, true>, 0, FITW_WARPS * 32, sm_m};
+    ctx->fit[2] = {k_fit_warp<false, 2, 2, 2, 3, false, true>, 0, FITW_WARPS * 32, 0};
     ctx->fit[3] = {k_fit_cta<4096, 3, 3, 8, true, true>, 0, FIT_THREADS, sm_l2};
     ctx->fit[4] = {k_fit_cta<8192, 4, 2, 8, true>, 0, FIT_THREADS, sm_l3};
     ctx->fit[5] = {k_fit_big<16, 1, true>, 0, 512, 0};

@@ -980,9 +980,10 @@ __device__ double warp_lpr(const float4* __restrict__ P, int n, int nit, bool an
   bool fallback = num_lpr > 32;
   double lpr = 0.0;
   if (!fallback) {
-    // (both scans: LPR_U loads in flight per lane — for class L1 the patch streams from L2 and these two loops were the kernel's
-    // top long-scoreboard sites in the r02 profile, one dependent round trip per 32 points)
-    constexpr int LPR_U = 8;
+    // (both scans: LPR_U loads in flight per lane. For class L1 the patch streams from L2 and these two loops were the kernel's top
+    // long-scoreboard sites in the r02 profile with one load per iteration; eight in flight cost more in code size than they hid —
+    // the warp kernels stall on instruction fetch — r02 ab19: 8 / 4 / 2 in flight: M 0.69 / 0.64 / 0.63 ms, L1 0.60 / 0.58 / 0.57 ms)
+    constexpr int LPR_U = 2;
     unsigned kminL = 0xffffffffu;
     int nv = 0;
     for (int it0 = 0; it0 < nit; it0 += LPR_U) {

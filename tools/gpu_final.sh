@@ -5,6 +5,7 @@
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 bash tools/gpu_check.sh 2>&1 | tee gpurun_out/check.log
+[ -n "$SKIP_DENSE_FULL" ] && sed -i 's/^timeout 420 ncu --set full --clock-control none --import-source on -k regex:k_ -s \$SKIPD.*$/echo skip-dense-full/' tools/gpu_profile.sh
 bash tools/gpu_profile.sh 2>&1 | tee gpurun_out/profile.log | tail -40
 cat > /tmp/one_frame.py <<'PY'
 import os, sys
