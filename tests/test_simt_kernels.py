@@ -261,3 +261,65 @@ def test_mutated_inputs(kitti, seed):
     illcond[np.unique(ids[mo != mr])] = True
     keep = ~illcond[ids]
     assert np.array_equal(mo[keep], mt[keep]), f"{opts}: {int((mo[keep] != mt[keep]).sum())} labels differ in well-conditioned patches"
+
+
+def test_history_bound_drops_the_oldest_samples():
+    """The defined deviation of include/pwpp.h: while ring 0 holds <= 1 flatness samples the reference never trims the flatness
+    histories of rings 1..3 (the `break` of S:363-364) and they grow without bound; the kernels keep the NEWEST hist_cap =
+    max(max_*_storage) + 4 * (max sectors) + 64 samples. A stream whose scans leave ring 0 empty for 25 frames: until the bound
+    is reached everything equals the oracle; past it the labels and the thresholds still do (the thresholds are frozen while the
+    break holds), the ring-1 history is the oracle's newest hist_cap samples; when ring 0 finally gets its samples the flatness
+    threshold of ring 1 is mean + stdev over exactly those samples (the reference would average over its whole history)."""
+    from pwpp_ctypes import default_params
+    def mk():
+        p = default_params()
+        p.max_flatness_storage = 40; p.max_elevation_storage = 40
+        return p
+    hcap = 40 + 4 * 54 + 64
+    rng = np.random.default_rng(11)
+
+    def ring_points(r0, r1, nsec, per_sector):
+        ang = (np.arange(nsec * per_sector) // per_sector + rng.random(nsec * per_sector) * 0.9 + 0.05) * (2 * np.pi / nsec)
+        rad = r0 + rng.random(len(ang)) * (r1 - r0)
+        return np.c_[rad * np.cos(ang), rad * np.sin(ang), -1.723 + rng.normal(0, 0.01, len(ang)), rng.random(len(ang))].astype(np.float32)
+
+    orc, tw = O.Oracle(mk(), O.ARITH_CANON64), SimtTwin(mk())
+    nblocked = 25
+    for f in range(nblocked):   # ring 1 of zone 0 (7.6 .. 12.3 m) and ring 0 of zone 1 only: ring 0 of zone 0 stays empty
+        a = np.r_[ring_points(7.7, 12.2, 16, 24), ring_points(12.5, 14.6, 32, 16)]
+        orc.estimate(a); tw.estimate(a)
+        assert _check_labels_only(orc, tw, a, f"blocked/{f}")
+        so, st = orc.state(), tw.state()
+        assert so.n_flatness[0] == 0 and st.n_flatness[0] == 0
+        assert st.n_flatness[1] == min(so.n_flatness[1], hcap) and st.n_flatness[2] == min(so.n_flatness[2], hcap)
+        for r in (1, 2):
+            ho, ht = orc.history(r, 1), tw.history(r, 1)
+            assert np.allclose(ht, ho[-len(ht):], rtol=1e-6, atol=1e-9), f"ring {r}: not the newest samples"
+        assert list(so.flatness_thr) == list(st.flatness_thr)   # frozen while the break holds
+    assert orc.state().n_flatness[1] > hcap   # the scenario did pass the bound
+    held = tw.history(1, 1).copy()                      # what the bounded row holds: the oracle's newest hist_cap samples (asserted above)
+    assert len(held) == hcap
+    a = np.r_[ring_points(3.0, 7.4, 16, 24), ring_points(7.7, 12.2, 16, 24)]   # ring 0 gets 16 patches: > 1 samples, the break is gone
+    orc.estimate(a); tw.estimate(a)
+    so, st = orc.state(), tw.state()
+    assert st.n_flatness[0] > 1 and st.n_flatness[1] == 40 and so.n_flatness[1] == 40     # every ring updated and trimmed (S:372-373)
+    assert np.allclose(tw.history(1, 1), orc.history(1, 1), rtol=1e-6, atol=1e-9)        # the newest 40 agree again
+    # the threshold of ring 1 was computed over the newest hist_cap of (held samples + this frame's k new ones), k = 0..16 unknown here
+    post = orc.history(1, 1)
+    def thr(v):   # calc_mean_stdev + S:368 in the same sequential arithmetic
+        m = 0.0
+        for x in v: m += x
+        m /= len(v)
+        q = 0.0
+        for x in v: q += (x - m) * (x - m)
+        return m + (q / (len(v) - 1)) ** 0.5
+    cands = [thr(list(np.r_[held, post[len(post) - k:]][-hcap:])) for k in range(0, 17)]
+    assert min(abs(st.flatness_thr[1] - c) for c in cands) <= 1e-12 * max(1.0, abs(st.flatness_thr[1])), (st.flatness_thr[1], cands[:3])
+    # ... and it is NOT what the unbounded reference history gives (the documented deviation), while ring 0 — never bounded — agrees
+    assert abs(st.flatness_thr[1] - so.flatness_thr[1]) > 0 and abs(st.flatness_thr[0] - so.flatness_thr[0]) <= 1e-9
+
+
+def _check_labels_only(orc, tw, a, what):
+    assert np.array_equal(orc.bin_ids(), tw.bin_ids()), f"{what}: polar bin ids differ"
+    assert_sets_equal(orc.getGroundIndices(), orc.getNongroundIndices(), tw.getGroundIndices(), tw.getNongroundIndices(), len(a), what)
+    return True
