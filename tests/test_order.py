@@ -56,3 +56,18 @@ def test_other_parameter_set_and_synthetic_and_ties():
 def conftest_kitti(f):
     import conftest
     return conftest.load_kitti(f)
+
+
+def test_sort_kernels_at_their_size_limits():
+    """Patches whose sizes sit on the limits of the sort kernels (k_order_warp: 16-key lanes, 512-key warps; k_order_cta<128/256/512>:
+    2048 / 4096 / 8192 keys) and of their padding (powers of two +- 1): one flat patch per frame, all frames in one batched call."""
+    rng = np.random.default_rng(5)
+    sizes = [10, 15, 16, 17, 31, 33, 63, 64, 65, 127, 129, 255, 256, 257, 511, 512, 513, 1023, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 8191, 8192]
+    frames = [np.c_[5 + rng.random(n) * 0.5, rng.random(n) * 0.5, -1.7 + rng.normal(0, 0.03, n), rng.random(n)].astype(np.float32) for n in sizes]
+    tw = SimtTwin(num_streams=len(frames), order=1)
+    tw.estimate_multi(frames)
+    for f, (n, a) in enumerate(zip(sizes, frames)):
+        ref = O.Reference(stable_sort=True)
+        ref.estimate(a)
+        tw.select(f)
+        _lists_equal(ref, tw, f"size {n}")

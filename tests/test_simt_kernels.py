@@ -323,3 +323,18 @@ def _check_labels_only(orc, tw, a, what):
     assert np.array_equal(orc.bin_ids(), tw.bin_ids()), f"{what}: polar bin ids differ"
     assert_sets_equal(orc.getGroundIndices(), orc.getNongroundIndices(), tw.getGroundIndices(), tw.getNongroundIndices(), len(a), what)
     return True
+
+
+def test_emit_tile_boundaries(kitti):
+    """k_emit cuts a frame's bin-sorted order into 1024-position tiles per warp (8192 per CTA): frame sizes on and around those
+    limits, in one batched call (the grid is sized for the largest frame: the others end inside it)."""
+    sizes = [1, 1023, 1024, 1025, 2049, 8191, 8192, 8193, 16385, 40000]
+    frames = [np.ascontiguousarray(kitti[(i % 3)][i * 7:i * 7 + 2 * n:2][:n]) for i, n in enumerate(sizes)]
+    tw = SimtTwin(num_streams=len(frames))
+    tw.estimate_multi(frames)
+    for f, a in enumerate(frames):
+        orc = O.Oracle(arith=O.ARITH_CANON64)
+        orc.estimate(a)
+        tw.select(f)
+        assert len(a) == sizes[f]
+        _check(orc, tw, a, f"emit tiles / {sizes[f]} points", allow_degenerate=True)
