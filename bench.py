@@ -11,10 +11,15 @@ over that batch. Frames shard across GPUs by global frame index with no data-pat
 value   : frames/s with the batch resident in HBM when the timed region starts (CUDA events, max over ranks)
 e2e     : the same metric through the C-ABI host entry point with page-locked HOST buffers: host->device copy of the
           batch and device->host read of all index lists inside the timed region
-roofline: of the slowest kernel of the step; algorithmic bytes = 20 B/point (16 B cloud read + 4 B index write,
-          SURVEY.md §8d) x points per launch / that kernel's mean CUDA-event time in the timed region
+roofline: per kernel, 20 B/point (16 B cloud read + 4 B index write) x the points that kernel's own work queue holds /
+          its mean CUDA-event time (roofline.per_kernel; the top-level fields are the slowest kernel's); whole_path_frac = 20 B x
+          all points / step time is the primary figure
 cpu_baseline / --impl reference: the reference's patchworkpp.cpp (compiled against oracle/eigen_shim into
           oracle/_ref/libpwref.so, unmodified control flow) on all host cores, one instance per frame.
+extra records (skipped with --no-extras): streaming (S streams x T consecutive frames, state carried), dense1m (BASELINE config 5
+          shape), reference_order (the timed batch with the reference's emission order inside a patch), kitti_scans (the six recorded
+          scans of tests/golden/ cycled to the batch size), latency_us (config 2: one frame per call through the drop-in C++ class),
+          parity_vs_reference (labels of the timed result against the reference's own code on the same arrays).
 """
 import argparse
 import json
