@@ -3,7 +3,7 @@
 # cycles of one plane solve (tools/solve_bench.cu). Every leg under its own timeout; results in gpurun_out/ab2.log.
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
-for cfg in ${AB_CFGS:-"PWPP_FRONT_BIDS=0" "PWPP_FRONT_BIDS=1"}; do
+for cfg in ${AB_CFGS:-"PWPP_X=0" "PWPP_FRONT=0" "PWPP_FIT_PATCH=1"}; do
   env $cfg timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ab.json 2> gpurun_out/ab.err
   python - "$cfg" <<'PY'
 import json, sys
@@ -14,7 +14,7 @@ except Exception as e:
     print(sys.argv[1], "ERR", e, open("gpurun_out/ab.err").read()[-1500:])
 PY
 done
-for cfg in ${LAT_CFGS:-"PWPP_X=0" "PWPP_FRONT=0" "PWPP_FIT_PATCH=1" "PWPP_FRONT_BIDS=1"}; do
+for cfg in ${LAT_CFGS:-"PWPP_X=0" "PWPP_SMALL_CALL=0" "PWPP_GRAPH=0"}; do
   echo "--- latency probe under $cfg"
   env $cfg timeout 120 python tools/gpu_latency_probe.py 2>&1 | tail -3
 done
