@@ -286,6 +286,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     # one process per GPU: pin this process (and the page-locked buffers it allocates from here on) to the GPU's NUMA node
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_node = pwpp_b200.bind_host_to_device(local)
     dist = pwpp_dist.Dist(backend="nccl")   # rendezvous + barriers + max-over-ranks only; no data-path collective
     barrier = dist.barrier
@@ -587,6 +588,11 @@ def run_ours(args):
         T = os.cpu_count() or 1
         nsample = min(F, max(T * 4, 64))
         frames = [pts[int(offs_np[f]):int(offs_np[f + 1])].cpu().numpy() for f in range(nsample)]
+        if full_affinity is not None:   # the GPU legs pinned this process to the GPU's NUMA node: the reference gets every host core back
+            try:
+                os.sched_setaffinity(0, full_affinity)
+            except OSError:
+                pass
         cpu, _, _ = cpu_reference_throughput(frames, args.cpu_seconds, cycle=True)
         if not args.no_extras:
             # labels of the timed result against the reference's own code on the same arrays (first 64 frames of the batch)
