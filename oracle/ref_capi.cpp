@@ -16,9 +16,7 @@
 #include <cstdint>
 #include <cstring>
 #include <iostream>
-#include <mutex>
 #include <numeric>
-#include <sstream>
 #include <vector>
 #include <time.h>
 
@@ -80,17 +78,17 @@ patchwork::Params to_params(const pwpp_params* p) {
 
 extern "C" {
 
+// The reference constructor prints an unconditional banner (patchworkpp.h:149). This library is the only user of std::cout in
+// the processes that load it (tests, bench.py), so the stream is switched off once when the library is loaded: insertions into
+// a stream whose failbit is set do nothing, and no constructor has to be serialised behind a lock (bench.py creates one
+// instance per frame from every host thread: a lock around the ~90 us constructor would cap the reference arm's parallelism).
+namespace {
+struct SilenceCout { SilenceCout() { std::cout.setstate(std::ios_base::failbit); } } g_silence_cout;
+}
+
 void* pwref_create(const pwpp_params* p) {
-  // the reference constructor prints an unconditional banner (patchworkpp.h:149); silence it. bench.py creates
-  // instances from many threads: redirecting std::cout is not thread-safe, so construction is serialised.
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  std::streambuf* old = std::cout.rdbuf();
-  std::ostringstream sink;
-  std::cout.rdbuf(sink.rdbuf());
   RefHandle* h = new RefHandle;
   h->obj = new patchwork::PatchWorkpp(to_params(p));
-  std::cout.rdbuf(old);
   return h;
 }
 void pwref_destroy(void* hv) {
