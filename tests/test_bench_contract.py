@@ -39,3 +39,26 @@ def test_product_arm_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=REPO)
     assert out.returncode != 0
     assert "no CUDA device" in (out.stderr + out.stdout) and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_front_end_stage_slots_are_merged_only_for_the_cluster_kernel():
+    """The cluster front end is one launch reported in the first of the three front-end stage slots: bench.py names it k_front and
+    computes no per-kernel figure for the two empty slots; the three stand-alone kernels (PWPP_FRONT=0) keep their own names."""
+    sys.path.insert(0, REPO)
+    import importlib
+    bench = importlib.import_module("bench")
+    cluster = {"k_bin_hist": 1.2, "k_bin_scan": 0.003, "k_scatter": 0.003, "k_fit_S": 0.24, "k_emit": 0.24}
+    m = bench.merge_front_stages(cluster)
+    assert list(m)[0] == "k_front" and abs(m["k_front"] - 1.206) < 1e-9 and "k_bin_scan" not in m and m["k_fit_S"] == 0.24
+    standalone = {"k_bin_hist": 0.66, "k_bin_scan": 0.05, "k_scatter": 0.83, "k_fit_S": 0.24}
+    assert bench.merge_front_stages(standalone) == standalone
+    # the committed bench line of the round carries what the driver and the judge read
+    line = os.path.join(REPO, "profiles", "r02", "bench_n1.json")
+    if os.path.exists(line):
+        j = json.load(open(line))
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                    "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+            assert key in j, key
+        r = j["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is not None and "k_front" in r["per_kernel"]
+        assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0 and j["gpu_launches"] > 0
